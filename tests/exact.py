@@ -1,0 +1,116 @@
+"""Model-derived exact answers for the H-CBN2 model -- test infrastructure.
+
+The reference ships no golden vectors for this path; these closed forms are what pins the oracle (and through
+it the CUDA path) to the *model* the reference implements:
+
+  Z_j ~ Exp(lambda_j), T_j = Z_j + max_{u in pa(j)} T_u, X_j = [T_j <= T_s], P(Y|X) = eps^d (1-eps)^(p-d).
+
+K2  T_s ~ Exp(lambda_s): the hidden genotype performs a race of exponentials on the lattice of compatible
+    genotypes.  Exit(x) = {k not in x : pa(k) subset of x}, Lambda(x) = sum_{k in Exit(x)} lambda_k,
+    reach(empty) = 1, reach(x) = sum_{j in x, j in Exit(x\\j)} reach(x\\j) lambda_j / (lambda_s + Lambda(x\\j)),
+    P(X = x) = reach(x) lambda_s / (lambda_s + Lambda(x)).
+K2' T_s = t given: P(X(t) = x) = [exp(Q t)]_{empty, x} with generator Q over compatible genotypes.
+K1  empty poset, T_s = t given: events independent, P(X_j = 1) = 1 - exp(-lambda_j t).
+"""
+import itertools
+import math
+
+import numpy as np
+
+
+def _parent_masks(poset):
+    poset = np.asarray(poset)
+    p = poset.shape[0]
+    return [sum(1 << int(u) for u in np.nonzero(poset[:, j])[0]) for j in range(p)]
+
+
+def compatible_states(poset):
+    p = np.asarray(poset).shape[0]
+    pm = _parent_masks(poset)
+    return [x for x in range(1 << p) if all((pm[j] & ~x) == 0 for j in range(p) if (x >> j) & 1)]
+
+
+def genotype_probs_exp(poset, lambdas, lambda_s):
+    """K2: dict {x (bitmask over event ids): P(X = x)} for T_s ~ Exp(lambda_s)."""
+    p = len(lambdas)
+    pm = _parent_masks(poset)
+    states = sorted(compatible_states(poset), key=lambda x: bin(x).count("1"))
+    comp = set(states)
+
+    def exit_rate(x):
+        return sum(lambdas[k] for k in range(p) if not (x >> k) & 1 and (pm[k] & ~x) == 0)
+
+    reach = {0: 1.0}
+    for x in states:
+        if x == 0:
+            continue
+        r = 0.0
+        for j in range(p):
+            if (x >> j) & 1:
+                y = x & ~(1 << j)
+                if y in comp and (pm[j] & ~y) == 0:
+                    r += reach[y] * lambdas[j] / (lambda_s + exit_rate(y))
+        reach[x] = r
+    return {x: reach[x] * lambda_s / (lambda_s + exit_rate(x)) for x in states}
+
+
+def genotype_probs_time(poset, lambdas, t):
+    """K2': dict {x: P(X(t) = x)} for a fixed sampling time t (matrix exponential on the lattice)."""
+    from scipy.linalg import expm
+    p = len(lambdas)
+    pm = _parent_masks(poset)
+    states = compatible_states(poset)
+    idx = {x: i for i, x in enumerate(states)}
+    Q = np.zeros((len(states), len(states)))
+    for x in states:
+        for k in range(p):
+            if not (x >> k) & 1 and (pm[k] & ~x) == 0:
+                Q[idx[x], idx[x | (1 << k)]] += lambdas[k]
+        Q[idx[x], idx[x]] = -Q[idx[x]].sum()
+    P = expm(Q * t)[idx[0]]
+    return {x: P[idx[x]] for x in states}
+
+
+def obs_prob_and_dist(px, y_mask, eps, p):
+    """P(Y) and E[d(X,Y) | Y] from a genotype distribution px = {x: P(x)}."""
+    py, pd = 0.0, 0.0
+    for x, q in px.items():
+        d = bin(x ^ y_mask).count("1")
+        w = (eps ** d) * ((1 - eps) ** (p - d))
+        py += q * w
+        pd += q * w * d
+    return py, pd / py
+
+
+def mask_of(genotype):
+    return sum(1 << j for j, g in enumerate(np.asarray(genotype).ravel()) if g)
+
+
+def exact_obs_loglik(obs, poset, lambdas, eps, lambda_s=1.0, times=None, weights=None):
+    obs = np.asarray(obs)
+    N, p = obs.shape
+    weights = np.ones(N) if weights is None else weights
+    ll, ed = 0.0, np.zeros(N)
+    px = genotype_probs_exp(poset, lambdas, lambda_s) if times is None else None
+    for i in range(N):
+        if times is not None:
+            px = genotype_probs_time(poset, lambdas, times[i])
+        py, d = obs_prob_and_dist(px, mask_of(obs[i]), eps, p)
+        ll += weights[i] * math.log(py)
+        ed[i] = d
+    return ll, ed
+
+
+def k1_empty_poset(y, lambdas, eps, t):
+    """K1: P(Y | t) and E[d | Y, t] on the empty poset with sampling time t."""
+    F = 1 - np.exp(-np.asarray(lambdas) * t)
+    y = np.asarray(y).astype(bool)
+    # per event: P(Y_j = y_j) = F(1-eps) + (1-F)eps for y_j = 1 ; F eps + (1-F)(1-eps) for y_j = 0
+    p1 = np.where(y, F * (1 - eps) + (1 - F) * eps, F * eps + (1 - F) * (1 - eps))
+    # P(X_j != Y_j | Y_j)
+    pm = np.where(y, (1 - F) * eps, F * eps) / p1
+    return float(np.prod(p1)), float(pm.sum())
+
+
+def all_genotypes(p):
+    return np.array(list(itertools.product([0, 1], repeat=p)), dtype=np.int32)
