@@ -1,0 +1,210 @@
+/* mccbn_b200.h -- C ABI of libmccbn_b200.so: the B200-native (sm_100a CUDA) replacement for the
+ * Monte-Carlo-EM E-step hot path of cbg-ethz/MC-CBN (H-CBN2 model).
+ *
+ * Drop-in boundary.  The reference is an R package whose R functions reach C++ through
+ * `.Call('_name', PACKAGE='mccbn', ...)` on `RcppExport SEXP _name(SEXP...)` symbols (useDynLib(mccbn) without a
+ * registration table, NAMESPACE:37, so R resolves by symbol name).  Every entry point below takes the SAME
+ * arguments in the SAME order and memory layout as the reference export it replaces (R's column-major int32
+ * matrices, double vectors, `float` lambda_s / max_lambda), followed by the dimensions R carries in the SEXP
+ * headers (N, p), the outputs the reference returns as an R list, and an error buffer.  INTEGRATION.md shows the
+ * ~10-line RcppExport stub per symbol that forwards to these functions.
+ *
+ * Conventions
+ *   - matrices are column-major: element (r, c) of an R x C matrix is a[c*R + r]
+ *   - poset[i + j*p] == 1  <=>  cover relation i -> j (i is a parent of j)      (src/model_impl.cpp:343-352)
+ *   - obs[i + j*N] != 0    <=>  event j observed in genotype i                   (as<MatrixXb>, src/mcem_hcbn.cpp:817)
+ *   - all pointers are HOST pointers unless the name ends in `_dev`
+ *   - return value: MCCBN_OK or an MCCBN_ERR_* code; on error `err` (if non-NULL) receives the message the
+ *     reference would have raised through Rf_error (src/mcem_hcbn.cpp:30-40)
+ *   - `thrds` is accepted for signature compatibility and ignored (the device replaces the OpenMP team)
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns MCCBN_ERR_CUDA
+ *
+ * Supported sizes: p <= 32 events for the Philox fast path (all BASELINE configs; one 32-bit genotype word),
+ * p <= 64 for the indexing entry points.
+ */
+#ifndef MCCBN_B200_H
+#define MCCBN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCCBN_OK 0
+#define MCCBN_ERR_NOT_ACYCLIC 1 /* "Poset does not correspond to an acyclic graph" (src/not_acyclic_exception.hpp:18) */
+#define MCCBN_ERR_ZERO_WEIGHT 2 /* "ERROR: all samples have weight 0. Consider increasing L" (src/mcem_hcbn.cpp:697) */
+#define MCCBN_ERR_CUDA 3        /* CUDA / NCCL failure, or no device */
+#define MCCBN_ERR_ARG 4         /* invalid argument (unknown sampling scheme, p too large, ...) */
+#define MCCBN_ERR_IO 5          /* ASA output files */
+
+#define MCCBN_MAX_P 64
+#define MCCBN_FAST_MAX_P 32
+#define MCCBN_NCCL_ID_BYTES 128
+
+typedef struct mccbn_ctx mccbn_ctx; /* owns the device buffers, stream, NCCL communicator */
+
+/* ---- context -------------------------------------------------------------------------------------------- */
+const char* mccbn_version(void);
+/* number of visible CUDA devices (0 if none / no driver) */
+int mccbn_device_count(void);
+/* Create a context on CUDA device `device`.  All entry points accept ctx == NULL and then use a lazily created
+ * process-wide context on device 0 (or $LOCAL_RANK if set). */
+int mccbn_ctx_create(mccbn_ctx** out, int device, char* err, size_t errlen);
+void mccbn_ctx_destroy(mccbn_ctx* ctx);
+/* Run on a caller-owned CUDA stream (cudaStream_t); NULL = the context's own non-blocking stream. */
+int mccbn_ctx_set_stream(mccbn_ctx* ctx, void* cuda_stream);
+/* Multi-GPU, one process per GPU: observations are sharded over `world` ranks; each EM iteration one
+ * sum-allreduce of p+3 doubles (NCCL over NVLink) combines the expected sufficient statistics
+ * (replaces the OpenMP reduction of src/mcem_hcbn.cpp:665).  Rank 0 calls mccbn_nccl_unique_id and ships the
+ * 128 bytes to the other ranks by any means (torch.distributed broadcast in the Python binding). */
+int mccbn_nccl_unique_id(unsigned char id[MCCBN_NCCL_ID_BYTES], char* err, size_t errlen);
+int mccbn_ctx_init_comm(mccbn_ctx* ctx, int rank, int world, const unsigned char id[MCCBN_NCCL_ID_BYTES], char* err,
+                        size_t errlen);
+/* Counters for the bench contract: kernels launched by this library since the last reset. */
+uint64_t mccbn_kernel_launches(mccbn_ctx* ctx, int reset);
+
+/* ---- extended options shared by the EM entry points ------------------------------------------------------ */
+typedef struct mccbn_em_options {
+  /* sharding (multi-GPU): `obs`, `times`, `weights` hold the LOCAL shard of N rows; obs_offset is the global
+   * index of local row 0, N_global the global number of observations (0 => N).  Philox counters use global row
+   * indices, so results do not depend on the number of ranks. */
+  int64_t obs_offset;
+  int64_t N_global;
+  /* optional per-iteration trace: max_iter x (p+2) doubles [obs_llhood, eps, lambda_0..lambda_{p-1}] row-major
+   * per iteration (the `verbose` line of src/mcem_hcbn.cpp:723-728); n_iter receives the number of rows */
+  double* trace;
+  int* n_iter;
+  /* 0 = fp32 sampling / fp64 reduction (default); 1 = fp64 sampling (validation mode, slower) */
+  int precision;
+  /* pool scheme: 0 = Rao-Blackwellised expectations over the pool (default), 1 = draw L indices like the reference */
+  int pool_resample;
+  /* stream id mixed into the Philox key so that independent evaluations (ASA candidates) decorrelate */
+  uint32_t stream_id;
+  uint32_t reserved[5];
+} mccbn_em_options;
+
+/* ---- hot-path entry points (names/arguments follow the reference exports) -------------------------------- */
+
+/* replaces `_MCEM_hcbn` (src/mcem_hcbn.cpp:804-864); returns list(lambda, eps, llhood) through the out pointers */
+int mccbn_MCEM_hcbn(mccbn_ctx* ctx, const double* ilambda, const int* poset, const int* obs, const double* times,
+                    float lambda_s, double eps, const double* weights, unsigned L, const char* sampling,
+                    unsigned max_iter, unsigned update_step_size, double tol, float max_lambda,
+                    unsigned neighborhood_dist, int sampling_times_available, int thrds, int verbose, int seed,
+                    /* dims */ int N, int p,
+                    /* out */ double* lambda_out, double* eps_out, double* llhood_out,
+                    /* optional */ const mccbn_em_options* opt, char* err, size_t errlen);
+
+/* replaces `_obs_log_likelihood` (src/mcem_hcbn.cpp:762-797) */
+int mccbn_obs_log_likelihood(mccbn_ctx* ctx, const int* obs, const int* poset, const double* lambda, double eps,
+                             const double* weights, const double* times, unsigned L, const char* sampling,
+                             unsigned neighborhood_dist, float lambda_s, int sampling_times_available, int thrds,
+                             int seed, int N, int p, double* llhood_out, const mccbn_em_options* opt, char* err,
+                             size_t errlen);
+
+/* replaces `_importance_weight` (src/mcem_hcbn.cpp:914-1010): per-observation sum w, sum w^2, L_eff (#w>0; only
+ * meaningful for backward/bernoulli, may be NULL), E[d], E[Z] (N x p column-major) */
+int mccbn_importance_weight(mccbn_ctx* ctx, const int* obs, unsigned L, const int* poset, const double* lambda,
+                            double eps, const double* times, const char* sampling, unsigned neighborhood_dist,
+                            float lambda_s, int sampling_times_available, int thrds, int seed, int N, int p,
+                            double* w_sum, double* w_sum_sq, int* L_eff, double* dist, double* Tdiff,
+                            const mccbn_em_options* opt, char* err, size_t errlen);
+
+/* replaces `_importance_weight_genotype` (src/mcem_hcbn.cpp:866-912): the raw per-sample quantities for ONE
+ * genotype: w[L], dist[L], Tdiff[L x p col-major].  *L_out = rows produced (backward rounds L down to
+ * reps * nrows_sum, :356-363).  forward/backward/bernoulli only. */
+int mccbn_importance_weight_genotype(mccbn_ctx* ctx, const int* genotype, unsigned L, const int* poset,
+                                     const double* lambda, double eps, double time, const char* sampling,
+                                     unsigned neighborhood_dist, float lambda_s, int sampling_times_available,
+                                     int seed, int p, int* L_out, double* w, int* dist, double* Tdiff,
+                                     const mccbn_em_options* opt, char* err, size_t errlen);
+
+/* replaces `_adaptive_simulated_annealing` (src/asa.cpp:596-665); poset_out = p x p adjacency over event ids */
+int mccbn_adaptive_simulated_annealing(mccbn_ctx* ctx, const int* poset, const int* obs, const double* times,
+                                       float lambda_s, const double* weights, unsigned L, const char* sampling,
+                                       unsigned max_iter_EM, unsigned update_step_size, double tol, float max_lambda,
+                                       float T0, float adap_rate, float acceptance_rate, int step_size,
+                                       unsigned max_iter_ASA, unsigned neighborhood_dist, int adaptive,
+                                       const char* outdir, int sampling_times_available, int thrds, int verbose,
+                                       int seed, int N, int p, double* lambda_out, double* eps_out, int* poset_out,
+                                       double* llhood_out, char* err, size_t errlen);
+
+/* replaces `MCEM` (legacy OT-CBN, src/mcem.cpp:307-335, called by estimate_mutation_rates): noise-free model,
+ * X == Y, conditional (truncated-exponential) proposal; returns list(lambda, llhood) */
+int mccbn_MCEM(mccbn_ctx* ctx, const double* ilambda, const int* poset, const int* O, const double* times,
+               int max_iter, float alpha, const int* topo_path, const double* weights, int nrOfSamples, int verbose,
+               float max_lambda, float lambda_s, int sampling_time_available, int seed, int N, int p,
+               double* lambda_out, double* llhood_out, char* err, size_t errlen);
+
+/* ---- indexing seams (bit-exact tier) --------------------------------------------------------------------- */
+
+/* Stage 1, poset flattening (adjacency_mat2list + has_cycles + topological_sort + get_direct_predecessors,
+ * src/model_impl.cpp:343-352,40-87): topo[p] = event ids in a valid topological order, parent_mask[p] = bitmask of
+ * direct parents by event id.  Returns MCCBN_ERR_NOT_ACYCLIC for a cyclic poset.  Host-only (no device needed). */
+int mccbn_flatten_poset(const int* poset, int p, int* topo, uint64_t* parent_mask, char* err, size_t errlen);
+
+/* replaces `_compatible_observations` (src/compatible_observations.cpp:91-116): out[i] = is_compatible(obs[i,])
+ * num_compatible / num_incompatible_events (may be NULL) follow :68-76 and :51-66.  Device reduction. */
+int mccbn_compatible_observations(mccbn_ctx* ctx, const int* obs, const int* poset, int N, int p, int* out,
+                                  int* num_compatible, int* num_incompatible_events, char* err, size_t errlen);
+
+/* replaces `_neighbors` (src/backward_sampling.cpp:79-103): the Hamming ball of radius k around `genotype` in the
+ * reference's enumeration order; out is nrows_sum x p column-major, ring[nrows_sum] (may be NULL) the distance.
+ * Host-only. */
+int mccbn_neighbors(int p, int k, const int* genotype, int* out, int* ring, int* nrows_sum, char* err, size_t errlen);
+
+/* initialize_lambda + the ASA start value of eps (src/asa.cpp:72-129, :640-642); device counts, float division */
+int mccbn_initialize_lambda(mccbn_ctx* ctx, const int* obs, const int* poset, int N, int p, float lambda_s,
+                            float max_lambda, double* lambda_out, double* eps_out, char* err, size_t errlen);
+
+/* ---- supplied-randomness seams (1e-10 fp64 tier; no RNG on either side) ---------------------------------- */
+
+/* forward scheme from host-supplied waiting times: Z is L x p, T_sampling is L.  Per sample: propagated event
+ * times T_sum (L x p, may be NULL), hidden genotype X (L x p int, may be NULL), Hamming distance to `genotype`,
+ * weight eps^d (1-eps)^(p-d)   (sample_genotypes :160-175 + hamming_dist_mat :326-330 + weights :386-388) */
+int mccbn_forward_from_times(mccbn_ctx* ctx, const int* genotype, int L, const int* poset, int p, double eps,
+                             const double* Z, const double* T_sampling, double* T_sum, int* X, int* dist, double* w,
+                             char* err, size_t errlen);
+
+/* One full E-step + M-step from supplied forward draws shared by all observations (if sampling_times_available
+ * the sampling time of observation i is times[i] instead of T_sampling[l]).  Outputs as `_importance_weight`
+ * plus totals[3+p] = [obs_llhood, expected_dist, N_eff, Tdiff_colsum...] and the M-step result
+ * (src/mcem_hcbn.cpp:683-709). */
+int mccbn_estep_forward_from_times(mccbn_ctx* ctx, const int* obs, int N, const int* poset, int p,
+                                   const double* lambda, double eps, const double* weights, const double* times,
+                                   int sampling_times_available, int L, const double* Z, const double* T_sampling,
+                                   float max_lambda, double* w_sum, double* w_sum_sq, double* dist, double* Tdiff,
+                                   double* totals, double* eps_new, double* lambda_new, char* err, size_t errlen);
+
+/* conditional proposal (generate_mutation_times + cbn_density_log, src/add_remove.cpp:156-216) from supplied
+ * uniforms u (L x p, indexed by event id) and sampling times: Tdiff (L x p), log q (L), log P(Z) (L),
+ * incompatible flag (L; any Z < 0, src/mcem_hcbn.cpp:524) */
+int mccbn_conditional_from_uniforms(mccbn_ctx* ctx, const int* X, int L, const int* poset, int p,
+                                    const double* lambda, const double* u, const double* T_sampling, double* Tdiff,
+                                    double* log_q, double* log_pz, int* incompatible, char* err, size_t errlen);
+
+/* ---- device-resident problem handle (what bench.py times with inputs already in HBM) --------------------- */
+typedef struct mccbn_problem mccbn_problem;
+
+/* upload + bit-pack the observation shard once */
+int mccbn_problem_create(mccbn_ctx* ctx, const int* obs, const double* times, const double* weights, int N, int p,
+                         int64_t obs_offset, int64_t N_global, mccbn_problem** out, char* err, size_t errlen);
+void mccbn_problem_destroy(mccbn_problem* pb);
+/* set poset + parameters (resets the EM iteration counter) */
+int mccbn_problem_set_model(mccbn_problem* pb, const int* poset, const double* lambda, double eps, float lambda_s,
+                            float max_lambda, char* err, size_t errlen);
+/* enqueue `n_iter` EM iterations (E-step, reduction, allreduce if sharded, M-step) on the context stream without
+ * synchronising; parameters stay on the device */
+int mccbn_problem_em_iterations(mccbn_problem* pb, unsigned L, const char* sampling, unsigned neighborhood_dist,
+                                int sampling_times_available, int seed, int n_iter, int update_params, char* err,
+                                size_t errlen);
+/* synchronise and read back the current parameters and the last observed log-likelihood */
+int mccbn_problem_read(mccbn_problem* pb, double* lambda, double* eps, double* llhood, char* err, size_t errlen);
+/* the CUDA stream the problem's work is enqueued on (for event timing by the caller) */
+void* mccbn_problem_stream(mccbn_problem* pb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCCBN_B200_H */

@@ -1,0 +1,69 @@
+// device_types.cuh -- data layout shared by host engine and kernels (libmccbn_b200)
+//
+// HBM layout (per problem = one shard of observations on one GPU):
+//   obs_bits   : N x uint64   bit j = event j observed (bit-packed once from R's N x p int32 matrix)
+//   times      : N x double   sampling times t_i (only read when sampling_times_available)
+//   weights    : N x double   observation weights wt_i
+//   part       : n_cand x n_items x PS doubles   per-(observation, chunk) partial sums of one E-step
+//   obs_out    : optional N x (3 + p) doubles    per-observation sum w, sum w^2, E[d], E[Z_j]
+//   blk_part   : n_cand x n_blocks x PS doubles  deterministic second-stage partials
+//   stats      : n_cand x PS doubles             [LL, N_eff, D, zero_weight_count, 0, S_0..S_{p-1}] -- the vector
+//                                                 that is all-reduced across GPUs
+// Read-only per-E-step model tables live in __constant__ memory (FwdConst), refreshed by a device-to-device
+// copy after every on-device M-step.
+#pragma once
+#include <cstdint>
+
+namespace mccbn {
+
+constexpr int kFastMaxP = 32;      // one 32-bit genotype word on the Philox fast path
+constexpr int kMaxCand = 16;       // concurrently scored candidate posets (ASA batching)
+constexpr int kMaxEdgesFast = 512; // >= 32*31/2
+constexpr int kFwdBlock = 128;     // threads per block of the forward E-step kernel
+constexpr int kStatHdr = 5;        // partial record: [sum w', sum w'^2, sum w' d, #{w>0}, log scale]; stats: [LL, N_eff, D, zero_count, -]
+constexpr int kRtabN = 72;         // relative-weight table r^delta, delta = 0..64, tail = 0
+
+// static structure of one poset, topological-position space (uploaded by the host)
+struct DevPoset {
+  int p;
+  int n_edges;
+  unsigned char ev[64];        // event id at topological position k
+  unsigned short pstart[68];   // CSR offsets into ppos (fast path, p <= 32)
+  unsigned char ppos[kMaxEdgesFast];  // parent positions
+  uint64_t parent_pos[64];     // by position: parents (positions)
+  uint64_t parent_ev[64];      // by event id: parents (event ids)
+  uint64_t ancestor_ev[64];    // by event id: all ancestors (event ids)
+  uint64_t has_children_pos;
+};
+
+// mutable model parameters + EM bookkeeping of one candidate (device resident)
+struct DevModel {
+  double lambda[64];  // by event id
+  double eps;
+  double lambda_s;    // the reference keeps this as float (src/mcem.hpp:190); widened once on the host
+  double max_lambda;  // float in the reference (src/mcem.hpp:218)
+  double llhood;      // obs_llhood of the last E-step
+  // weight tables for the forward scheme: w = base * r^d' with d' = flip ? p - d : d  (r <= 1 always)
+  double log_base;    // flip ? p*log(eps) : p*log1p(-eps)
+  double log_r;       // log(min(r, 1/r)), r = eps/(1-eps)
+  double rtab_d[kRtabN];
+  float rtab[kRtabN];
+  int flip;
+  int iter;           // EM iterations done since set_model
+  int zero_weight;    // sticky: some observation had sum w == 0
+  int pad;
+};
+
+// __constant__ tables of the forward kernel (per candidate)
+struct FwdConst {
+  float c[kFastMaxP];   // -ln2 / lambda at topological position k:  Z = log2(u) * c
+  float cs;             // -ln2 / lambda_s
+  int p;
+  unsigned store_mask;  // bit k: T_k has children and must be staged in shared memory
+  int flip;
+  unsigned char ev[kFastMaxP];
+  unsigned short pstart[kFastMaxP + 4];
+  unsigned short poff[kMaxEdgesFast];  // byte offset of the parent's row in the per-thread T staging area
+};
+
+}  // namespace mccbn

@@ -1,0 +1,902 @@
+// engine_impl.cuh -- E-step dispatch, EM driver (MCEM_hcbn host logic) and the extern "C" entry points.
+// Included at the end of mccbn_b200.cu (single translation unit: kernels, __constant__ tables and host code).
+#pragma once
+
+// ----------------------------------------------------------------------------------------------------------------
+// E-step dispatch
+// ----------------------------------------------------------------------------------------------------------------
+namespace mccbn {
+
+struct BackwardPlan {
+  std::vector<uint64_t> masks;
+  int n_ball = 0, reps = 0, L_eff_total = 0;
+};
+
+static BackwardPlan plan_backward(int p, unsigned neighborhood_dist, unsigned L) {
+  BackwardPlan bp;
+  bp.masks = hamming_ball_masks((unsigned)p, neighborhood_dist);
+  bp.n_ball = (int)bp.masks.size();           // nrows_sum (src/mcem_hcbn.cpp:356-361)
+  bp.reps = (int)(L / (unsigned)bp.n_ball);   // :362
+  bp.L_eff_total = bp.reps * bp.n_ball;       // :363
+  return bp;
+}
+
+}  // namespace mccbn
+
+struct CondLauncher {
+  template <typename real, int PMAX>
+  static void go(const CondArgs& a, bool times_given, int mode, dim3 grid, cudaStream_t s) {
+#define MCCBN_COND(TG, MD) estep_conditional_kernel<real, PMAX, TG, MD><<<grid, kFwdBlock, 0, s>>>(a)
+    if (mode == kCondBackward) {
+      if (times_given) MCCBN_COND(true, kCondBackward); else MCCBN_COND(false, kCondBackward);
+    } else if (mode == kCondBernoulli) {
+      if (times_given) MCCBN_COND(true, kCondBernoulli); else MCCBN_COND(false, kCondBernoulli);
+    } else {
+      if (times_given) MCCBN_COND(true, kCondOtcbn); else MCCBN_COND(false, kCondOtcbn);
+    }
+#undef MCCBN_COND
+  }
+};
+
+void mccbn_problem::enqueue_iteration(Scheme scheme, int L, unsigned neighborhood_dist, bool times_given,
+                                      uint32_t seed, int update_params, bool per_obs_out, int precision) {
+  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  cudaStream_t s = ctx->stream;
+  const int iter = iter_host[0];
+  int chunks = 1, chunk_len = L, grid_x = 1;
+  long long n_items = 0;
+  int L_eff = L;
+
+  if (scheme == kForward) {
+    choose_chunks(L, chunks, chunk_len, grid_x);
+    n_items = (long long)N * chunks;
+    FwdArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.obs_bits = bits.ptr;
+    a.times = times.ptr;
+    a.models = models.ptr;
+    a.part = part.ensure((size_t)n_cand * n_items * PS());
+    a.N = N;
+    a.L = L;
+    a.chunks = chunks;
+    a.chunk_len = chunk_len;
+    a.n_items = n_items;
+    a.obs_offset = obs_offset;
+    const PhiloxKey key = make_key(seed, (uint32_t)iter, 0u);
+    a.key0 = key.k0;
+    a.key1 = key.k1;
+    for (int c = 0; c < kMaxCand; ++c) a.cand_ctr[c] = eval_id[c];
+    a.PS = PS();
+    const dim3 grid(grid_x, n_cand);
+    if (precision == 1)
+      launch_forward<double>(a, times_given, grid);
+    else
+      launch_forward<float>(a, times_given, grid);
+  } else if (scheme == kBackward || scheme == kBernoulli) {
+    CondArgs a;
+    std::memset(&a, 0, sizeof(a));
+    int mode = scheme == kBackward ? kCondBackward : kCondBernoulli;
+    if (scheme == kBackward) {
+      BackwardPlan bp = plan_backward(p, neighborhood_dist, (unsigned)L);
+      if (bp.reps == 0) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);  // L < nrows_sum: no samples at all
+      if (ball_p != p || ball_k != (int)neighborhood_dist) {
+        ball.ensure(bp.masks.size());
+        MCCBN_CUDA(cudaMemcpyAsync(ball.ptr, bp.masks.data(), sizeof(uint64_t) * bp.masks.size(),
+                                   cudaMemcpyHostToDevice, s));
+        MCCBN_CUDA(cudaStreamSynchronize(s));
+        ball_p = p;
+        ball_k = (int)neighborhood_dist;
+      }
+      a.ball = ball.ptr;
+      a.n_ball = bp.n_ball;
+      a.reps = bp.reps;
+      a.L = bp.L_eff_total;
+      // chunk over ball genotypes; keep >= ~256 samples per chunk
+      const int per_geno = bp.reps;
+      int genos_per_chunk = std::max(1, (256 + per_geno - 1) / per_geno);
+      const long long total_warps = (long long)ctx->sm_count * 16;
+      long long want = (total_warps * 24 + N - 1) / std::max(1, N);
+      int max_chunks = std::max(1, bp.n_ball / genos_per_chunk);
+      chunks = (int)std::max(1LL, std::min<long long>(want, max_chunks));
+      chunk_len = (bp.n_ball + chunks - 1) / chunks;
+      chunks = (bp.n_ball + chunk_len - 1) / chunk_len;
+      L_eff = 0;  // #{w > 0} per observation (src/mcem_hcbn.cpp:688-689)
+    } else {
+      int gx_unused;
+      choose_chunks(L, chunks, chunk_len, gx_unused);
+      a.L = L;
+      L_eff = L;
+    }
+    n_items = (long long)N * chunks;
+    a.obs_bits = bits.ptr;
+    a.times = times.ptr;
+    a.models = models.ptr;
+    a.posets = posets.ptr;
+    a.part = part.ensure((size_t)n_cand * n_items * PS());
+    a.N = N;
+    a.chunks = chunks;
+    a.chunk_len = chunk_len;
+    a.n_items = n_items;
+    a.obs_offset = obs_offset;
+    const PhiloxKey key = make_key(seed, (uint32_t)iter, scheme == kBackward ? 1u : 2u);
+    a.key0 = key.k0;
+    a.key1 = key.k1;
+    for (int c = 0; c < kMaxCand; ++c) a.cand_ctr[c] = eval_id[c];
+    a.PS = PS();
+    const int warps_per_block = kFwdBlock / 32;
+    long long blocks = (n_items + warps_per_block - 1) / warps_per_block;
+    grid_x = (int)std::max(1LL, std::min<long long>(blocks, (long long)ctx->sm_count * 4));
+    const dim3 grid(grid_x, n_cand);
+    if (precision == 1) {
+      CondLauncher::go<double, 32>(a, times_given, mode, grid, s);
+    } else if (p <= 16) {
+      CondLauncher::go<float, 16>(a, times_given, mode, grid, s);
+    } else {
+      CondLauncher::go<float, 32>(a, times_given, mode, grid, s);
+    }
+    ctx->launches++;
+    MCCBN_CUDA(cudaGetLastError());
+  } else {
+    throw Error(MCCBN_ERR_ARG, scheme == kPool ? "sampling scheme 'pool' is not implemented in this build"
+                                               : "sampling scheme 'add-remove' is not implemented in this build");
+  }
+  run_finalize(chunks, n_items, L_eff, 0, per_obs_out);
+  run_mstep(update_params);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// EM driver: the host-side control flow of MCEM_hcbn (src/mcem_hcbn.cpp:571-736) for candidate slot 0..n_cand-1
+// ----------------------------------------------------------------------------------------------------------------
+namespace mccbn {
+
+struct EmControl {  // ControlEM (src/mcem.hpp:213-226)
+  unsigned max_iter = 100, update_step_size = 20;
+  double tol = 0.001;
+  float max_lambda = 1e6f;
+  unsigned neighborhood_dist = 1;
+};
+
+struct EmResult {
+  std::vector<double> lambda;
+  double eps = 0, llhood = 0;
+  int n_iter = 0;
+};
+
+// Runs MCEM on slot 0 (single poset).  trace_out (optional) receives the per-iteration rows.
+static EmResult run_mcem(mccbn_problem& pb, Scheme scheme, unsigned L, const EmControl& ctl, bool times_given,
+                         uint32_t seed, bool verbose, int precision, double* trace_out, int* n_iter_out) {
+  const int p = pb.p;
+  EmResult res;
+  res.lambda.assign(p, 0.0);
+  if (ctl.update_step_size == 0) throw Error(MCCBN_ERR_ARG, "update_step_size must be >= 1");
+  std::vector<double> avg_lambda(p, 0.0), avg_lambda_current(p, 0.0);
+  double avg_eps = 0.0, avg_eps_current = 0.0, avg_llhood = 0.0;
+  unsigned boundary = ctl.update_step_size;
+  const int stride = p + 2;
+  pb.ensure_trace((int)std::max(1u, ctl.max_iter));
+  std::vector<double> rows;
+
+  if (verbose) {
+    DevModel dm;
+    pb.read_model(0, dm);
+    std::printf("Initial value of the error rate - epsilon: %g\n", dm.eps);
+    std::printf("Initial value of the rate parameters - lambda:");
+    for (int j = 0; j < p; ++j) std::printf(" %g", dm.lambda[j]);
+    std::printf("\n");
+  }
+
+  unsigned iter = 0;
+  bool converged = false;
+  while (iter < ctl.max_iter) {
+    if (iter == boundary) {  // :622-642
+      for (auto& x : avg_lambda_current) x /= ctl.update_step_size;
+      avg_eps_current /= ctl.update_step_size;
+      avg_llhood /= ctl.update_step_size;
+      bool ok = std::abs(avg_eps - avg_eps_current) <= ctl.tol;
+      for (int j = 0; j < p && ok; ++j) ok = std::abs(avg_lambda[j] - avg_lambda_current[j]) <= ctl.tol;
+      if (ok) {
+        converged = true;
+        break;
+      }
+      avg_lambda = avg_lambda_current;
+      avg_eps = avg_eps_current;
+      boundary += ctl.update_step_size;
+      std::fill(avg_lambda_current.begin(), avg_lambda_current.end(), 0.0);
+      avg_eps_current = 0.0;
+      avg_llhood = 0.0;
+    }
+    const unsigned n_run = std::min(boundary, ctl.max_iter) - iter;
+    for (unsigned t = 0; t < n_run; ++t)
+      pb.enqueue_iteration(scheme, (int)L, ctl.neighborhood_dist, times_given, seed, 1, false, precision);
+    // one host sync per batch: fetch the trace rows of this batch
+    rows.resize((size_t)n_run * stride);
+    MCCBN_CUDA(cudaMemcpyAsync(rows.data(), pb.trace.ptr + (size_t)iter * stride, sizeof(double) * rows.size(),
+                               cudaMemcpyDeviceToHost, pb.ctx->stream));
+    DevModel dm;
+    pb.read_model(0, dm);  // synchronises the stream
+    if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
+    for (unsigned t = 0; t < n_run; ++t) {
+      const double* row = rows.data() + (size_t)t * stride;
+      for (int j = 0; j < p; ++j) avg_lambda_current[j] += row[2 + j];  // :711-713
+      avg_eps_current += row[1];
+      avg_llhood += row[0];
+      if (verbose) {
+        if (iter + t == 0) std::printf("llhood\tepsilon\tlambdas\n");
+        std::printf("%g\t%g\t", row[0], row[1]);
+        for (int j = 0; j < p; ++j) std::printf(" %g", row[2 + j]);
+        std::printf("\n");
+      }
+      if (trace_out) std::memcpy(trace_out + (size_t)(iter + t) * stride, row, sizeof(double) * stride);
+    }
+    iter += n_run;
+    if (iter == ctl.max_iter) {  // :715-721
+      const unsigned num_iter = ctl.max_iter - boundary + ctl.update_step_size;
+      for (auto& x : avg_lambda_current) x /= num_iter;
+      avg_eps_current /= num_iter;
+      avg_llhood /= num_iter;
+    }
+  }
+  (void)converged;
+  res.lambda = avg_lambda_current;  // :731-735: the batch averages are the result
+  res.eps = avg_eps_current;
+  res.llhood = avg_llhood;
+  res.n_iter = (int)iter;
+  if (n_iter_out) *n_iter_out = (int)iter;
+  return res;
+}
+
+static std::mutex g_default_mu;
+static mccbn_ctx* g_default_ctx = nullptr;
+
+static void ctx_init(mccbn_ctx* c, int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw Error(MCCBN_ERR_CUDA, std::string("no CUDA device available (libmccbn_b200 has no CPU fallback): ") +
+                                    cudaGetErrorString(e));
+  if (device < 0 || device >= n) throw Error(MCCBN_ERR_ARG, "invalid CUDA device index");
+  c->device = device;
+  MCCBN_CUDA(cudaSetDevice(device));
+  MCCBN_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  cudaDeviceProp prop;
+  MCCBN_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+}
+
+static mccbn_ctx* get_ctx(mccbn_ctx* c) {
+  if (c) {
+    MCCBN_CUDA(cudaSetDevice(c->device));
+    return c;
+  }
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  if (!g_default_ctx) {
+    int dev = 0;
+    if (const char* lr = std::getenv("LOCAL_RANK")) dev = std::atoi(lr);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) dev %= n;
+    mccbn_ctx* nc = new mccbn_ctx();
+    try {
+      ctx_init(nc, dev);
+    } catch (...) {
+      delete nc;
+      throw;
+    }
+    g_default_ctx = nc;
+  }
+  MCCBN_CUDA(cudaSetDevice(g_default_ctx->device));
+  return g_default_ctx;
+}
+
+static int report(const std::exception& e, char* err, size_t errlen) {
+  int code = MCCBN_ERR_CUDA;
+  if (auto* me = dynamic_cast<const Error*>(&e)) code = me->code;
+  if (err && errlen) {
+    std::snprintf(err, errlen, "%s", e.what());
+  }
+  return code;
+}
+
+// host-built weight table, same libm expression as the reference (src/mcem_hcbn.cpp:387-388)
+static std::vector<double> host_wtab(double eps, int p) {
+  std::vector<double> w(65, 0.0);
+  for (int d = 0; d <= p; ++d) w[d] = std::pow(eps, (double)d) * std::pow(1 - eps, (double)p - (double)d);
+  return w;
+}
+
+static uint64_t pack_genotype(const int* g, int p) {
+  uint64_t w = 0;
+  for (int j = 0; j < p; ++j) w |= (uint64_t)(g[j] != 0) << j;
+  return w;
+}
+
+}  // namespace mccbn
+
+#define MCCBN_TRY try {
+#define MCCBN_CATCH                                           \
+  }                                                           \
+  catch (const std::exception& e) { return report(e, err, errlen); } \
+  return MCCBN_OK;
+
+// ================================================================================================================
+// C ABI
+// ================================================================================================================
+extern "C" {
+
+const char* mccbn_version(void) { return "mccbn_b200 0.1 (sm_100a)"; }
+
+int mccbn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int mccbn_ctx_create(mccbn_ctx** out, int device, char* err, size_t errlen) {
+  MCCBN_TRY
+  mccbn_ctx* c = new mccbn_ctx();
+  try {
+    ctx_init(c, device);
+  } catch (...) {
+    delete c;
+    throw;
+  }
+  *out = c;
+  MCCBN_CATCH
+}
+
+void mccbn_ctx_destroy(mccbn_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->comm) c->nccl.CommDestroy(c->comm);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int mccbn_ctx_set_stream(mccbn_ctx* c, void* stream) {
+  char* err = nullptr;
+  size_t errlen = 0;
+  MCCBN_TRY
+  c = get_ctx(c);
+  c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+  MCCBN_CATCH
+}
+
+int mccbn_nccl_unique_id(unsigned char id[MCCBN_NCCL_ID_BYTES], char* err, size_t errlen) {
+  MCCBN_TRY
+  NcclApi api;
+  api.load();
+  NcclApi::unique_id u;
+  api.check(api.GetUniqueId(&u), "ncclGetUniqueId");
+  std::memcpy(id, u.internal, MCCBN_NCCL_ID_BYTES);
+  MCCBN_CATCH
+}
+
+int mccbn_ctx_init_comm(mccbn_ctx* c, int rank, int world, const unsigned char id[MCCBN_NCCL_ID_BYTES], char* err,
+                        size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (world < 1 || rank < 0 || rank >= world) throw Error(MCCBN_ERR_ARG, "invalid rank/world");
+  c->rank = rank;
+  c->world = world;
+  if (world > 1) {
+    c->nccl.load();
+    NcclApi::unique_id u;
+    std::memcpy(u.internal, id, MCCBN_NCCL_ID_BYTES);
+    c->nccl.check(c->nccl.CommInitRank(&c->comm, world, u, rank), "ncclCommInitRank");
+  }
+  MCCBN_CATCH
+}
+
+uint64_t mccbn_kernel_launches(mccbn_ctx* c, int reset) {
+  try {
+    c = get_ctx(c);
+  } catch (...) {
+    return 0;
+  }
+  uint64_t v = c->launches;
+  if (reset) c->launches = 0;
+  return v;
+}
+
+// ---- device-resident problem ------------------------------------------------------------------------------------
+int mccbn_problem_create(mccbn_ctx* c, const int* obs, const double* times, const double* weights, int N, int p,
+                         int64_t obs_offset, int64_t N_global, mccbn_problem** out, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (N < 1) throw Error(MCCBN_ERR_ARG, "N must be >= 1");
+  if (p < 1 || p > kMaxP) throw Error(MCCBN_ERR_ARG, "p must be in [1, 64]");
+  mccbn_problem* pb = new mccbn_problem();
+  pb->ctx = c;
+  pb->N = N;
+  pb->p = p;
+  pb->obs_offset = obs_offset;
+  pb->N_global = N_global > 0 ? N_global : N;
+  try {
+    pb->upload(obs, times, weights);
+  } catch (...) {
+    delete pb;
+    throw;
+  }
+  *out = pb;
+  MCCBN_CATCH
+}
+
+void mccbn_problem_destroy(mccbn_problem* pb) {
+  if (!pb) return;
+  cudaSetDevice(pb->ctx->device);
+  delete pb;
+}
+
+int mccbn_problem_set_model(mccbn_problem* pb, const int* poset, const double* lambda, double eps, float lambda_s,
+                            float max_lambda, char* err, size_t errlen) {
+  MCCBN_TRY
+  get_ctx(pb->ctx);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, pb->p, P, f);
+  pb->set_model(0, f, lambda, eps, lambda_s, max_lambda);
+  pb->prepare(1);
+  pb->ensure_trace(4096);
+  MCCBN_CATCH
+}
+
+int mccbn_problem_em_iterations(mccbn_problem* pb, unsigned L, const char* sampling, unsigned neighborhood_dist,
+                                int sampling_times_available, int seed, int n_iter, int update_params, char* err,
+                                size_t errlen) {
+  MCCBN_TRY
+  get_ctx(pb->ctx);
+  const Scheme sc = parse_scheme(sampling);
+  for (int t = 0; t < n_iter; ++t)
+    pb->enqueue_iteration(sc, (int)L, neighborhood_dist, sampling_times_available != 0, (uint32_t)seed, update_params,
+                          false, 0);
+  MCCBN_CATCH
+}
+
+int mccbn_problem_read(mccbn_problem* pb, double* lambda, double* eps, double* llhood, char* err, size_t errlen) {
+  MCCBN_TRY
+  get_ctx(pb->ctx);
+  DevModel dm;
+  pb->read_model(0, dm);
+  if (lambda) std::memcpy(lambda, dm.lambda, sizeof(double) * pb->p);
+  if (eps) *eps = dm.eps;
+  if (llhood) *llhood = dm.llhood;
+  if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
+  MCCBN_CATCH
+}
+
+void* mccbn_problem_stream(mccbn_problem* pb) { return (void*)pb->ctx->stream; }
+
+// ---- hot-path entry points --------------------------------------------------------------------------------------
+int mccbn_MCEM_hcbn(mccbn_ctx* c, const double* ilambda, const int* poset, const int* obs, const double* times,
+                    float lambda_s, double eps, const double* weights, unsigned L, const char* sampling,
+                    unsigned max_iter, unsigned update_step_size, double tol, float max_lambda,
+                    unsigned neighborhood_dist, int sampling_times_available, int thrds, int verbose, int seed, int N,
+                    int p, double* lambda_out, double* eps_out, double* llhood_out, const mccbn_em_options* opt,
+                    char* err, size_t errlen) {
+  (void)thrds;
+  MCCBN_TRY
+  c = get_ctx(c);
+  const Scheme sc = parse_scheme(sampling);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  // Model::update_lambda(ilambda, max_lambda) (src/mcem_hcbn.cpp:837)
+  std::vector<double> lam(ilambda, ilambda + p);
+  for (auto& l : lam)
+    if (l > max_lambda || !std::isfinite(l)) l = max_lambda;
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.obs_offset = opt ? opt->obs_offset : 0;
+  pb.N_global = (opt && opt->N_global > 0) ? opt->N_global : N;
+  pb.upload(obs, times, weights);
+  if (opt) pb.eval_id[0] = opt->stream_id;
+  pb.set_model(0, f, lam.data(), eps, lambda_s, max_lambda);
+  pb.prepare(1);
+  EmControl ctl;
+  ctl.max_iter = max_iter;
+  ctl.update_step_size = update_step_size;
+  ctl.tol = tol;
+  ctl.max_lambda = max_lambda;
+  ctl.neighborhood_dist = neighborhood_dist;
+  EmResult r = run_mcem(pb, sc, L, ctl, sampling_times_available != 0, (uint32_t)seed, verbose != 0,
+                        opt ? opt->precision : 0, opt ? opt->trace : nullptr, opt ? opt->n_iter : nullptr);
+  std::copy(r.lambda.begin(), r.lambda.end(), lambda_out);
+  *eps_out = r.eps;
+  *llhood_out = r.llhood;
+  MCCBN_CATCH
+}
+
+static void single_estep(mccbn_ctx* c, mccbn_problem& pb, const int* obs, const int* poset, const double* lambda,
+                         double eps, const double* weights, const double* times, unsigned L, const char* sampling,
+                         unsigned neighborhood_dist, float lambda_s, int times_available, int seed, int N, int p,
+                         const mccbn_em_options* opt, bool per_obs) {
+  const Scheme sc = parse_scheme(sampling);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.obs_offset = opt ? opt->obs_offset : 0;
+  pb.N_global = (opt && opt->N_global > 0) ? opt->N_global : N;
+  pb.upload(obs, times, weights);
+  if (opt) pb.eval_id[0] = opt->stream_id;
+  pb.set_model(0, f, lambda, eps, lambda_s, 1e6f);
+  pb.prepare(1);
+  pb.ensure_trace(1);
+  pb.enqueue_iteration(sc, (int)L, neighborhood_dist, times_available != 0, (uint32_t)seed, 0, per_obs,
+                       opt ? opt->precision : 0);
+}
+
+int mccbn_obs_log_likelihood(mccbn_ctx* c, const int* obs, const int* poset, const double* lambda, double eps,
+                             const double* weights, const double* times, unsigned L, const char* sampling,
+                             unsigned neighborhood_dist, float lambda_s, int sampling_times_available, int thrds,
+                             int seed, int N, int p, double* llhood_out, const mccbn_em_options* opt, char* err,
+                             size_t errlen) {
+  (void)thrds;
+  MCCBN_TRY
+  c = get_ctx(c);
+  mccbn_problem pb;
+  single_estep(c, pb, obs, poset, lambda, eps, weights, times, L, sampling, neighborhood_dist, lambda_s,
+               sampling_times_available, seed, N, p, opt, false);
+  DevModel dm;
+  pb.read_model(0, dm);
+  if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
+  *llhood_out = dm.llhood;
+  MCCBN_CATCH
+}
+
+int mccbn_importance_weight(mccbn_ctx* c, const int* obs, unsigned L, const int* poset, const double* lambda,
+                            double eps, const double* times, const char* sampling, unsigned neighborhood_dist,
+                            float lambda_s, int sampling_times_available, int thrds, int seed, int N, int p,
+                            double* w_sum, double* w_sum_sq, int* L_eff, double* dist, double* Tdiff,
+                            const mccbn_em_options* opt, char* err, size_t errlen) {
+  (void)thrds;
+  MCCBN_TRY
+  c = get_ctx(c);
+  mccbn_problem pb;
+  single_estep(c, pb, obs, poset, lambda, eps, nullptr, times, L, sampling, neighborhood_dist, lambda_s,
+               sampling_times_available, seed, N, p, opt, true);
+  cudaStream_t s = c->stream;
+  if (w_sum) MCCBN_CUDA(cudaMemcpyAsync(w_sum, pb.out_w.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (w_sum_sq) MCCBN_CUDA(cudaMemcpyAsync(w_sum_sq, pb.out_w2.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (L_eff) MCCBN_CUDA(cudaMemcpyAsync(L_eff, pb.out_leff.ptr, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
+  if (dist) MCCBN_CUDA(cudaMemcpyAsync(dist, pb.out_dist.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, pb.out_T.ptr, sizeof(double) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  MCCBN_CATCH
+}
+
+int mccbn_importance_weight_genotype(mccbn_ctx* c, const int* genotype, unsigned L, const int* poset,
+                                     const double* lambda, double eps, double time, const char* sampling,
+                                     unsigned neighborhood_dist, float lambda_s, int sampling_times_available,
+                                     int seed, int p, int* L_out, double* w, int* dist, double* Tdiff,
+                                     const mccbn_em_options* opt, char* err, size_t errlen) {
+  (void)neighborhood_dist;
+  MCCBN_TRY
+  c = get_ctx(c);
+  const Scheme sc = parse_scheme(sampling);
+  if (sc != kForward) throw Error(MCCBN_ERR_ARG, "importance_weight_genotype: only 'forward' exposes per-sample output");
+  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  int one_obs[64];
+  for (int j = 0; j < p; ++j) one_obs[j] = genotype[j];
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = 1;
+  pb.p = p;
+  pb.upload(one_obs, &time, nullptr);
+  pb.set_model(0, f, lambda, eps, lambda_s, 1e6f);
+  pb.prepare(1);
+  cudaStream_t s = c->stream;
+  DevBuf<double> dZ, dTs;
+  DevBuf<int> dD;
+  DevBuf<uint32_t> dX;
+  FwdDumpArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.obs_word = pack_genotype(genotype, p);
+  a.time = time;
+  a.model = pb.models.ptr;
+  a.Z_out = dZ.ensure((size_t)L * p);
+  a.dist_out = dD.ensure(L);
+  a.X_out = dX.ensure(L);
+  a.Ts_out = dTs.ensure(L);
+  a.L = (int)L;
+  a.gi = (uint32_t)(opt ? opt->obs_offset : 0);
+  const PhiloxKey key = make_key((uint32_t)seed, 0u, 0u);
+  a.key0 = key.k0;
+  a.key1 = key.k1;
+  a.cw = opt ? opt->stream_id : 0u;
+  const int grid = (int)std::min<unsigned>((L + kFwdBlock - 1) / kFwdBlock, 4096u);
+  const bool tg = sampling_times_available != 0;
+  const int prec = opt ? opt->precision : 0;
+  if (prec == 1) {
+    if (tg) forward_dump_kernel<double, 32, true><<<grid, kFwdBlock, 0, s>>>(a);
+    else forward_dump_kernel<double, 32, false><<<grid, kFwdBlock, 0, s>>>(a);
+  } else {
+    if (tg) forward_dump_kernel<float, 32, true><<<grid, kFwdBlock, 0, s>>>(a);
+    else forward_dump_kernel<float, 32, false><<<grid, kFwdBlock, 0, s>>>(a);
+  }
+  c->launches++;
+  MCCBN_CUDA(cudaGetLastError());
+  std::vector<int> hd(L);
+  MCCBN_CUDA(cudaMemcpyAsync(hd.data(), dD.ptr, sizeof(int) * L, cudaMemcpyDeviceToHost, s));
+  if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, dZ.ptr, sizeof(double) * (size_t)L * p, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  const std::vector<double> wt = host_wtab(eps, p);
+  for (unsigned l = 0; l < L; ++l) {
+    if (dist) dist[l] = hd[l];
+    if (w) w[l] = wt[hd[l]];
+  }
+  if (L_out) *L_out = (int)L;
+  MCCBN_CATCH
+}
+
+// ---- indexing seams ---------------------------------------------------------------------------------------------
+int mccbn_flatten_poset(const int* poset, int p, int* topo, uint64_t* parent_mask, char* err, size_t errlen) {
+  MCCBN_TRY
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  for (int k = 0; k < p; ++k) topo[k] = f.topo[k];
+  for (int j = 0; j < p; ++j) parent_mask[j] = f.parent_ev[j];
+  MCCBN_CATCH
+}
+
+int mccbn_neighbors(int p, int k, const int* genotype, int* out, int* ring, int* nrows_sum, char* err,
+                    size_t errlen) {
+  MCCBN_TRY
+  if (p < 1 || p > kMaxP || k < 0 || k > p) throw Error(MCCBN_ERR_ARG, "invalid p or k");
+  std::vector<int> rg;
+  std::vector<uint64_t> masks = hamming_ball_masks((unsigned)p, (unsigned)k, &rg);
+  const int n = (int)masks.size();
+  if (nrows_sum) *nrows_sum = n;
+  if (out)
+    for (int r = 0; r < n; ++r)
+      for (int j = 0; j < p; ++j) out[(size_t)j * n + r] = ((genotype[j] != 0) != (bool)((masks[r] >> j) & 1)) ? 1 : 0;
+  if (ring) std::copy(rg.begin(), rg.end(), ring);
+  MCCBN_CATCH
+}
+
+int mccbn_compatible_observations(mccbn_ctx* c, const int* obs, const int* poset, int N, int p, int* out,
+                                  int* num_compatible, int* num_incompatible_events, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.upload(obs, nullptr, nullptr);
+  DevPoset dp;
+  fill_dev_poset(f, dp);
+  cudaStream_t s = c->stream;
+  MCCBN_CUDA(cudaMemcpyAsync(pb.posets.ptr, &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
+  DevBuf<int> flags;
+  DevBuf<unsigned long long> counts;
+  flags.ensure(N);
+  counts.ensure(2);
+  MCCBN_CUDA(cudaMemsetAsync(counts.ptr, 0, 2 * sizeof(unsigned long long), s));
+  compat_kernel<<<dim3(std::min(1024, (N + 255) / 256), 1), 256, 0, s>>>(pb.bits.ptr, N, pb.posets.ptr, flags.ptr,
+                                                                          counts.ptr);
+  c->launches++;
+  MCCBN_CUDA(cudaGetLastError());
+  unsigned long long h[2];
+  if (out) MCCBN_CUDA(cudaMemcpyAsync(out, flags.ptr, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaMemcpyAsync(h, counts.ptr, sizeof(h), cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  if (num_compatible) *num_compatible = (int)h[0];
+  if (num_incompatible_events) *num_incompatible_events = (int)h[1];
+  MCCBN_CATCH
+}
+
+namespace mccbn {
+// initialize_lambda from device counts (src/asa.cpp:92-128): float arithmetic reproduced on the host
+static void lambda_from_counts(const FlatPoset& f, const unsigned long long* cnt, int N, float lambda_s,
+                               float max_lambda, double* lambda_out) {
+  for (int j = 0; j < f.p; ++j) {
+    unsigned count = 1;
+    float mutated = 1e-7f;
+    if (f.ancestor_ev[j]) {
+      count += (unsigned)cnt[j * 2 + 0];
+      mutated += (int)cnt[j * 2 + 1];
+    } else {
+      count += (unsigned)N;
+      mutated += (int)cnt[j * 2 + 1];
+    }
+    const float aux = mutated / count;
+    double lam = aux * lambda_s / (1.0 - aux);
+    if (lam > max_lambda || !std::isfinite(lam)) lam = max_lambda;
+    lambda_out[j] = lam;
+  }
+}
+}  // namespace mccbn
+
+int mccbn_initialize_lambda(mccbn_ctx* c, const int* obs, const int* poset, int N, int p, float lambda_s,
+                            float max_lambda, double* lambda_out, double* eps_out, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.upload(obs, nullptr, nullptr);
+  DevPoset dp;
+  fill_dev_poset(f, dp);
+  cudaStream_t s = c->stream;
+  MCCBN_CUDA(cudaMemcpyAsync(pb.posets.ptr, &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
+  DevBuf<unsigned long long> cnt, counts;
+  cnt.ensure(128);
+  counts.ensure(2);
+  MCCBN_CUDA(cudaMemsetAsync(cnt.ptr, 0, 128 * sizeof(unsigned long long), s));
+  MCCBN_CUDA(cudaMemsetAsync(counts.ptr, 0, 2 * sizeof(unsigned long long), s));
+  const int gx = std::min(1024, (N + 255) / 256);
+  init_lambda_counts_kernel<<<dim3(gx, 1), 256, 0, s>>>(pb.bits.ptr, N, pb.posets.ptr, cnt.ptr);
+  compat_kernel<<<dim3(gx, 1), 256, 0, s>>>(pb.bits.ptr, N, pb.posets.ptr, nullptr, counts.ptr);
+  c->launches += 2;
+  MCCBN_CUDA(cudaGetLastError());
+  unsigned long long hc[128], h2[2];
+  MCCBN_CUDA(cudaMemcpyAsync(hc, cnt.ptr, sizeof(hc), cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaMemcpyAsync(h2, counts.ptr, sizeof(h2), cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  lambda_from_counts(f, hc, N, lambda_s, max_lambda, lambda_out);
+  if (eps_out) {
+    const double e = (double)(int)h2[1] / ((double)N * p);
+    *eps_out = std::max(std::min(e, 1 - DBL_EPSILON), DBL_EPSILON);
+  }
+  MCCBN_CATCH
+}
+
+// ---- supplied-randomness seams ----------------------------------------------------------------------------------
+int mccbn_forward_from_times(mccbn_ctx* c, const int* genotype, int L, const int* poset, int p, double eps,
+                             const double* Z, const double* T_sampling, double* T_sum, int* X, int* dist, double* w,
+                             char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  cudaStream_t s = c->stream;
+  DevPoset dp;
+  fill_dev_poset(f, dp);
+  DevBuf<DevPoset> dpos;
+  DevBuf<double> dZ, dT, dTs, dW, dWt;
+  DevBuf<int> dX, dD;
+  dpos.ensure(1);
+  const size_t LP = (size_t)L * p;
+  MCCBN_CUDA(cudaMemcpyAsync(dpos.ptr, &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dZ.ensure(LP), Z, sizeof(double) * LP, cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dTs.ensure(L), T_sampling, sizeof(double) * L, cudaMemcpyHostToDevice, s));
+  const std::vector<double> wt = host_wtab(eps, p);
+  MCCBN_CUDA(cudaMemcpyAsync(dWt.ensure(65), wt.data(), sizeof(double) * 65, cudaMemcpyHostToDevice, s));
+  dT.ensure(LP);
+  const int grid = std::min(2048, (L + 127) / 128);
+  propagate_times_kernel<<<grid, 128, 0, s>>>(dZ.ptr, dT.ptr, L, dpos.ptr);
+  forward_from_times_kernel<<<grid, 128, 0, s>>>(dT.ptr, dTs.ptr, pack_genotype(genotype, p), L, p, dWt.ptr,
+                                                 X ? dX.ensure(LP) : nullptr, dD.ensure(L), dW.ensure(L));
+  c->launches += 2;
+  MCCBN_CUDA(cudaGetLastError());
+  if (T_sum) MCCBN_CUDA(cudaMemcpyAsync(T_sum, dT.ptr, sizeof(double) * LP, cudaMemcpyDeviceToHost, s));
+  if (X) MCCBN_CUDA(cudaMemcpyAsync(X, dX.ptr, sizeof(int) * LP, cudaMemcpyDeviceToHost, s));
+  if (dist) MCCBN_CUDA(cudaMemcpyAsync(dist, dD.ptr, sizeof(int) * L, cudaMemcpyDeviceToHost, s));
+  if (w) MCCBN_CUDA(cudaMemcpyAsync(w, dW.ptr, sizeof(double) * L, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  MCCBN_CATCH
+}
+
+int mccbn_estep_forward_from_times(mccbn_ctx* c, const int* obs, int N, const int* poset, int p,
+                                   const double* lambda, double eps, const double* weights, const double* times,
+                                   int sampling_times_available, int L, const double* Z, const double* T_sampling,
+                                   float max_lambda, double* w_sum, double* w_sum_sq, double* dist, double* Tdiff,
+                                   double* totals, double* eps_new, double* lambda_new, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.upload(obs, times, weights);
+  pb.set_model(0, f, lambda, eps, 1.0f, max_lambda);
+  pb.prepare(1);
+  pb.ensure_trace(1);
+  cudaStream_t s = c->stream;
+  DevBuf<double> dZ, dT, dTs, dWt;
+  const size_t LP = (size_t)L * p;
+  MCCBN_CUDA(cudaMemcpyAsync(dZ.ensure(LP), Z, sizeof(double) * LP, cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dTs.ensure(L), T_sampling, sizeof(double) * L, cudaMemcpyHostToDevice, s));
+  const std::vector<double> wt = host_wtab(eps, p);
+  MCCBN_CUDA(cudaMemcpyAsync(dWt.ensure(65), wt.data(), sizeof(double) * 65, cudaMemcpyHostToDevice, s));
+  dT.ensure(LP);
+  propagate_times_kernel<<<std::min(2048, (L + 127) / 128), 128, 0, s>>>(dZ.ptr, dT.ptr, L, pb.posets.ptr);
+  pb.part.ensure((size_t)N * pb.PS());
+  estep_from_times_kernel<<<std::min(N, c->sm_count * 8), kF64Block, 0, s>>>(
+      dZ.ptr, dT.ptr, dTs.ptr, pb.bits.ptr, pb.times.ptr, sampling_times_available, N, L, pb.posets.ptr, dWt.ptr,
+      pb.part.ptr, pb.PS());
+  c->launches += 2;
+  MCCBN_CUDA(cudaGetLastError());
+  pb.run_finalize(1, N, L, 0, true);
+  // totals before the M-step overwrites nothing: stats = [LL, N_eff, D, zero, 0, S_k (topological order)]
+  std::vector<double> st(pb.PS());
+  MCCBN_CUDA(cudaMemcpyAsync(st.data(), pb.stats.ptr, sizeof(double) * pb.PS(), cudaMemcpyDeviceToHost, s));
+  pb.run_mstep(1);
+  DevModel dm;
+  pb.read_model(0, dm);
+  if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
+  if (w_sum) MCCBN_CUDA(cudaMemcpyAsync(w_sum, pb.out_w.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (w_sum_sq) MCCBN_CUDA(cudaMemcpyAsync(w_sum_sq, pb.out_w2.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (dist) MCCBN_CUDA(cudaMemcpyAsync(dist, pb.out_dist.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, pb.out_T.ptr, sizeof(double) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  if (totals) {
+    totals[0] = st[0];
+    totals[1] = st[2];
+    totals[2] = st[1];
+    for (int k = 0; k < p; ++k) totals[3 + f.topo[k]] = st[kStatHdr + k];
+  }
+  if (eps_new) *eps_new = dm.eps;
+  if (lambda_new) std::memcpy(lambda_new, dm.lambda, sizeof(double) * p);
+  MCCBN_CATCH
+}
+
+int mccbn_conditional_from_uniforms(mccbn_ctx* c, const int* X, int L, const int* poset, int p,
+                                    const double* lambda, const double* u, const double* T_sampling, double* Tdiff,
+                                    double* log_q, double* log_pz, int* incompatible, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  cudaStream_t s = c->stream;
+  DevPoset dp;
+  fill_dev_poset(f, dp);
+  DevBuf<DevPoset> dpos;
+  DevBuf<double> dU, dTs, dLam, dT, dq, dpz;
+  DevBuf<int> dX, dInc;
+  const size_t LP = (size_t)L * p;
+  MCCBN_CUDA(cudaMemcpyAsync(dpos.ensure(1), &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dX.ensure(LP), X, sizeof(int) * LP, cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dU.ensure(LP), u, sizeof(double) * LP, cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dTs.ensure(L), T_sampling, sizeof(double) * L, cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dLam.ensure(p), lambda, sizeof(double) * p, cudaMemcpyHostToDevice, s));
+  conditional_from_uniforms_kernel<<<std::min(2048, (L + 127) / 128), 128, 0, s>>>(
+      dX.ptr, dU.ptr, dTs.ptr, L, dpos.ptr, dLam.ptr, dT.ensure(LP), dq.ensure(L), dpz.ensure(L), dInc.ensure(L));
+  c->launches++;
+  MCCBN_CUDA(cudaGetLastError());
+  if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, dT.ptr, sizeof(double) * LP, cudaMemcpyDeviceToHost, s));
+  if (log_q) MCCBN_CUDA(cudaMemcpyAsync(log_q, dq.ptr, sizeof(double) * L, cudaMemcpyDeviceToHost, s));
+  if (log_pz) MCCBN_CUDA(cudaMemcpyAsync(log_pz, dpz.ptr, sizeof(double) * L, cudaMemcpyDeviceToHost, s));
+  if (incompatible) MCCBN_CUDA(cudaMemcpyAsync(incompatible, dInc.ptr, sizeof(int) * L, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  MCCBN_CATCH
+}
+
+// ---- not yet implemented in this build (declared by the header; they fail loudly) ---------------------------------
+int mccbn_adaptive_simulated_annealing(mccbn_ctx*, const int*, const int*, const double*, float, const double*,
+                                       unsigned, const char*, unsigned, unsigned, double, float, float, float, float,
+                                       int, unsigned, unsigned, int, const char*, int, int, int, int, int, int, double*,
+                                       double*, int*, double*, char* err, size_t errlen) {
+  MCCBN_TRY
+  throw Error(MCCBN_ERR_ARG, "adaptive_simulated_annealing is not implemented in this build");
+  MCCBN_CATCH
+}
+
+int mccbn_MCEM(mccbn_ctx*, const double*, const int*, const int*, const double*, int, float, const int*, const double*,
+               int, int, float, float, int, int, int, int, double*, double*, char* err, size_t errlen) {
+  MCCBN_TRY
+  throw Error(MCCBN_ERR_ARG, "OT-CBN MCEM is not implemented in this build");
+  MCCBN_CATCH
+}
+
+}  // extern "C"

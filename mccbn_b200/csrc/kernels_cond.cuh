@@ -1,0 +1,293 @@
+// kernels_cond.cuh -- conditional ("truncated-exponential") proposal E-step for sm_100a: the backward
+// (Hamming-ball) and bernoulli schemes of the reference, and the OT-CBN proposal (X == Y).
+//
+// Replaces, per (observation i, sample l):
+//   neighbors / replicate          src/backward_sampling.cpp:37-54, src/mcem_hcbn.cpp:497-513  X = Y ^ flip[l mod n]
+//   coin_tossing                   src/backward_sampling.cpp:64-77                              X = Y ^ Bernoulli(eps) mask
+//   generate_mutation_times        src/add_remove.cpp:156-203   T_s ~ Exp(lambda_s); per node in topological order
+//                                     m = max_pa T; X_j ? z ~ TExp(lambda_j, 0, T_s - m), T_j = m + z
+//                                                       : z ~ Exp(lambda_j),            T_j = max(m, T_s) + z;  Z_j = T_j - m
+//   cbn_density_log + weights      src/add_remove.cpp:206-216, src/mcem_hcbn.cpp:524-532, :559-562
+//
+// The importance weight is evaluated through the algebraic identity (checked against the oracle in
+// tests/test_oracle_exact.py::test_k3_density_identity)
+//     log P(Z) - log q_Z = sum_{X_j=1} log F_j(T_s - m_j)  -  sum_{X_j=0} lambda_j max(0, T_s - m_j),
+// i.e. the lambda*z terms cancel, so no log/exp of the density itself is needed.  A sample is incompatible
+// (weight 0, reference: any Z_j < 0) iff some mutated event has an unmutated parent -- pure bit work.
+// Weights are continuous here, so each lane keeps a running log2 reference (online log-sum-exp) and the warp
+// aligns the lanes before the fp64 reduction.
+#pragma once
+#include "device_types.cuh"
+#include "kernels_forward.cuh"
+#include "philox.cuh"
+
+namespace mccbn {
+
+enum CondMode { kCondBackward = 0, kCondBernoulli = 1, kCondOtcbn = 2 };
+
+struct CondArgs {
+  const uint64_t* obs_bits;
+  const double* times;
+  const DevModel* models;
+  const DevPoset* posets;
+  const uint64_t* ball;  // backward: flip masks of the Hamming ball (event-id bit order), n_ball entries
+  double* part;
+  int N, L;              // L = samples per observation actually drawn (backward: reps * n_ball)
+  int n_ball, reps;      // backward only
+  int chunks, chunk_len; // backward: chunk over ball genotypes; bernoulli/otcbn: chunk over samples
+  long long n_items;
+  long long obs_offset;
+  uint32_t key0, key1;
+  uint32_t cand_ctr[kMaxCand];
+  int PS;
+};
+
+template <typename real>
+struct CondMath;
+template <>
+struct CondMath<float> {
+  // scale constants per node: lam2 = lambda * log2(e), inv = ln2 / lambda
+  static __device__ __forceinline__ float u01(uint32_t b) { return __uint_as_float((b >> 9) | 0x3f800000u) - 1.0f; }  // [0,1)
+  static __device__ __forceinline__ float F_of(float a, float lam2) { return 1.0f - fast_ex2(-a * lam2); }
+  static __device__ __forceinline__ float z_of(float u, float F, float inv) { return -fast_lg2(1.0f - u * F) * inv; }
+  static __device__ __forceinline__ float lg2(float x) { return fast_lg2(x); }
+  static __device__ __forceinline__ float ex2(float x) { return fast_ex2(x); }
+};
+template <>
+struct CondMath<double> {
+  static __device__ __forceinline__ double F_of(double a, double lam2) { return -expm1(-a * lam2 * 0.693147180559945309417); }
+  static __device__ __forceinline__ double z_of(double u, double F, double inv) {
+    return -log1p(-u * F) * inv * 1.44269504088896340736;
+  }
+  static __device__ __forceinline__ double lg2(double x) { return log2(x); }
+  static __device__ __forceinline__ double ex2(double x) { return exp2(x); }
+};
+
+template <typename real>
+__device__ __forceinline__ real cond_uniform(const uint4& r, int w) {
+  if (sizeof(real) == 4) {
+    const uint32_t bits = w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
+    return (real)CondMath<float>::u01(bits);
+  } else {
+    const uint32_t hi = w == 0 ? r.x : r.z, lo = w == 0 ? r.y : r.w;
+    const uint64_t m = ((uint64_t)hi << 21) ^ (uint64_t)(lo >> 11);
+    return (real)((double)m * (1.0 / 9007199254740992.0));  // [0, 1)
+  }
+}
+
+// One conditional draw.  Xt = hidden genotype (topological bit order).  Returns log2 of P(Z)/q_Z.
+template <typename real, int PMAX, bool TIMES_GIVEN>
+__device__ __forceinline__ real sample_conditional(const FwdConst& fc, const int p, real* __restrict__ Tcol,
+                                                   const real* __restrict__ s_lam2, const real* __restrict__ s_inv,
+                                                   const uint32_t l, const uint32_t gi, const uint32_t k0,
+                                                   const uint32_t k1, const uint32_t cw, const real ts_given,
+                                                   const uint32_t Xt, real (&Z)[PMAX], real& Ts_out) {
+  constexpr int UPB = RealTraits<real>::kUniPerBlock;
+  uint4 r = make_uint4(0, 0, 0, 0);
+  real Ts = ts_given;
+  if (!TIMES_GIVEN) {
+    r = philox4x32_10(l, gi, 0u, cw, k0, k1);
+    const real u = cond_uniform<real>(r, 0);
+    Ts = CondMath<real>::z_of(u, (real)1, s_inv[PMAX]);  // Exp(lambda_s)
+  }
+  real lw2 = (real)0;
+#pragma unroll
+  for (int k = 0; k < PMAX; ++k) {
+    if (k < p) {
+      const int ui = k + (TIMES_GIVEN ? 0 : 1);
+      if (ui % UPB == 0) r = philox4x32_10(l, gi, (uint32_t)(ui / UPB), cw, k0, k1);
+      const real u = cond_uniform<real>(r, ui % UPB);
+      real m = (real)0;
+      const int e1 = fc.pstart[k + 1];
+      for (int e = fc.pstart[k]; e < e1; ++e)
+        m = max(m, *reinterpret_cast<const real*>(reinterpret_cast<const char*>(Tcol) +
+                                                   (size_t)fc.poff[e] * (sizeof(real) / 4)));
+      const bool xk = (Xt >> k) & 1u;
+      const real a = Ts - m;
+      const real Fx = CondMath<real>::F_of(a, s_lam2[k]);
+      const real F = xk ? Fx : (real)1;
+      const real z = CondMath<real>::z_of(u, F, s_inv[k]);
+      const real base = xk ? m : max(m, Ts);
+      const real t = base + z;
+      if ((fc.store_mask >> k) & 1u) Tcol[k * kFwdBlock] = t;
+      Z[k] = t - m;
+      lw2 += xk ? CondMath<real>::lg2(Fx) : -s_lam2[k] * max(a, (real)0);
+    }
+  }
+  Ts_out = Ts;
+  return lw2;
+}
+
+// compatibility of a genotype in topological bit order: every mutated event has all parents mutated
+template <int PMAX>
+__device__ __forceinline__ bool compatible_topo(const uint32_t* __restrict__ s_pm, const int p, const uint32_t Xt) {
+  uint32_t bad = 0u;
+#pragma unroll
+  for (int k = 0; k < PMAX; ++k)
+    if (k < p) bad |= ((Xt >> k) & 1u) ? (s_pm[k] & ~Xt) : 0u;
+  return bad == 0u;
+}
+
+template <typename real, int PMAX, bool TIMES_GIVEN, int MODE>
+__global__ void __launch_bounds__(kFwdBlock) estep_conditional_kernel(const CondArgs a) {
+  __shared__ real s_T[PMAX * kFwdBlock];
+  __shared__ real s_lam2[PMAX + 1];
+  __shared__ real s_inv[PMAX + 1];
+  __shared__ real s_lpyx2[68];     // log2 P(Y|X) by Hamming distance
+  __shared__ uint32_t s_pm[PMAX];  // parent masks, topological bit order
+
+  const int cand = blockIdx.y;
+  const FwdConst& fc = c_fwd[cand];
+  const DevModel* __restrict__ mdl = a.models + cand;
+  const DevPoset* __restrict__ pos = a.posets + cand;
+  const int p = fc.p;
+  const int lane = threadIdx.x & 31;
+  constexpr int kWarps = kFwdBlock / 32;
+  real* Tcol = s_T + threadIdx.x;
+  const double kLog2e = 1.44269504088896340736;
+
+  for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock) {
+    const double lam = t < p ? mdl->lambda[fc.ev[t]] : mdl->lambda_s;
+    s_lam2[t] = (real)(lam * kLog2e);
+    s_inv[t] = (real)(1.0 / (lam * kLog2e));
+    if (t < PMAX) s_pm[t] = t < p ? (uint32_t)pos->parent_pos[t] : 0u;
+  }
+  for (int d = threadIdx.x; d < 68; d += kFwdBlock) {
+    double lp = 0.0;
+    if (MODE == kCondBackward && d <= p) {
+      // log_bernoulli_process (src/mcem_hcbn.cpp:84-100), incl. the eps == 0 special case
+      const double eps = mdl->eps;
+      if (eps == 0.0)
+        lp = d ? log(eps + DBL_EPSILON) * d + log1p(-eps - DBL_EPSILON) * (p - d) : 0.0;
+      else
+        lp = log(eps) * d + log1p(-eps) * (p - d);
+    }
+    s_lpyx2[d] = (real)(lp * kLog2e);
+  }
+  __syncthreads();
+
+  const long long gw = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * kWarps;
+  const uint32_t cw = a.cand_ctr[cand];
+  const uint32_t eps_thr = (MODE == kCondBernoulli) ? (uint32_t)fmin(mdl->eps * 4294967296.0, 4294967295.0) : 0u;
+
+  for (long long item = gw; item < a.n_items; item += nw) {
+    const int i = (int)(item / a.chunks);
+    const int ch = (int)(item - (long long)i * a.chunks);
+    const uint64_t yw = a.obs_bits[i];
+    const uint32_t yt = to_topo_bits<PMAX>(fc, p, yw);
+    const real ts_given = TIMES_GIVEN ? (real)a.times[i] : (real)0;
+    const uint32_t gi = (uint32_t)(a.obs_offset + i);
+
+    real acc[PMAX];
+#pragma unroll
+    for (int k = 0; k < PMAX; ++k) acc[k] = (real)0;
+    real aw = (real)0, aw2 = (real)0, awd = (real)0, npos = (real)0;
+    real mref = (real)-1e30;  // this lane's log2 reference
+
+    auto consume = [&](const uint32_t l, const uint32_t Xt, const int d, const bool valid) {
+      real Z[PMAX];
+      real Ts;
+      const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(fc, p, Tcol, s_lam2, s_inv, l, gi, a.key0, a.key1,
+                                                                    cw, ts_given, Xt, Z, Ts);
+      const real lw2 = lw2s + s_lpyx2[d];
+      const bool ok = valid && (lw2 > (real)-1e30);  // F <= 0 (incompatible) gives NaN / -inf -> not ok
+      if (ok && lw2 > mref) {  // rare after the first few samples: move the reference up (with head-room)
+        const real nref = lw2 + (real)4;
+        const real s = CondMath<real>::ex2(mref - nref);
+        aw *= s;
+        aw2 *= s * s;
+        awd *= s;
+#pragma unroll
+        for (int k = 0; k < PMAX; ++k) acc[k] *= s;
+        mref = nref;
+      }
+      const real wr = ok ? CondMath<real>::ex2(lw2 - mref) : (real)0;
+      aw += wr;
+      aw2 = fma(wr, wr, aw2);
+      awd = fma(wr, (real)d, awd);
+      npos += (wr > (real)0) ? (real)1 : (real)0;
+#pragma unroll
+      for (int k = 0; k < PMAX; ++k)
+        if (k < p) acc[k] = fma(wr, Z[k], acc[k]);
+    };
+
+    double lscale_extra = 0.0;
+    if (MODE == kCondBackward) {
+      // number of compatible genotypes in the whole ball (:525: nrows_sum - #incompatible)
+      int n_compat = 0;
+      for (int g = lane; g < a.n_ball; g += 32)
+        n_compat += compatible_topo<PMAX>(s_pm, p, to_topo_bits<PMAX>(fc, p, yw ^ a.ball[g]));
+      n_compat = __reduce_add_sync(0xffffffffu, n_compat);
+      lscale_extra = log((double)n_compat);
+      const int g_begin = ch * a.chunk_len, g_end = min(a.n_ball, g_begin + a.chunk_len);
+      for (int g = g_begin; g < g_end; ++g) {
+        const uint64_t flip = a.ball[g];
+        const uint32_t Xt = to_topo_bits<PMAX>(fc, p, yw ^ flip);
+        if (!compatible_topo<PMAX>(s_pm, p, Xt)) continue;  // warp-uniform
+        const int d = __popcll(flip);
+        for (int r0 = 0; r0 < a.reps; r0 += 32) {
+          const int rep = r0 + lane;
+          // sample index as in the reference's replicate(reps, 1) layout: row l = g + n_ball * rep
+          consume((uint32_t)(g + a.n_ball * rep), Xt, d, rep < a.reps);
+        }
+      }
+    } else {
+      const int l_begin = ch * a.chunk_len, l_end = min(a.L, l_begin + a.chunk_len);
+      for (int l0 = l_begin; l0 < l_end; l0 += 32) {
+        const int l = l0 + lane;
+        uint32_t Xt = yt;
+        if (MODE == kCondBernoulli) {
+          // coin_tossing: flip each bit independently with probability eps (32 random bits per coin)
+          uint4 rc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int k = 0; k < PMAX; ++k) {
+            if (k < p) {
+              if ((k & 3) == 0) rc = philox4x32_10((uint32_t)l, gi, 64u + (uint32_t)(k >> 2), cw, a.key0, a.key1);
+              const uint32_t bits = (k & 3) == 0 ? rc.x : ((k & 3) == 1 ? rc.y : ((k & 3) == 2 ? rc.z : rc.w));
+              Xt ^= (bits < eps_thr) ? (1u << k) : 0u;
+            }
+          }
+        }
+        const bool comp = compatible_topo<PMAX>(s_pm, p, Xt);
+        consume((uint32_t)l, Xt, __popc(Xt ^ yt), (l < l_end) && comp);
+      }
+    }
+
+    // align the lanes to the warp-wide reference, then reduce in fp64
+    real mmax = mref;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+    const real s = (mref > (real)-1e29) ? CondMath<real>::ex2(mref - mmax) : (real)0;
+    double* out = a.part + ((size_t)cand * a.n_items + item) * a.PS;
+    double v0 = (double)(aw * s), v1 = (double)(aw2 * s * s), v2 = (double)(awd * s), v3 = (double)npos;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+    }
+    if (lane == 0) {
+      out[0] = v0;
+      out[1] = v1;
+      out[2] = v2;
+      out[3] = v3;
+      // natural-log scale of this record: true weights = exp(lscale) * relative weights
+      out[4] = (mmax > (real)-1e29) ? (double)mmax * 0.693147180559945309417 + lscale_extra : -INFINITY;
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < PMAX; ++k) {
+      if (k < p) {
+        double v = (double)(acc[k] * s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == (k & 31)) mine = v;
+      }
+    }
+    if (lane < p) out[kStatHdr + lane] = mine;
+  }
+}
+
+}  // namespace mccbn

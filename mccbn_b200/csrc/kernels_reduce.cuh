@@ -1,0 +1,271 @@
+// kernels_reduce.cuh -- stages 5 and 6 of the hot path: per-observation finalisation, deterministic reduction of
+// the expected sufficient statistics, on-device M-step, and the small indexing kernels (bit-packing,
+// compatibility counts, initialize_lambda counts).
+//
+// Reference arithmetic being replaced:
+//   per-observation (src/mcem_hcbn.cpp:683-694): aux = sum w; N_eff += wt_i; obs_llhood += wt_i log(aux / L_eff);
+//       expected_dist += wt_i (sum w d)/aux; expected_Tdiff[i,] = (sum w Z)/aux
+//   M-step (:707-709, src/model_impl.cpp:21-34): eps = clamp(expected_dist/(N_eff p)); lambda_j = 1/(S_j/N_eff), clamped
+#pragma once
+#include <cfloat>
+
+#include "device_types.cuh"
+#include "kernels_forward.cuh"
+
+namespace mccbn {
+
+constexpr int kFinBlock = 256;
+constexpr int kFinWarps = kFinBlock / 32;
+constexpr int kMaxPS = kStatHdr + 64;
+
+struct FinArgs {
+  const double* part;       // n_cand x n_items x PS
+  const DevModel* models;   // n_cand
+  const DevPoset* posets;   // n_cand
+  const double* weights;    // N
+  double* blk_part;         // n_cand x gridDim.x x PS
+  double* w_sum;            // optional per-observation outputs (candidate 0 only)
+  double* w_sum_sq;
+  double* dist;
+  double* Tdiff;            // N x p column-major by event id
+  int* L_eff_out;
+  int N, chunks, PS, p;
+  long long n_items;
+  int L_eff;                // > 0: fixed L_eff (forward / bernoulli / pool: L); <= 0: #{w > 0} (backward, :688-689)
+  int uniform_fallback;     // OT-CBN: sum w == 0 => uniform weights instead of an error (src/mcem.cpp:123-127)
+};
+
+// Partial record (one per observation and chunk): [0]=sum w', [1]=sum w'^2, [2]=sum w' d, [3]=#{w>0},
+// [4]=natural-log scale s (true weight w = exp(s) w'), [5+k]=sum w' Z_k (topological position k).
+// Chunks are merged with a log-sum-exp over their scales.  Output stats: [0]=LL, [1]=N_eff, [2]=D,
+// [3]=#observations whose weights are all zero, [4]=0, [5+k]=S_k.
+// One warp per observation, lane s owns record slot s (and s+32): coalesced reads, no shuffles except broadcasts.
+__global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) {
+  __shared__ double s_acc[kFinWarps][kMaxPS];
+  const int cand = blockIdx.y;
+  const DevPoset* __restrict__ pos = a.posets + cand;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int PS = a.PS;
+  const int sA = lane, sB = lane + 32;
+  double accA = 0.0, accB = 0.0;
+
+  for (int i = blockIdx.x * kFinWarps + warp; i < a.N; i += gridDim.x * kFinWarps) {
+    const double* rec = a.part + ((size_t)cand * a.n_items + (size_t)i * a.chunks) * PS;
+    double M = rec[4];
+    for (int c = 1; c < a.chunks; ++c) M = fmax(M, rec[(size_t)c * PS + 4]);
+    const bool any = M > -INFINITY;
+    double vA = 0.0, vB = 0.0;
+    for (int c = 0; c < a.chunks; ++c) {
+      const double* rc = rec + (size_t)c * PS;
+      const double s = any ? exp(rc[4] - M) : 0.0;
+      if (sA < PS) vA += (sA == 1 ? s * s : (sA == 3 ? 1.0 : s)) * rc[sA];
+      if (sB < PS) vB += s * rc[sB];
+    }
+    const double W = __shfl_sync(0xffffffffu, vA, 0);
+    const double npos = __shfl_sync(0xffffffffu, vA, 3);
+    const double wt = a.weights[i];
+    const double logW = any ? log(W) + M : -INFINITY;
+    const double w_true = exp(logW);
+    const bool ok = w_true > 0.0;  // the reference aborts when aux == 0 (src/mcem_hcbn.cpp:695-699)
+    const double Leff = a.L_eff > 0 ? (double)a.L_eff : npos;
+    if (lane == 0) {
+      accA += ok ? wt * (logW - log(Leff)) : 0.0;
+      if (a.w_sum && cand == 0) a.w_sum[i] = w_true;
+      if (a.L_eff_out && cand == 0) a.L_eff_out[i] = (int)npos;
+    } else if (lane == 1) {
+      accA += ok ? wt : 0.0;
+      if (a.w_sum_sq && cand == 0) a.w_sum_sq[i] = any ? vA * exp(2.0 * M) : 0.0;
+    } else if (lane == 2) {
+      const double ed = vA / W;
+      accA += ok ? wt * ed : 0.0;
+      if (a.dist && cand == 0) a.dist[i] = ed;
+    } else if (lane == 3) {
+      accA += ok ? 0.0 : 1.0;
+    } else if (lane > 4 && sA < PS) {
+      const double ez = vA / W;
+      accA += ok ? wt * ez : 0.0;
+      if (a.Tdiff && cand == 0) a.Tdiff[(size_t)pos->ev[sA - kStatHdr] * a.N + i] = ez;
+    }
+    if (sB < PS) {
+      const double ez = vB / W;
+      accB += ok ? wt * ez : 0.0;
+      if (a.Tdiff && cand == 0) a.Tdiff[(size_t)pos->ev[sB - kStatHdr] * a.N + i] = ez;
+    }
+  }
+  if (sA < PS) s_acc[warp][sA] = accA;
+  if (sB < PS) s_acc[warp][sB] = accB;
+  __syncthreads();
+  for (int s = threadIdx.x; s < PS; s += kFinBlock) {
+    double t = 0.0;
+    for (int w = 0; w < kFinWarps; ++w) t += s_acc[w][s];
+    a.blk_part[((size_t)cand * gridDim.x + blockIdx.x) * PS + s] = t;
+  }
+}
+
+// second stage: fixed-order sum of the block partials -> stats[cand][PS]
+__global__ void reduce_stats_kernel(const double* __restrict__ blk_part, double* __restrict__ stats, int n_blocks,
+                                    int PS) {
+  const int cand = blockIdx.x;
+  for (int s = threadIdx.x; s < PS; s += blockDim.x) {
+    double t = 0.0;
+    for (int b = 0; b < n_blocks; ++b) t += blk_part[((size_t)cand * n_blocks + b) * PS + s];
+    stats[(size_t)cand * PS + s] = t;
+  }
+}
+
+// Derived tables for the next E-step (device function, one block per candidate).
+__device__ inline void prepare_tables(const DevPoset* __restrict__ pos, DevModel* __restrict__ mdl,
+                                      FwdConst* __restrict__ fcs) {
+  const int p = pos->p;
+  const double eps = mdl->eps;
+  const double le = log(eps), l1 = log1p(-eps);
+  const int flip = (eps > 0.5) ? 1 : 0;
+  const double rr = flip ? (1.0 - eps) / eps : eps / (1.0 - eps);
+  for (int t = threadIdx.x; t < kRtabN; t += blockDim.x) {
+    double v = (t <= p) ? pow(rr, (double)t) : 0.0;
+    if (t == 0) v = 1.0;
+    mdl->rtab_d[t] = v;
+    mdl->rtab[t] = (float)v;
+  }
+  if (threadIdx.x == 0) {
+    mdl->flip = flip;
+    mdl->log_base = flip ? p * le : p * l1;
+    mdl->log_r = flip ? (l1 - le) : (le - l1);
+  }
+  if (fcs && p <= kFastMaxP) {
+    const double kLn2 = 0.693147180559945309417;
+    for (int k = threadIdx.x; k < kFastMaxP; k += blockDim.x) {
+      fcs->c[k] = k < p ? (float)(-kLn2 / mdl->lambda[pos->ev[k]]) : 0.f;
+      fcs->ev[k] = k < p ? pos->ev[k] : 0;
+    }
+    for (int k = threadIdx.x; k < kFastMaxP + 4; k += blockDim.x) fcs->pstart[k] = pos->pstart[min(k, p)];
+    for (int e = threadIdx.x; e < kMaxEdgesFast; e += blockDim.x)
+      fcs->poff[e] = e < pos->n_edges ? (unsigned short)(pos->ppos[e] * kFwdBlock * 4) : 0;
+    if (threadIdx.x == 0) {
+      fcs->cs = (float)(-kLn2 / mdl->lambda_s);
+      fcs->p = p;
+      fcs->store_mask = (unsigned)pos->has_children_pos;
+      fcs->flip = flip;
+    }
+  }
+}
+
+__global__ void prepare_kernel(const DevPoset* posets, DevModel* models, FwdConst* staging) {
+  prepare_tables(posets + blockIdx.x, models + blockIdx.x, staging ? staging + blockIdx.x : nullptr);
+}
+
+// Stage 6: M-step + trace row + tables for the next iteration.  One block per candidate.
+// stats may have been all-reduced across GPUs in between (identical on every rank => replicated M-step).
+__global__ void mstep_kernel(const double* __restrict__ stats, const DevPoset* posets, DevModel* models,
+                             FwdConst* staging, double* trace, int trace_stride, int max_trace_rows, int PS,
+                             int update_params) {
+  const int cand = blockIdx.x;
+  const DevPoset* pos = posets + cand;
+  DevModel* mdl = models + cand;
+  const double* st = stats + (size_t)cand * PS;
+  const int p = pos->p;
+  const double LL = st[0], Neff = st[1], D = st[2], zero = st[3];
+  if (update_params) {
+    for (int k = threadIdx.x; k < p; k += blockDim.x) {
+      double lam = 1.0 / (st[kStatHdr + k] / Neff);
+      if (lam > mdl->max_lambda || !isfinite(lam)) lam = mdl->max_lambda;  // Model::update_lambda
+      mdl->lambda[pos->ev[k]] = lam;
+    }
+    if (threadIdx.x == 0) {
+      const double e = D / (Neff * p);
+      mdl->eps = fmax(fmin(e, 1.0 - DBL_EPSILON), DBL_EPSILON);  // Model::update_epsilon
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mdl->llhood = LL;
+    if (zero > 0.0) mdl->zero_weight = 1;
+  }
+  const int it = mdl->iter;
+  if (trace && it < max_trace_rows) {
+    double* row = trace + ((size_t)cand * max_trace_rows + it) * trace_stride;
+    if (threadIdx.x == 0) {
+      row[0] = LL;
+      row[1] = mdl->eps;
+    }
+    for (int j = threadIdx.x; j < p; j += blockDim.x) row[2 + j] = mdl->lambda[j];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) mdl->iter = it + 1;
+  if (update_params) prepare_tables(pos, mdl, staging ? staging + cand : nullptr);
+}
+
+// ---- indexing kernels ---------------------------------------------------------------------------------------
+
+// R's N x p int32 column-major observation matrix -> one 64-bit word per observation (bit j = event j)
+__global__ void pack_obs_kernel(const int* __restrict__ obs, uint64_t* __restrict__ bits, int N, int p) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    uint64_t w = 0;
+    for (int j = 0; j < p; ++j) w |= (uint64_t)(obs[(size_t)j * N + i] != 0) << j;  // coalesced along i
+    bits[i] = w;
+  }
+}
+
+// is_compatible / num_compatible_observations / num_incompatible_events
+// (src/compatible_observations.cpp:12-28, :68-76, :51-66) for n_cand posets at once.
+// counts[cand*2 + 0] = #compatible observations, counts[cand*2 + 1] = sum over direct edges u->v of #{i: !obs_u & obs_v}
+__global__ void compat_kernel(const uint64_t* __restrict__ bits, int N, const DevPoset* posets, int* flags /*N or null*/,
+                              unsigned long long* counts) {
+  const DevPoset* pos = posets + blockIdx.y;
+  __shared__ uint64_t s_par[64];
+  const int p = pos->p;
+  for (int j = threadIdx.x; j < 64; j += blockDim.x) s_par[j] = j < p ? pos->parent_ev[j] : 0ull;
+  __syncthreads();
+  unsigned ncomp = 0, ninc = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const uint64_t g = bits[i];
+    unsigned bad = 0;
+    for (uint64_t m = g; m; m &= m - 1) {
+      const int j = __ffsll((long long)m) - 1;
+      bad += __popcll(s_par[j] & ~g);
+    }
+    ninc += bad;
+    ncomp += bad == 0;
+    if (flags && blockIdx.y == 0) flags[i] = bad == 0;
+  }
+  // block reduction (integers: order-independent, exact)
+  for (int o = 16; o > 0; o >>= 1) {
+    ncomp += __shfl_xor_sync(0xffffffffu, ncomp, o);
+    ninc += __shfl_xor_sync(0xffffffffu, ninc, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&counts[blockIdx.y * 2 + 0], (unsigned long long)ncomp);
+    atomicAdd(&counts[blockIdx.y * 2 + 1], (unsigned long long)ninc);
+  }
+}
+
+// counts for initialize_lambda (src/asa.cpp:72-129): per event j, with A_j = all ancestors of j:
+//   cnt[cand][j][0] = #{i : A_j subset of obs_i},  cnt[cand][j][1] = #{i : A_j u {j} subset of obs_i}
+__global__ void init_lambda_counts_kernel(const uint64_t* __restrict__ bits, int N, const DevPoset* posets,
+                                          unsigned long long* cnt) {
+  const DevPoset* pos = posets + blockIdx.y;
+  const int p = pos->p;
+  __shared__ uint64_t s_anc[64];
+  __shared__ unsigned s_cnt[64][2];
+  for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+    s_anc[j] = j < p ? pos->ancestor_ev[j] : 0ull;
+    s_cnt[j][0] = s_cnt[j][1] = 0;
+  }
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const uint64_t g = bits[i];
+    for (int j = 0; j < p; ++j) {
+      if ((s_anc[j] & ~g) == 0) {
+        atomicAdd(&s_cnt[j][0], 1u);
+        if ((g >> j) & 1ull) atomicAdd(&s_cnt[j][1], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < p; j += blockDim.x) {
+    atomicAdd(&cnt[((size_t)blockIdx.y * 64 + j) * 2 + 0], (unsigned long long)s_cnt[j][0]);
+    atomicAdd(&cnt[((size_t)blockIdx.y * 64 + j) * 2 + 1], (unsigned long long)s_cnt[j][1]);
+  }
+}
+
+}  // namespace mccbn

@@ -1,0 +1,262 @@
+// mccbn_b200.cu -- libmccbn_b200.so: device-resident problem, EM driver and the C ABI (include/mccbn_b200.h).
+//
+// Host flow of one MCEM run (replaces MCEM_hcbn, src/mcem_hcbn.cpp:571-736):
+//   upload + bit-pack observations once  ->  for each EM iteration, all stream-ordered with no host sync:
+//     E-step kernel (Philox sampling + weights + per-(observation, chunk) partial sums)
+//     finalize kernel (per-observation log-sum-exp combine, E[d], E[Z], first-stage reduction)
+//     reduce kernel   (fixed-order second stage -> stats vector of p+4 doubles)
+//     [ncclAllReduce of the stats vector when observations are sharded over GPUs]
+//     M-step kernel   (lambda/eps update with the reference's clamps, trace row, tables for the next E-step)
+//     device-to-device refresh of the __constant__ model tables
+//   the host synchronises once per `update_step_size` iterations to apply the reference's batch-average /
+//   convergence rule on the trace rows.
+#include <algorithm>
+#include <cfloat>
+#include <mutex>
+
+#include "engine.cuh"
+#include "kernels_cond.cuh"
+#include "kernels_forward.cuh"
+#include "kernels_fp64.cuh"
+#include "kernels_reduce.cuh"
+
+using namespace mccbn;
+
+namespace mccbn {
+
+enum Scheme { kForward = 0, kAddRemove = 1, kBackward = 2, kBernoulli = 3, kPool = 4 };
+
+static Scheme parse_scheme(const char* s) {
+  if (!s) throw Error(MCCBN_ERR_ARG, "sampling scheme is NULL");
+  const std::string v(s);
+  if (v == "forward") return kForward;
+  if (v == "add-remove") return kAddRemove;
+  if (v == "backward") return kBackward;
+  if (v == "bernoulli") return kBernoulli;
+  if (v == "pool") return kPool;
+  throw Error(MCCBN_ERR_ARG, "unknown sampling scheme: " + v);
+}
+
+static void flatten_or_throw(const int* poset, int p, Poset& P, FlatPoset& f) {
+  if (p < 1 || p > kMaxP) throw Error(MCCBN_ERR_ARG, "p must be in [1, 64]");
+  P = Poset::from_adjacency(poset, p);
+  for (int v = 0; v < p; ++v)
+    if (P.has_edge(v, v)) throw Error(MCCBN_ERR_NOT_ACYCLIC, kMsgNotAcyclic);
+  if (!P.sort()) throw Error(MCCBN_ERR_NOT_ACYCLIC, kMsgNotAcyclic);
+  P.flatten(f);
+}
+
+static void fill_dev_poset(const FlatPoset& f, DevPoset& d) {
+  std::memset(&d, 0, sizeof(d));
+  d.p = f.p;
+  d.n_edges = f.n_edges;
+  int e = 0;
+  for (int k = 0; k < f.p; ++k) {
+    d.ev[k] = (unsigned char)f.topo[k];
+    d.parent_pos[k] = f.parent_pos[k];
+    if (f.p <= kFastMaxP) {
+      d.pstart[k] = (unsigned short)e;
+      for (uint64_t m = f.parent_pos[k]; m; m &= m - 1) d.ppos[e++] = (unsigned char)ctz64(m);
+    }
+  }
+  if (f.p <= kFastMaxP)
+    for (int k = f.p; k < 68; ++k) d.pstart[k] = (unsigned short)e;
+  for (int j = 0; j < f.p; ++j) {
+    d.parent_ev[j] = f.parent_ev[j];
+    d.ancestor_ev[j] = f.ancestor_ev[j];
+  }
+  d.has_children_pos = f.has_children_pos;
+}
+
+}  // namespace mccbn
+
+// ================================================================================================================
+// device-resident problem
+// ================================================================================================================
+struct mccbn_problem {
+  mccbn_ctx* ctx = nullptr;
+  int N = 0, p = 0;
+  int64_t obs_offset = 0, N_global = 0;
+  DevBuf<uint64_t> bits;
+  DevBuf<double> times, weights;
+  DevBuf<DevPoset> posets;
+  DevBuf<DevModel> models;
+  DevBuf<FwdConst> staging;
+  DevBuf<double> part, blk, stats, trace;
+  DevBuf<double> out_w, out_w2, out_dist, out_T;
+  DevBuf<int> out_leff;
+  DevBuf<uint64_t> ball;  // backward scheme: flip masks of the Hamming ball
+  int ball_p = -1, ball_k = -1;
+  int n_cand = 1;
+  int trace_rows = 0;
+  FlatPoset flat[kMaxCand];
+  int iter_host[kMaxCand];
+  uint32_t eval_id[kMaxCand];
+  int fin_blocks = 0;
+
+  int PS() const { return kStatHdr + p; }
+
+  void upload(const int* obs, const double* t, const double* w) {
+    cudaStream_t s = ctx->stream;
+    DevBuf<int> tmp;
+    tmp.ensure((size_t)N * p);
+    MCCBN_CUDA(cudaMemcpyAsync(tmp.ptr, obs, sizeof(int) * (size_t)N * p, cudaMemcpyHostToDevice, s));
+    bits.ensure(N);
+    pack_obs_kernel<<<std::min(1024, (N + 255) / 256), 256, 0, s>>>(tmp.ptr, bits.ptr, N, p);
+    ctx->launches++;
+    times.ensure(N);
+    weights.ensure(N);
+    std::vector<double> ones;
+    if (!w) {
+      ones.assign(N, 1.0);
+      w = ones.data();
+    }
+    std::vector<double> zeros;
+    if (!t) {
+      zeros.assign(N, 0.0);
+      t = zeros.data();
+    }
+    MCCBN_CUDA(cudaMemcpyAsync(times.ptr, t, sizeof(double) * N, cudaMemcpyHostToDevice, s));
+    MCCBN_CUDA(cudaMemcpyAsync(weights.ptr, w, sizeof(double) * N, cudaMemcpyHostToDevice, s));
+    MCCBN_CUDA(cudaStreamSynchronize(s));  // host staging buffers go out of scope
+    posets.ensure(kMaxCand);
+    models.ensure(kMaxCand);
+    staging.ensure(kMaxCand);
+    stats.ensure((size_t)kMaxCand * kMaxPS);
+    for (int c = 0; c < kMaxCand; ++c) {
+      iter_host[c] = 0;
+      eval_id[c] = (uint32_t)c;
+    }
+  }
+
+  // set poset + parameters of candidate slot `c`
+  void set_model(int c, const FlatPoset& f, const double* lambda, double eps, float lambda_s, float max_lambda) {
+    cudaStream_t s = ctx->stream;
+    flat[c] = f;
+    DevPoset dp;
+    fill_dev_poset(f, dp);
+    DevModel dm;
+    std::memset(&dm, 0, sizeof(dm));
+    for (int j = 0; j < p; ++j) dm.lambda[j] = lambda[j];
+    dm.eps = eps;
+    dm.lambda_s = (double)lambda_s;
+    dm.max_lambda = (double)max_lambda;
+    MCCBN_CUDA(cudaMemcpyAsync(posets.ptr + c, &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
+    MCCBN_CUDA(cudaMemcpyAsync(models.ptr + c, &dm, sizeof(dm), cudaMemcpyHostToDevice, s));
+    MCCBN_CUDA(cudaStreamSynchronize(s));  // dp/dm are stack objects
+    iter_host[c] = 0;
+  }
+  // derived tables for slots [0, n) + refresh of the __constant__ copy
+  void prepare(int n) {
+    cudaStream_t s = ctx->stream;
+    prepare_kernel<<<n, 128, 0, s>>>(posets.ptr, models.ptr, staging.ptr);
+    ctx->launches++;
+    if (p <= kFastMaxP)
+      MCCBN_CUDA(cudaMemcpyToSymbolAsync(c_fwd, staging.ptr, sizeof(FwdConst) * n, 0, cudaMemcpyDeviceToDevice, s));
+    n_cand = n;
+  }
+  void ensure_trace(int rows) {
+    if (rows > trace_rows || !trace.ptr) {
+      trace.ensure((size_t)kMaxCand * rows * (p + 2));
+      trace_rows = rows;
+    }
+  }
+
+  template <typename real>
+  void launch_forward(const FwdArgs& a, bool times_given, dim3 grid) {
+    cudaStream_t s = ctx->stream;
+#define MCCBN_FWD(PM)                                                                        \
+  do {                                                                                       \
+    if (times_given)                                                                         \
+      estep_forward_kernel<real, PM, true><<<grid, kFwdBlock, 0, s>>>(a);                    \
+    else                                                                                     \
+      estep_forward_kernel<real, PM, false><<<grid, kFwdBlock, 0, s>>>(a);                   \
+  } while (0)
+    if (sizeof(real) == 8) {
+      MCCBN_FWD(32);
+    } else if (p <= 8) {
+      MCCBN_FWD(8);
+    } else if (p <= 16) {
+      MCCBN_FWD(16);
+    } else if (p <= 24) {
+      MCCBN_FWD(24);
+    } else {
+      MCCBN_FWD(32);
+    }
+#undef MCCBN_FWD
+    ctx->launches++;
+    MCCBN_CUDA(cudaGetLastError());
+  }
+
+  // chunking of the L samples of one observation over warps (see DESIGN.md "work decomposition")
+  void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x) const {
+    const int warps_per_block = kFwdBlock / 32;
+    const int resident_blocks = ctx->sm_count * 4;  // 4 blocks x 4 warps per SM (register bound, see -Xptxas -v)
+    const long long total_warps = (long long)resident_blocks * warps_per_block;
+    long long want_items = total_warps * 24;
+    long long c = (want_items + N - 1) / std::max(1, N);
+    long long cmax = std::max(1, L / 256);
+    c = std::max(1LL, std::min(c, cmax));
+    chunk_len = (int)(((L + c - 1) / c + 31) / 32 * 32);
+    chunks = (L + chunk_len - 1) / chunk_len;
+    long long items = (long long)N * chunks;
+    long long blocks = (items + warps_per_block - 1) / warps_per_block;
+    grid_x = (int)std::max(1LL, std::min(blocks, (long long)resident_blocks));
+  }
+
+  // Enqueue one E-step (+ reduction, allreduce, M-step) for candidate slots [0, n_cand).  No host sync.
+  void enqueue_iteration(Scheme scheme, int L, unsigned neighborhood_dist, bool times_given, uint32_t seed,
+                         int update_params, bool per_obs_out, int precision);
+
+  void run_finalize(int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out) {
+    cudaStream_t s = ctx->stream;
+    FinArgs fa;
+    std::memset(&fa, 0, sizeof(fa));
+    fa.part = part.ptr;
+    fa.models = models.ptr;
+    fa.posets = posets.ptr;
+    fa.weights = weights.ptr;
+    fin_blocks = std::max(1, std::min((N + kFinWarps - 1) / kFinWarps, ctx->sm_count * 2));
+    fa.blk_part = blk.ensure((size_t)kMaxCand * fin_blocks * PS());
+    if (per_obs_out) {
+      fa.w_sum = out_w.ensure(N);
+      fa.w_sum_sq = out_w2.ensure(N);
+      fa.dist = out_dist.ensure(N);
+      fa.Tdiff = out_T.ensure((size_t)N * p);
+      fa.L_eff_out = out_leff.ensure(N);
+    }
+    fa.N = N;
+    fa.chunks = chunks;
+    fa.PS = PS();
+    fa.p = p;
+    fa.n_items = n_items;
+    fa.L_eff = L_eff;
+    fa.uniform_fallback = uniform_fallback;
+    finalize_kernel<<<dim3(fin_blocks, n_cand), kFinBlock, 0, s>>>(fa);
+    reduce_stats_kernel<<<n_cand, 64, 0, s>>>(blk.ptr, stats.ptr, fin_blocks, PS());
+    ctx->launches += 2;
+    MCCBN_CUDA(cudaGetLastError());
+  }
+  void run_mstep(int update_params) {
+    cudaStream_t s = ctx->stream;
+    if (ctx->world > 1)
+      ctx->nccl.check(ctx->nccl.AllReduce(stats.ptr, stats.ptr, (size_t)n_cand * PS(), NcclApi::kDouble, NcclApi::kSum,
+                                          ctx->comm, s),
+                      "ncclAllReduce");
+    mstep_kernel<<<n_cand, 64, 0, s>>>(stats.ptr, posets.ptr, models.ptr, staging.ptr, trace.ptr, p + 2, trace_rows,
+                                       PS(), update_params);
+    ctx->launches++;
+    if (update_params && p <= kFastMaxP)
+      MCCBN_CUDA(
+          cudaMemcpyToSymbolAsync(c_fwd, staging.ptr, sizeof(FwdConst) * n_cand, 0, cudaMemcpyDeviceToDevice, s));
+    MCCBN_CUDA(cudaGetLastError());
+    for (int c = 0; c < n_cand; ++c) iter_host[c]++;
+  }
+
+  void read_model(int c, DevModel& dm) {
+    MCCBN_CUDA(cudaMemcpyAsync(&dm, models.ptr + c, sizeof(dm), cudaMemcpyDeviceToHost, ctx->stream));
+    MCCBN_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+};
+
+#include "engine_impl.cuh"
