@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MCEM E-step hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg2|cfg1|cfg5]
+
+metric   importance samples / second of one EM iteration (E-step + reduction + [allreduce] + M-step), whole job
+workload BASELINE config 3: MCEM.hcbn forward scheme, p=30, N=100,000, L=10,000 (1e9 samples per E-step); the
+         N observations are sharded over the ranks (strong scaling: total work fixed)
+value    inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks
+e2e      the same metric through the reference-facing C ABI call (`mccbn_obs_log_likelihood`: one E-step) with HOST
+         buffers: H2D of the observation matrix and D2H of the result inside the timed region
+roofline the path is instruction-issue bound (Philox INT32 + FP32/SFU), not HBM or tensor bound: see DESIGN.md.
+         peak  = 32-bit random words/s of a pure Philox4x32-10 generator micro-kernel measured live on this GPU
+         achieved = random words/s consumed by the E-step kernel (PMAX/4 Philox blocks per sample)
+cpu_baseline / --impl reference: the CPU oracle (oracle/, a restatement of the reference's OpenMP loop -- the
+         reference itself cannot be compiled in this image) on all host cores over a bounded slice of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (p, N, L, eps_true, sampling, description)
+    "cfg1": (10, 100, 100, 0.01, "forward", "README H-CBN2 example p=10 N=100 L=100"),
+    "cfg2": (16, 10000, 1000, 0.05, "forward", "MCEM.hcbn p=16 N=10,000 L=1,000"),
+    "cfg3": (30, 100000, 10000, 0.05, "forward", "MCEM.hcbn p=30 N=100,000 L=10,000"),
+    "cfg5": (25, 50000, 5000, 0.05, "backward", "MCEM.hcbn backward k=1 p=25 N=50,000 L=5,000 eps=0.05"),
+}
+
+
+def make_problem(name):
+    from mccbn_b200 import synth
+    p, N, L, eps, sampling, desc = CONFIGS[name]
+    cfg = synth.make_config(p, N, eps=eps, seed=10)
+    return cfg, p, N, L, sampling, desc
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def philox_peak_words_per_s(torch):
+    """Pure Philox4x32-10 generator micro-kernel (same round function as the E-step), words/s."""
+    import ctypes as C
+    from mccbn_b200 import _capi
+    lib = _capi.lib()
+    if not hasattr(lib, "mccbn_microbench_philox"):
+        return None
+    lib.mccbn_microbench_philox.restype = C.c_double
+    lib.mccbn_microbench_philox.argtypes = [C.c_void_p, C.c_int]
+    return float(lib.mccbn_microbench_philox(None, 5))
+
+
+def run_reference(args):
+    """Reference arm: the CPU oracle (the reference's OpenMP loop restated) on all host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    orc.build()
+    cfg, p, N, L, sampling, desc = make_problem(args.config)
+    cores = orc.num_threads()
+    kw = dict(L=L, sampling=sampling, thrds=cores)
+    # calibrate a bounded slice: ~args.ref_seconds of CPU work per step
+    n0 = min(N, 4 * cores)
+    t0 = time.perf_counter()
+    orc.obs_log_likelihood(cfg["obs"][:n0], cfg["poset"], cfg["lambdas"], cfg["eps"], seed=1, **kw)
+    dt = time.perf_counter() - t0
+    n_s = int(max(cores, min(N, n0 * args.ref_seconds / max(dt, 1e-6))))
+    n_s -= n_s % cores or 0
+    n_s = max(n_s, cores)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        orc.obs_log_likelihood(cfg["obs"][:n_s], cfg["poset"], cfg["lambdas"], cfg["eps"], seed=2 + it, **kw)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    L_eff = L if sampling != "backward" else (L // (p + 1)) * (p + 1)
+    ms = 1e3 * float(np.mean(times))
+    val = n_s * L_eff / (ms * 1e-3)
+    sample = f"{n_s} of {N} observations x L={L} per step (observations are independent in the reference loop)"
+    line = {
+        "impl": "reference", "metric": "importance samples/sec per E-step", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {desc}", "sampling": sampling, "p": p, "N": N, "L": L},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import mccbn_b200 as mc
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    cfg, p, N, L, sampling, desc = make_problem(args.config)
+    # shard observations contiguously over ranks (strong scaling)
+    lo = (N * rank) // world
+    hi = (N * (rank + 1)) // world
+    obs = np.ascontiguousarray(cfg["obs"][lo:hi])
+    obs = np.asfortranarray(obs)
+
+    ctx = mc.Context(local)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(mc.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        ctx.init_comm(rank, world, bytes(idt.cpu().tolist()))
+
+    pb = mc.Problem(obs, ctx=ctx, obs_offset=lo, N_global=N)
+    pb.set_model(cfg["poset"], cfg["lambda0"], 0.1 if cfg["eps"] != 0.01 else 0.01)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(seed):
+        pb.em_iterations(L, n_iter=1, sampling=sampling, seed=seed, update_params=True)
+
+    with torch.cuda.stream(stream):
+        for w in range(args.warmup):
+            one_step(100 + w)
+        barrier()
+        ctx.kernel_launches(reset=True)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        evs = []
+        barrier()
+        for k in range(args.steps):
+            flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            one_step(1000 + k)
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        launches = ctx.kernel_launches()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    out = pb.read()
+    assert np.all(np.isfinite(out["lambda_"])), "E-step produced non-finite parameters"
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+
+    L_eff = L if sampling != "backward" else (L // (p + 1)) * (p + 1)
+    value = N * L_eff / (ms * 1e-3)
+
+    # ---- end-to-end through the C ABI with host buffers (one E-step per call) ----
+    e2e_steps = max(2, min(args.steps, 5))
+    with torch.cuda.stream(stream):
+        mc.obs_loglikelihood(obs, cfg["poset"], cfg["lambda0"], 0.1, L=L, sampling=sampling, seed=7, ctx=ctx,
+                             obs_offset=lo)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            mc.obs_loglikelihood(obs, cfg["poset"], cfg["lambda0"], 0.1, L=L, sampling=sampling, seed=8 + k, ctx=ctx,
+                                 obs_offset=lo)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    n_loc = hi - lo
+    h2d = n_loc * p * 4 + 2 * n_loc * 8
+    d2h = 1600
+
+    line = {
+        "metric": "importance samples/sec per E-step", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 sampling / f64 reduction", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {desc}", "sampling": sampling, "p": p, "N": N, "L": L,
+                   "sec_per_mcem_iteration": ms * 1e-3, "l2": "256 MiB buffer written between timed iterations",
+                   "parallelism": f"observations sharded over {world} rank(s), 1 allreduce of p+5 doubles / iteration"},
+        "e2e": {"value": N * L_eff / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world, "call": "mccbn_obs_log_likelihood (host buffers, one E-step)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if rank == 0:
+        # roofline of the dominant kernel (estep_forward / estep_conditional): see module docstring
+        pmax = ((p + 3) // 4) * 4
+        words_per_sample = pmax if sampling == "forward" else pmax + 4
+        peak = None
+        try:
+            with torch.cuda.stream(stream):
+                peak = philox_peak_words_per_s(torch)
+        except Exception:
+            peak = None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        ach = value / world * words_per_sample
+        hbm_bytes = (N / world) * (8 + (5 + p) * 8 * 2) + 0.0  # obs word read + partial record write/read per obs
+        line["roofline"] = {
+            "bound": "instruction issue (Philox INT32 + FP32/SFU); not hbm/tensor",
+            "achieved": ach / 1e9, "peak": (peak / 1e9) if peak else None, "unit": "Gword/s (32-bit Philox output)",
+            "frac": (ach / peak) if peak else None, "traffic": None,
+            "peak_source": "pure Philox4x32-10 generator micro-kernel measured live on this GPU",
+            "hbm": {"achieved_GBs": hbm_bytes / (ms * 1e-3) / 1e9, "peak_GBs": peaks.get("hbm_gbs"),
+                    "note": "algorithmic HBM bytes per E-step / step time: memory is not the limiter"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg, p, N, L, sampling, args)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, p, N, L, sampling, args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    orc.build()
+    cores = orc.num_threads()
+    kw = dict(L=L, sampling=sampling, thrds=cores)
+    n0 = min(N, 4 * cores)
+    t0 = time.perf_counter()
+    orc.obs_log_likelihood(cfg["obs"][:n0], cfg["poset"], cfg["lambdas"], cfg["eps"], seed=1, **kw)
+    dt = time.perf_counter() - t0
+    n_s = int(max(cores, min(N, n0 * args.cpu_seconds / max(dt, 1e-6))))
+    n_s = max(cores, n_s - n_s % cores)
+    t0 = time.perf_counter()
+    orc.obs_log_likelihood(cfg["obs"][:n_s], cfg["poset"], cfg["lambdas"], cfg["eps"], seed=2, **kw)
+    dt = time.perf_counter() - t0
+    L_eff = L if sampling != "backward" else (L // (p + 1)) * (p + 1)
+    return {"value": n_s * L_eff / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n_s} of {N} observations x L={L}, one E-step, {dt:.1f} s (oracle = restated reference loop)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=8.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -204,6 +204,11 @@ int mccbn_problem_read(mccbn_problem* pb, double* lambda, double* eps, double* l
 /* the CUDA stream the problem's work is enqueued on (for event timing by the caller) */
 void* mccbn_problem_stream(mccbn_problem* pb);
 
+/* ---- measurement helper ------------------------------------------------------------------------------------ */
+/* 32-bit random words per second of a pure Philox4x32-10 generator kernel on this GPU: the INT32 ceiling against
+ * which bench.py reports the E-step kernels (the path is instruction-issue bound, not HBM/tensor bound). */
+double mccbn_microbench_philox(mccbn_ctx* ctx, int reps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,13 @@
+"""mccbn_b200 -- B200-native (sm_100a CUDA) Monte-Carlo-EM E-step of MC-CBN's H-CBN2 model.
+
+Python mirror of the reference's R entry points (see api.py) over the C ABI of libmccbn_b200.so
+(include/mccbn_b200.h).  Only the hot path named in BASELINE.json is implemented; see DESIGN.md.
+"""
+from . import synth  # noqa: F401
+from ._capi import LIB_PATH, MccbnError  # noqa: F401
+from .api import (Context, Problem, MCEM_hcbn, adaptive_simulated_annealing, compatible_observations,  # noqa: F401
+                  conditional_from_uniforms, device_count, estep_forward_from_times, flatten_poset,
+                  forward_from_times, importance_weight, initialize_lambda, neighbors, nccl_unique_id,
+                  obs_loglikelihood)
+
+__version__ = "0.1.0"

@@ -9,8 +9,8 @@
 //   blk_part   : n_cand x n_blocks x PS doubles  deterministic second-stage partials
 //   stats      : n_cand x PS doubles             [LL, N_eff, D, zero_weight_count, 0, S_0..S_{p-1}] -- the vector
 //                                                 that is all-reduced across GPUs
-// Read-only per-E-step model tables live in __constant__ memory (FwdConst), refreshed by a device-to-device
-// copy after every on-device M-step.
+// The static poset program is a __grid_constant__ kernel parameter (PosetProg); the lambda-derived scales live
+// in __constant__ memory (FwdScale), refreshed by a device-to-device copy after every on-device M-step.
 #pragma once
 #include <cstdint>
 
@@ -54,16 +54,30 @@ struct DevModel {
   int pad;
 };
 
-// __constant__ tables of the forward kernel (per candidate)
-struct FwdConst {
-  float c[kFastMaxP];   // -ln2 / lambda at topological position k:  Z = log2(u) * c
-  float cs;             // -ln2 / lambda_s
+// Static "program" of one poset for the sampling kernels.  It is known to the host, so it travels as a
+// __grid_constant__ kernel parameter: every field is a warp-uniform constant-bank operand at a fixed offset
+// (no per-thread loads, no dynamic indexing).  Nodes are addressed by topological position k; T_k of nodes that
+// have children is staged in a per-thread shared-memory column, row PMAX of that column holds 0 so that
+// absent parents can be loaded unconditionally (max with 0 is the reference's T_max initialisation).
+struct PosetProg {
   int p;
-  unsigned store_mask;  // bit k: T_k has children and must be staged in shared memory
-  int flip;
-  unsigned char ev[kFastMaxP];
-  unsigned short pstart[kFastMaxP + 4];
-  unsigned short poff[kMaxEdgesFast];  // byte offset of the parent's row in the per-thread T staging area
+  unsigned store_mask;   // bit k: T_k has children -> stage it
+  unsigned multi_mask;   // bit k: node k has more than two parents -> rare path below
+  unsigned valid_mask;   // (1 << p) - 1
+  uint2 off[kFastMaxP];            // byte offsets (within the thread's column) of the first two parents' rows
+  unsigned char ev[kFastMaxP];     // event id at position k
+  unsigned parent_mask[kFastMaxP]; // parents of k as a bitmask over positions (compatibility checks)
+  unsigned short xstart[kFastMaxP + 2];  // CSR over `xoff`: third and further parents of node k
+  unsigned short xoff[kMaxEdgesFast];
+};
+
+// lambda-derived scales of the exponential draws, refreshed on the device after every M-step and mirrored into
+// __constant__ memory so that they are immediate constant-bank operands of the FMULs.
+struct FwdScale {
+  float c[kFastMaxP];  // -ln2 / lambda at topological position k:  Z = log2(u) * c
+  float cs;            // -ln2 / lambda_s
+  int flip;            // 1 if eps > 1/2 (weights increase with the Hamming distance)
+  int pad[2];
 };
 
 }  // namespace mccbn

@@ -25,8 +25,9 @@ static BackwardPlan plan_backward(int p, unsigned neighborhood_dist, unsigned L)
 
 struct CondLauncher {
   template <typename real, int PMAX>
-  static void go(const CondArgs& a, bool times_given, int mode, dim3 grid, cudaStream_t s) {
-#define MCCBN_COND(TG, MD) estep_conditional_kernel<real, PMAX, TG, MD><<<grid, kFwdBlock, 0, s>>>(a)
+  static void go(const CondArgs& a, const FlatPoset& f, bool times_given, int mode, int grid, cudaStream_t s) {
+    const PosetProg pg = build_prog(f, PMAX, (int)sizeof(real));
+#define MCCBN_COND(TG, MD) estep_conditional_kernel<real, PMAX, TG, MD><<<grid, kFwdBlock, 0, s>>>(a, pg)
     if (mode == kCondBackward) {
       if (times_given) MCCBN_COND(true, kCondBackward); else MCCBN_COND(false, kCondBackward);
     } else if (mode == kCondBernoulli) {
@@ -38,11 +39,12 @@ struct CondLauncher {
   }
 };
 
-void mccbn_problem::enqueue_iteration(Scheme scheme, int L, unsigned neighborhood_dist, bool times_given,
+void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neighborhood_dist, bool times_given,
                                       uint32_t seed, int update_params, bool per_obs_out, int precision) {
   if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
   cudaStream_t s = ctx->stream;
-  const int iter = iter_host[0];
+  const int iter = iter_host[c];
+  bind_scales(c);
   int chunks = 1, chunk_len = L, grid_x = 1;
   long long n_items = 0;
   int L_eff = L;
@@ -54,8 +56,8 @@ void mccbn_problem::enqueue_iteration(Scheme scheme, int L, unsigned neighborhoo
     std::memset(&a, 0, sizeof(a));
     a.obs_bits = bits.ptr;
     a.times = times.ptr;
-    a.models = models.ptr;
-    a.part = part.ensure((size_t)n_cand * n_items * PS());
+    a.model = models.ptr + c;
+    a.part = part.ensure((size_t)n_items * PS());
     a.N = N;
     a.L = L;
     a.chunks = chunks;
@@ -65,13 +67,12 @@ void mccbn_problem::enqueue_iteration(Scheme scheme, int L, unsigned neighborhoo
     const PhiloxKey key = make_key(seed, (uint32_t)iter, 0u);
     a.key0 = key.k0;
     a.key1 = key.k1;
-    for (int c = 0; c < kMaxCand; ++c) a.cand_ctr[c] = eval_id[c];
+    a.cw = eval_id[c];
     a.PS = PS();
-    const dim3 grid(grid_x, n_cand);
     if (precision == 1)
-      launch_forward<double>(a, times_given, grid);
+      launch_forward<double>(a, flat[c], times_given, grid_x);
     else
-      launch_forward<float>(a, times_given, grid);
+      launch_forward<float>(a, flat[c], times_given, grid_x);
   } else if (scheme == kBackward || scheme == kBernoulli) {
     CondArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -110,9 +111,8 @@ void mccbn_problem::enqueue_iteration(Scheme scheme, int L, unsigned neighborhoo
     n_items = (long long)N * chunks;
     a.obs_bits = bits.ptr;
     a.times = times.ptr;
-    a.models = models.ptr;
-    a.posets = posets.ptr;
-    a.part = part.ensure((size_t)n_cand * n_items * PS());
+    a.model = models.ptr + c;
+    a.part = part.ensure((size_t)n_items * PS());
     a.N = N;
     a.chunks = chunks;
     a.chunk_len = chunk_len;
@@ -121,18 +121,19 @@ void mccbn_problem::enqueue_iteration(Scheme scheme, int L, unsigned neighborhoo
     const PhiloxKey key = make_key(seed, (uint32_t)iter, scheme == kBackward ? 1u : 2u);
     a.key0 = key.k0;
     a.key1 = key.k1;
-    for (int c = 0; c < kMaxCand; ++c) a.cand_ctr[c] = eval_id[c];
+    a.cw = eval_id[c];
     a.PS = PS();
     const int warps_per_block = kFwdBlock / 32;
     long long blocks = (n_items + warps_per_block - 1) / warps_per_block;
-    grid_x = (int)std::max(1LL, std::min<long long>(blocks, (long long)ctx->sm_count * 4));
-    const dim3 grid(grid_x, n_cand);
+    grid_x = (int)std::max(1LL, std::min<long long>(blocks, (long long)ctx->sm_count * 2));
     if (precision == 1) {
-      CondLauncher::go<double, 32>(a, times_given, mode, grid, s);
+      CondLauncher::go<double, 32>(a, flat[c], times_given, mode, grid_x, s);
     } else if (p <= 16) {
-      CondLauncher::go<float, 16>(a, times_given, mode, grid, s);
+      CondLauncher::go<float, 16>(a, flat[c], times_given, mode, grid_x, s);
+    } else if (p <= 24) {
+      CondLauncher::go<float, 24>(a, flat[c], times_given, mode, grid_x, s);
     } else {
-      CondLauncher::go<float, 32>(a, times_given, mode, grid, s);
+      CondLauncher::go<float, 32>(a, flat[c], times_given, mode, grid_x, s);
     }
     ctx->launches++;
     MCCBN_CUDA(cudaGetLastError());
@@ -140,8 +141,8 @@ void mccbn_problem::enqueue_iteration(Scheme scheme, int L, unsigned neighborhoo
     throw Error(MCCBN_ERR_ARG, scheme == kPool ? "sampling scheme 'pool' is not implemented in this build"
                                                : "sampling scheme 'add-remove' is not implemented in this build");
   }
-  run_finalize(chunks, n_items, L_eff, 0, per_obs_out);
-  run_mstep(update_params);
+  run_finalize(c, chunks, n_items, L_eff, 0, per_obs_out);
+  run_mstep(c, update_params);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -207,10 +208,10 @@ static EmResult run_mcem(mccbn_problem& pb, Scheme scheme, unsigned L, const EmC
     }
     const unsigned n_run = std::min(boundary, ctl.max_iter) - iter;
     for (unsigned t = 0; t < n_run; ++t)
-      pb.enqueue_iteration(scheme, (int)L, ctl.neighborhood_dist, times_given, seed, 1, false, precision);
+      pb.enqueue_iteration(0, scheme, (int)L, ctl.neighborhood_dist, times_given, seed, 1, false, precision);
     // one host sync per batch: fetch the trace rows of this batch
     rows.resize((size_t)n_run * stride);
-    MCCBN_CUDA(cudaMemcpyAsync(rows.data(), pb.trace.ptr + (size_t)iter * stride, sizeof(double) * rows.size(),
+    MCCBN_CUDA(cudaMemcpyAsync(rows.data(), pb.trace_of(0) + (size_t)iter * stride, sizeof(double) * rows.size(),
                                cudaMemcpyDeviceToHost, pb.ctx->stream));
     DevModel dm;
     pb.read_model(0, dm);  // synchronises the stream
@@ -434,9 +435,8 @@ int mccbn_problem_set_model(mccbn_problem* pb, const int* poset, const double* l
   Poset P;
   FlatPoset f;
   flatten_or_throw(poset, pb->p, P, f);
-  pb->set_model(0, f, lambda, eps, lambda_s, max_lambda);
-  pb->prepare(1);
   pb->ensure_trace(4096);
+  pb->set_model(0, f, lambda, eps, lambda_s, max_lambda);
   MCCBN_CATCH
 }
 
@@ -447,7 +447,7 @@ int mccbn_problem_em_iterations(mccbn_problem* pb, unsigned L, const char* sampl
   get_ctx(pb->ctx);
   const Scheme sc = parse_scheme(sampling);
   for (int t = 0; t < n_iter; ++t)
-    pb->enqueue_iteration(sc, (int)L, neighborhood_dist, sampling_times_available != 0, (uint32_t)seed, update_params,
+    pb->enqueue_iteration(0, sc, (int)L, neighborhood_dist, sampling_times_available != 0, (uint32_t)seed, update_params,
                           false, 0);
   MCCBN_CATCH
 }
@@ -493,7 +493,6 @@ int mccbn_MCEM_hcbn(mccbn_ctx* c, const double* ilambda, const int* poset, const
   pb.upload(obs, times, weights);
   if (opt) pb.eval_id[0] = opt->stream_id;
   pb.set_model(0, f, lam.data(), eps, lambda_s, max_lambda);
-  pb.prepare(1);
   EmControl ctl;
   ctl.max_iter = max_iter;
   ctl.update_step_size = update_step_size;
@@ -523,10 +522,9 @@ static void single_estep(mccbn_ctx* c, mccbn_problem& pb, const int* obs, const 
   pb.N_global = (opt && opt->N_global > 0) ? opt->N_global : N;
   pb.upload(obs, times, weights);
   if (opt) pb.eval_id[0] = opt->stream_id;
-  pb.set_model(0, f, lambda, eps, lambda_s, 1e6f);
-  pb.prepare(1);
   pb.ensure_trace(1);
-  pb.enqueue_iteration(sc, (int)L, neighborhood_dist, times_available != 0, (uint32_t)seed, 0, per_obs,
+  pb.set_model(0, f, lambda, eps, lambda_s, 1e6f);
+  pb.enqueue_iteration(0, sc, (int)L, neighborhood_dist, times_available != 0, (uint32_t)seed, 0, per_obs,
                        opt ? opt->precision : 0);
 }
 
@@ -591,7 +589,7 @@ int mccbn_importance_weight_genotype(mccbn_ctx* c, const int* genotype, unsigned
   pb.p = p;
   pb.upload(one_obs, &time, nullptr);
   pb.set_model(0, f, lambda, eps, lambda_s, 1e6f);
-  pb.prepare(1);
+  pb.bind_scales(0);
   cudaStream_t s = c->stream;
   DevBuf<double> dZ, dTs;
   DevBuf<int> dD;
@@ -615,11 +613,13 @@ int mccbn_importance_weight_genotype(mccbn_ctx* c, const int* genotype, unsigned
   const bool tg = sampling_times_available != 0;
   const int prec = opt ? opt->precision : 0;
   if (prec == 1) {
-    if (tg) forward_dump_kernel<double, 32, true><<<grid, kFwdBlock, 0, s>>>(a);
-    else forward_dump_kernel<double, 32, false><<<grid, kFwdBlock, 0, s>>>(a);
+    const PosetProg pg = build_prog(f, 32, 8);
+    if (tg) forward_dump_kernel<double, 32, true><<<grid, kFwdBlock, 0, s>>>(a, pg);
+    else forward_dump_kernel<double, 32, false><<<grid, kFwdBlock, 0, s>>>(a, pg);
   } else {
-    if (tg) forward_dump_kernel<float, 32, true><<<grid, kFwdBlock, 0, s>>>(a);
-    else forward_dump_kernel<float, 32, false><<<grid, kFwdBlock, 0, s>>>(a);
+    const PosetProg pg = build_prog(f, 32, 4);
+    if (tg) forward_dump_kernel<float, 32, true><<<grid, kFwdBlock, 0, s>>>(a, pg);
+    else forward_dump_kernel<float, 32, false><<<grid, kFwdBlock, 0, s>>>(a, pg);
   }
   c->launches++;
   MCCBN_CUDA(cudaGetLastError());
@@ -808,9 +808,8 @@ int mccbn_estep_forward_from_times(mccbn_ctx* c, const int* obs, int N, const in
   pb.N = N;
   pb.p = p;
   pb.upload(obs, times, weights);
-  pb.set_model(0, f, lambda, eps, 1.0f, max_lambda);
-  pb.prepare(1);
   pb.ensure_trace(1);
+  pb.set_model(0, f, lambda, eps, 1.0f, max_lambda);
   cudaStream_t s = c->stream;
   DevBuf<double> dZ, dT, dTs, dWt;
   const size_t LP = (size_t)L * p;
@@ -826,11 +825,11 @@ int mccbn_estep_forward_from_times(mccbn_ctx* c, const int* obs, int N, const in
       pb.part.ptr, pb.PS());
   c->launches += 2;
   MCCBN_CUDA(cudaGetLastError());
-  pb.run_finalize(1, N, L, 0, true);
+  pb.run_finalize(0, 1, N, L, 0, true);
   // totals before the M-step overwrites nothing: stats = [LL, N_eff, D, zero, 0, S_k (topological order)]
   std::vector<double> st(pb.PS());
-  MCCBN_CUDA(cudaMemcpyAsync(st.data(), pb.stats.ptr, sizeof(double) * pb.PS(), cudaMemcpyDeviceToHost, s));
-  pb.run_mstep(1);
+  MCCBN_CUDA(cudaMemcpyAsync(st.data(), pb.stats_of(0), sizeof(double) * pb.PS(), cudaMemcpyDeviceToHost, s));
+  pb.run_mstep(0, 1);
   DevModel dm;
   pb.read_model(0, dm);
   if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
@@ -880,6 +879,52 @@ int mccbn_conditional_from_uniforms(mccbn_ctx* c, const int* X, int L, const int
   if (incompatible) MCCBN_CUDA(cudaMemcpyAsync(incompatible, dInc.ptr, sizeof(int) * L, cudaMemcpyDeviceToHost, s));
   MCCBN_CUDA(cudaStreamSynchronize(s));
   MCCBN_CATCH
+}
+
+// ---- roofline helper: pure Philox4x32-10 generation rate of this GPU (the INT32 ceiling of the sampling kernels) --
+}  // extern "C"
+namespace mccbn {
+__global__ void __launch_bounds__(256) philox_peak_kernel(uint32_t* __restrict__ out, int iters, uint32_t k0,
+                                                          uint32_t k1) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t acc = 0u;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    const uint4 r = philox4x32_10((uint32_t)i, tid, 0u, 0u, k0, k1);
+    acc ^= r.x ^ r.y ^ r.z ^ r.w;
+  }
+  out[tid] = acc;
+}
+}  // namespace mccbn
+extern "C" {
+// returns 32-bit random words generated per second (best of `reps` launches), 0 on failure
+double mccbn_microbench_philox(mccbn_ctx* c, int reps) {
+  try {
+    c = get_ctx(c);
+    cudaStream_t s = c->stream;
+    const int blocks = c->sm_count * 8, threads = 256, iters = 4096;
+    DevBuf<uint32_t> out;
+    out.ensure((size_t)blocks * threads);
+    cudaEvent_t e0, e1;
+    MCCBN_CUDA(cudaEventCreate(&e0));
+    MCCBN_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; ++r) {
+      MCCBN_CUDA(cudaEventRecord(e0, s));
+      philox_peak_kernel<<<blocks, threads, 0, s>>>(out.ptr, iters, 1234u, 5678u + r);
+      MCCBN_CUDA(cudaEventRecord(e1, s));
+      MCCBN_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      MCCBN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double words = 4.0 * iters * (double)blocks * threads;
+      if (r > 0) best = std::max(best, words / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return best;
+  } catch (...) {
+    return 0.0;
+  }
 }
 
 // ---- not yet implemented in this build (declared by the header; they fail loudly) ---------------------------------

@@ -28,8 +28,7 @@ enum CondMode { kCondBackward = 0, kCondBernoulli = 1, kCondOtcbn = 2 };
 struct CondArgs {
   const uint64_t* obs_bits;
   const double* times;
-  const DevModel* models;
-  const DevPoset* posets;
+  const DevModel* model;
   const uint64_t* ball;  // backward: flip masks of the Hamming ball (event-id bit order), n_ball entries
   double* part;
   int N, L;              // L = samples per observation actually drawn (backward: reps * n_ball)
@@ -38,7 +37,7 @@ struct CondArgs {
   long long n_items;
   long long obs_offset;
   uint32_t key0, key1;
-  uint32_t cand_ctr[kMaxCand];
+  uint32_t cw;
   int PS;
 };
 
@@ -77,7 +76,7 @@ __device__ __forceinline__ real cond_uniform(const uint4& r, int w) {
 
 // One conditional draw.  Xt = hidden genotype (topological bit order).  Returns log2 of P(Z)/q_Z.
 template <typename real, int PMAX, bool TIMES_GIVEN>
-__device__ __forceinline__ real sample_conditional(const FwdConst& fc, const int p, real* __restrict__ Tcol,
+__device__ __forceinline__ real sample_conditional(const PosetProg& pg, real* __restrict__ Tcol,
                                                    const real* __restrict__ s_lam2, const real* __restrict__ s_inv,
                                                    const uint32_t l, const uint32_t gi, const uint32_t k0,
                                                    const uint32_t k1, const uint32_t cw, const real ts_given,
@@ -91,28 +90,24 @@ __device__ __forceinline__ real sample_conditional(const FwdConst& fc, const int
     Ts = CondMath<real>::z_of(u, (real)1, s_inv[PMAX]);  // Exp(lambda_s)
   }
   real lw2 = (real)0;
+  const unsigned multi_mask = pg.multi_mask;
+  // all PMAX slots run unconditionally; slots k >= p have lam2 = inv = 0 and X_k = 0: they contribute nothing
 #pragma unroll
   for (int k = 0; k < PMAX; ++k) {
-    if (k < p) {
-      const int ui = k + (TIMES_GIVEN ? 0 : 1);
-      if (ui % UPB == 0) r = philox4x32_10(l, gi, (uint32_t)(ui / UPB), cw, k0, k1);
-      const real u = cond_uniform<real>(r, ui % UPB);
-      real m = (real)0;
-      const int e1 = fc.pstart[k + 1];
-      for (int e = fc.pstart[k]; e < e1; ++e)
-        m = max(m, *reinterpret_cast<const real*>(reinterpret_cast<const char*>(Tcol) +
-                                                   (size_t)fc.poff[e] * (sizeof(real) / 4)));
-      const bool xk = (Xt >> k) & 1u;
-      const real a = Ts - m;
-      const real Fx = CondMath<real>::F_of(a, s_lam2[k]);
-      const real F = xk ? Fx : (real)1;
-      const real z = CondMath<real>::z_of(u, F, s_inv[k]);
-      const real base = xk ? m : max(m, Ts);
-      const real t = base + z;
-      if ((fc.store_mask >> k) & 1u) Tcol[k * kFwdBlock] = t;
-      Z[k] = t - m;
-      lw2 += xk ? CondMath<real>::lg2(Fx) : -s_lam2[k] * max(a, (real)0);
-    }
+    const int ui = k + (TIMES_GIVEN ? 0 : 1);
+    if (ui % UPB == 0) r = philox4x32_10(l, gi, (uint32_t)(ui / UPB), cw, k0, k1);
+    const real u = cond_uniform<real>(r, ui % UPB);
+    const real m = parents_max<real>(pg, multi_mask, k, Tcol);
+    const bool xk = (Xt >> k) & 1u;
+    const real a = Ts - m;
+    const real Fx = CondMath<real>::F_of(a, s_lam2[k]);
+    const real F = xk ? Fx : (real)1;
+    const real z = CondMath<real>::z_of(u, F, s_inv[k]);
+    const real base = xk ? m : max(m, Ts);
+    const real t = base + z;
+    Tcol[k * kFwdBlock] = t;
+    Z[k] = t - m;
+    lw2 += xk ? CondMath<real>::lg2(Fx) : -s_lam2[k] * max(a, (real)0);
   }
   Ts_out = Ts;
   return lw2;
@@ -120,37 +115,35 @@ __device__ __forceinline__ real sample_conditional(const FwdConst& fc, const int
 
 // compatibility of a genotype in topological bit order: every mutated event has all parents mutated
 template <int PMAX>
-__device__ __forceinline__ bool compatible_topo(const uint32_t* __restrict__ s_pm, const int p, const uint32_t Xt) {
+__device__ __forceinline__ bool compatible_topo(const PosetProg& pg, const uint32_t Xt) {
   uint32_t bad = 0u;
 #pragma unroll
   for (int k = 0; k < PMAX; ++k)
-    if (k < p) bad |= ((Xt >> k) & 1u) ? (s_pm[k] & ~Xt) : 0u;
+    if (k < pg.p) bad |= ((Xt >> k) & 1u) ? (pg.parent_mask[k] & ~Xt) : 0u;
   return bad == 0u;
 }
 
 template <typename real, int PMAX, bool TIMES_GIVEN, int MODE>
-__global__ void __launch_bounds__(kFwdBlock) estep_conditional_kernel(const CondArgs a) {
-  __shared__ real s_T[PMAX * kFwdBlock];
+__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
+    estep_conditional_kernel(const CondArgs a, const __grid_constant__ PosetProg pg) {
+  __shared__ real s_T[(PMAX + 1) * kFwdBlock];
   __shared__ real s_lam2[PMAX + 1];
   __shared__ real s_inv[PMAX + 1];
-  __shared__ real s_lpyx2[68];     // log2 P(Y|X) by Hamming distance
-  __shared__ uint32_t s_pm[PMAX];  // parent masks, topological bit order
+  __shared__ real s_lpyx2[68];  // log2 P(Y|X) by Hamming distance
 
-  const int cand = blockIdx.y;
-  const FwdConst& fc = c_fwd[cand];
-  const DevModel* __restrict__ mdl = a.models + cand;
-  const DevPoset* __restrict__ pos = a.posets + cand;
-  const int p = fc.p;
+  const DevModel* __restrict__ mdl = a.model;
+  const int p = pg.p;
   const int lane = threadIdx.x & 31;
   constexpr int kWarps = kFwdBlock / 32;
   real* Tcol = s_T + threadIdx.x;
+  Tcol[PMAX * kFwdBlock] = (real)0;  // dummy parent row
   const double kLog2e = 1.44269504088896340736;
 
   for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock) {
-    const double lam = t < p ? mdl->lambda[fc.ev[t]] : mdl->lambda_s;
-    s_lam2[t] = (real)(lam * kLog2e);
-    s_inv[t] = (real)(1.0 / (lam * kLog2e));
-    if (t < PMAX) s_pm[t] = t < p ? (uint32_t)pos->parent_pos[t] : 0u;
+    const double lam = t < p ? mdl->lambda[pg.ev[t]] : mdl->lambda_s;
+    const bool live = t < p || t == PMAX;
+    s_lam2[t] = live ? (real)(lam * kLog2e) : (real)0;
+    s_inv[t] = live ? (real)(1.0 / (lam * kLog2e)) : (real)0;
   }
   for (int d = threadIdx.x; d < 68; d += kFwdBlock) {
     double lp = 0.0;
@@ -168,14 +161,14 @@ __global__ void __launch_bounds__(kFwdBlock) estep_conditional_kernel(const Cond
 
   const long long gw = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * kWarps;
-  const uint32_t cw = a.cand_ctr[cand];
+  const uint32_t cw = a.cw;
   const uint32_t eps_thr = (MODE == kCondBernoulli) ? (uint32_t)fmin(mdl->eps * 4294967296.0, 4294967295.0) : 0u;
 
   for (long long item = gw; item < a.n_items; item += nw) {
     const int i = (int)(item / a.chunks);
     const int ch = (int)(item - (long long)i * a.chunks);
     const uint64_t yw = a.obs_bits[i];
-    const uint32_t yt = to_topo_bits<PMAX>(fc, p, yw);
+    const uint32_t yt = to_topo_bits<PMAX>(pg, yw);
     const real ts_given = TIMES_GIVEN ? (real)a.times[i] : (real)0;
     const uint32_t gi = (uint32_t)(a.obs_offset + i);
 
@@ -188,8 +181,8 @@ __global__ void __launch_bounds__(kFwdBlock) estep_conditional_kernel(const Cond
     auto consume = [&](const uint32_t l, const uint32_t Xt, const int d, const bool valid) {
       real Z[PMAX];
       real Ts;
-      const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(fc, p, Tcol, s_lam2, s_inv, l, gi, a.key0, a.key1,
-                                                                    cw, ts_given, Xt, Z, Ts);
+      const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(pg, Tcol, s_lam2, s_inv, l, gi, a.key0, a.key1, cw,
+                                                                    ts_given, Xt, Z, Ts);
       const real lw2 = lw2s + s_lpyx2[d];
       const bool ok = valid && (lw2 > (real)-1e30);  // F <= 0 (incompatible) gives NaN / -inf -> not ok
       if (ok && lw2 > mref) {  // rare after the first few samples: move the reference up (with head-room)
@@ -208,8 +201,7 @@ __global__ void __launch_bounds__(kFwdBlock) estep_conditional_kernel(const Cond
       awd = fma(wr, (real)d, awd);
       npos += (wr > (real)0) ? (real)1 : (real)0;
 #pragma unroll
-      for (int k = 0; k < PMAX; ++k)
-        if (k < p) acc[k] = fma(wr, Z[k], acc[k]);
+      for (int k = 0; k < PMAX; ++k) acc[k] = fma(wr, Z[k], acc[k]);
     };
 
     double lscale_extra = 0.0;
@@ -217,14 +209,14 @@ __global__ void __launch_bounds__(kFwdBlock) estep_conditional_kernel(const Cond
       // number of compatible genotypes in the whole ball (:525: nrows_sum - #incompatible)
       int n_compat = 0;
       for (int g = lane; g < a.n_ball; g += 32)
-        n_compat += compatible_topo<PMAX>(s_pm, p, to_topo_bits<PMAX>(fc, p, yw ^ a.ball[g]));
+        n_compat += compatible_topo<PMAX>(pg, to_topo_bits<PMAX>(pg, yw ^ a.ball[g]));
       n_compat = __reduce_add_sync(0xffffffffu, n_compat);
       lscale_extra = log((double)n_compat);
       const int g_begin = ch * a.chunk_len, g_end = min(a.n_ball, g_begin + a.chunk_len);
       for (int g = g_begin; g < g_end; ++g) {
         const uint64_t flip = a.ball[g];
-        const uint32_t Xt = to_topo_bits<PMAX>(fc, p, yw ^ flip);
-        if (!compatible_topo<PMAX>(s_pm, p, Xt)) continue;  // warp-uniform
+        const uint32_t Xt = to_topo_bits<PMAX>(pg, yw ^ flip);
+        if (!compatible_topo<PMAX>(pg, Xt)) continue;  // warp-uniform
         const int d = __popcll(flip);
         for (int r0 = 0; r0 < a.reps; r0 += 32) {
           const int rep = r0 + lane;
@@ -249,7 +241,7 @@ __global__ void __launch_bounds__(kFwdBlock) estep_conditional_kernel(const Cond
             }
           }
         }
-        const bool comp = compatible_topo<PMAX>(s_pm, p, Xt);
+        const bool comp = compatible_topo<PMAX>(pg, Xt);
         consume((uint32_t)l, Xt, __popc(Xt ^ yt), (l < l_end) && comp);
       }
     }
@@ -259,7 +251,7 @@ __global__ void __launch_bounds__(kFwdBlock) estep_conditional_kernel(const Cond
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
     const real s = (mref > (real)-1e29) ? CondMath<real>::ex2(mref - mmax) : (real)0;
-    double* out = a.part + ((size_t)cand * a.n_items + item) * a.PS;
+    double* out = a.part + (size_t)item * a.PS;
     double v0 = (double)(aw * s), v1 = (double)(aw2 * s * s), v2 = (double)(awd * s), v3 = (double)npos;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

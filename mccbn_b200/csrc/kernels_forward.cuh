@@ -7,34 +7,37 @@
 //   forward weights      src/mcem_hcbn.cpp:386-388   w = eps^d (1-eps)^(p-d)
 //   per-observation sums src/mcem_hcbn.cpp:683-694   sum w, sum w d, sum w Z_j   (+ sum w^2 for :994)
 //
-// Mapping: one WARP per (observation, chunk of samples); lane = sample; the p waiting times Z_k of the current
-// sample live in registers (static indices: the node loop is unrolled over topological positions), the event
-// times T_k that have children are staged in a per-thread shared-memory column (runtime posets cannot index
-// registers), parent lists come from __constant__ memory (warp-uniform -> ULDC).  Weights are tracked relative to
-// the best (smallest-distance) sample seen so far, r^(d - dref) in fp32 with r = eps/(1-eps) <= 1, a running
-// log-sum-exp: per-lane fp32 partial sums over <= L/32 samples are then reduced across the warp in fp64.
+// Mapping: one WARP per (observation, chunk of samples); lane = sample.  The node loop is fully unrolled over
+// topological positions, so the p waiting times Z_k of the current sample and the p+3 running sums live in
+// registers with static indices.  Event times T_k that have children are staged in a per-thread shared-memory
+// column (a runtime poset cannot index registers); the poset itself is a __grid_constant__ parameter, i.e. the
+// two parent offsets of node k are constant-bank operands and every node costs exactly two LDS + one FMNMX
+// (absent parents read a row that holds 0); nodes with more than two parents take a warp-uniform rare path.
+// Weights are tracked relative to the best (smallest-distance) sample seen so far, r^(d - dref) in fp32 with
+// r = eps/(1-eps) <= 1 -- a running log-sum-exp -- and the per-lane fp32 partial sums over <= L/32 samples are
+// reduced across the warp in fp64.
 #pragma once
 #include "device_types.cuh"
 #include "philox.cuh"
 
 namespace mccbn {
 
-__constant__ FwdConst c_fwd[kMaxCand];
+__constant__ FwdScale c_scale;
 
 struct FwdArgs {
   const uint64_t* obs_bits;  // N
   const double* times;       // N (TIMES_GIVEN only)
-  const DevModel* models;    // n_cand
-  double* part;              // n_cand x n_items x PS
+  const DevModel* model;     // this candidate's parameters (weight tables; fp64 mode: lambda)
+  double* part;              // n_items x PS
   int N;
   int L;
   int chunks;                // chunks per observation
-  int chunk_len;             // samples per chunk (multiple of 32 except the last)
+  int chunk_len;             // samples per chunk (multiple of 32)
   long long n_items;         // N * chunks
   long long obs_offset;      // global index of local observation 0
   uint32_t key0, key1;       // Philox key (seed, iteration tag)
-  uint32_t cand_ctr[kMaxCand];  // Philox counter word 3 per candidate (evaluation id)
-  int PS;                    // stats stride = kStatHdr + p
+  uint32_t cw;               // Philox counter word 3 (evaluation / candidate id)
+  int PS;                    // record stride = kStatHdr + p
 };
 
 template <typename real>
@@ -56,90 +59,130 @@ struct RealTraits<double> {
   }
 };
 
+// per-node exponential scale: fp32 -> constant-bank operand, fp64 -> shared memory (validation mode)
+template <typename real, int PMAX>
+struct ScaleSrc;
+template <int PMAX>
+struct ScaleSrc<float, PMAX> {
+  const float* unused;
+  __device__ __forceinline__ float operator()(int k) const { return k < 0 ? c_scale.cs : c_scale.c[k]; }
+};
+template <int PMAX>
+struct ScaleSrc<double, PMAX> {
+  const double* s;  // [PMAX + 1], last = sampling
+  __device__ __forceinline__ double operator()(int k) const { return s[k < 0 ? PMAX : k]; }
+};
+
+// third and further parents of node k (cold path, kept out of line so the hot block stays compact)
+template <typename real>
+__device__ __noinline__ real parents_extra(const PosetProg& pg, const int k, const real* __restrict__ Tcol, real m) {
+  const char* base = reinterpret_cast<const char*>(Tcol);
+#pragma unroll 1
+  for (int e = pg.xstart[k]; e < pg.xstart[k + 1]; ++e)
+    m = max(m, *reinterpret_cast<const real*>(base + (size_t)pg.xoff[e] * (sizeof(real) / 4)));
+  return m;
+}
+
+// max over the parents of node k (0 without parents): two unconditional loads (absent parents read the dummy
+// row, which holds 0) + a warp-uniform rare path for in-degree > 2
+template <typename real>
+__device__ __forceinline__ real parents_max(const PosetProg& pg, const unsigned multi_mask, const int k,
+                                            const real* __restrict__ Tcol) {
+  const char* base = reinterpret_cast<const char*>(Tcol);
+  const uint2 o = pg.off[k];
+  real m = max(*reinterpret_cast<const real*>(base + o.x), *reinterpret_cast<const real*>(base + o.y));
+  if ((multi_mask >> k) & 1u) m = parents_extra<real>(pg, k, Tcol, m);
+  return m;
+}
+
 // One forward draw for sample l of (global) observation gi.  Z[k] = waiting time of the event at topological
 // position k, X = hidden genotype in topological-position space.  `Tcol` is this thread's staging column
-// (element k at Tcol[k * kFwdBlock]); cexp[k] is the per-node exponential scale (register/constant operand).
-template <typename real, int PMAX, bool TIMES_GIVEN, typename ScaleFn>
-__device__ __forceinline__ void sample_forward(const FwdConst& fc, const int p, real* __restrict__ Tcol,
-                                               const uint32_t l, const uint32_t gi, const uint32_t k0,
-                                               const uint32_t k1, const uint32_t cw, const real ts_given,
-                                               ScaleFn scale, real (&Z)[PMAX], uint32_t& X, real& Ts_out) {
+// (element k at Tcol[k * kFwdBlock]).  All PMAX slots are executed unconditionally (no per-node branch): slots
+// k >= p have scale 0 and no parents, so their T is 0; the caller masks X with pg.valid_mask.
+// Random stream of a sample: node k consumes word k%4 of Philox block k/4 (23 high bits); the sampling time
+// consumes the otherwise unused 9 low bits of the first three words of block 0 (independent of the high bits).
+template <typename real, int PMAX, bool TIMES_GIVEN>
+__device__ __forceinline__ void sample_forward(const PosetProg& pg, real* __restrict__ Tcol, const uint32_t l,
+                                               const uint32_t gi, const uint32_t k0, const uint32_t k1,
+                                               const uint32_t cw, const real ts_given,
+                                               const ScaleSrc<real, PMAX> scale, real (&Z)[PMAX], uint32_t& X,
+                                               real& Ts_out) {
   constexpr int UPB = RealTraits<real>::kUniPerBlock;
+  const unsigned multi_mask = pg.multi_mask;
   uint4 r = make_uint4(0, 0, 0, 0);
   real Ts = ts_given;
-  if (!TIMES_GIVEN) {
-    r = philox4x32_10(l, gi, 0u, cw, k0, k1);
+  if (!TIMES_GIVEN && sizeof(real) == 8) {
+    r = philox4x32_10(l, gi, 255u, cw, k0, k1);
     Ts = RealTraits<real>::expo(r, 0, scale(-1));
   }
   X = 0u;
 #pragma unroll
   for (int k = 0; k < PMAX; ++k) {
-    if (k < p) {
-      const int ui = k + (TIMES_GIVEN ? 0 : 1);  // index of this node's uniform in the sample's stream
-      if (ui % UPB == 0) r = philox4x32_10(l, gi, (uint32_t)(ui / UPB), cw, k0, k1);
-      const real z = RealTraits<real>::expo(r, ui % UPB, scale(k));
-      real tmax = (real)0;
-      const int e1 = fc.pstart[k + 1];
-      for (int e = fc.pstart[k]; e < e1; ++e)
-        tmax = max(tmax, *reinterpret_cast<const real*>(reinterpret_cast<const char*>(Tcol) +
-                                                        (size_t)fc.poff[e] * (sizeof(real) / 4)));
-      const real t = z + tmax;
-      if ((fc.store_mask >> k) & 1u) Tcol[k * kFwdBlock] = t;
-      Z[k] = z;
-      X |= (t <= Ts) ? (1u << k) : 0u;
+    if (k % UPB == 0) {
+      r = philox4x32_10(l, gi, (uint32_t)(k / UPB), cw, k0, k1);
+      if (k == 0 && !TIMES_GIVEN && sizeof(real) == 4) {
+        const uint32_t low = (r.x & 0x1ffu) | ((r.y & 0x1ffu) << 9) | ((r.z & 0x1fu) << 18);
+        Ts = (real)(fast_lg2(2.0f - __uint_as_float(low | 0x3f800000u)) * (float)scale(-1));
+      }
     }
+    const real z = RealTraits<real>::expo(r, k % UPB, scale(k));
+    const real t = z + parents_max<real>(pg, multi_mask, k, Tcol);
+    Tcol[k * kFwdBlock] = t;
+    Z[k] = z;
+    if (t <= Ts) X |= (1u << k);
   }
+  X &= pg.valid_mask;
   Ts_out = Ts;
 }
 
 // observed genotype word (event-id bit order) -> topological-position bit order
 template <int PMAX>
-__device__ __forceinline__ uint32_t to_topo_bits(const FwdConst& fc, const int p, const uint64_t yw) {
+__device__ __forceinline__ uint32_t to_topo_bits(const PosetProg& pg, const uint64_t yw) {
   uint32_t yt = 0u;
 #pragma unroll
   for (int k = 0; k < PMAX; ++k)
-    if (k < p) yt |= (uint32_t)((yw >> fc.ev[k]) & 1ull) << k;
+    if (k < pg.p) yt |= (uint32_t)((yw >> pg.ev[k]) & 1ull) << k;
   return yt;
 }
 
-template <typename real, int PMAX, bool TIMES_GIVEN>
-__global__ void __launch_bounds__(kFwdBlock) estep_forward_kernel(const FwdArgs a) {
-  __shared__ real s_T[PMAX * kFwdBlock];
-  __shared__ real s_rtab[kRtabN];
-  __shared__ real s_scale[PMAX + 1];  // fp64 mode only: -1/lambda per position, [PMAX] = -1/lambda_s
+template <typename real, int PMAX>
+__device__ __forceinline__ void load_scales_fp64(const PosetProg& pg, const DevModel* __restrict__ mdl, real* s_scale) {
+  if (sizeof(real) == 8) {
+    for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock)
+      s_scale[t] = t < pg.p ? (real)(-1.0 / mdl->lambda[pg.ev[t]]) : (t == PMAX ? (real)(-1.0 / mdl->lambda_s) : (real)0);
+  }
+}
 
-  const int cand = blockIdx.y;
-  const FwdConst& fc = c_fwd[cand];
-  const DevModel* __restrict__ mdl = a.models + cand;
-  const int p = fc.p;
+template <typename real, int PMAX, bool TIMES_GIVEN>
+__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 4 : 1)
+    estep_forward_kernel(const FwdArgs a, const __grid_constant__ PosetProg pg) {
+  __shared__ real s_T[(PMAX + 1) * kFwdBlock];  // rows 0..PMAX-1: staged T_k; row PMAX: the dummy row (0)
+  __shared__ real s_rtab[kRtabN];
+  __shared__ real s_scale[PMAX + 1];  // fp64 mode only
+
+  const DevModel* __restrict__ mdl = a.model;
+  const int p = pg.p;
   const int lane = threadIdx.x & 31;
   constexpr int kWarps = kFwdBlock / 32;
   real* Tcol = s_T + threadIdx.x;
+  Tcol[PMAX * kFwdBlock] = (real)0;
 
   for (int t = threadIdx.x; t < kRtabN; t += kFwdBlock)
     s_rtab[t] = sizeof(real) == 4 ? (real)mdl->rtab[t] : (real)mdl->rtab_d[t];
-  if (sizeof(real) == 8) {
-    for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock) {
-      double lam = t < p ? mdl->lambda[fc.ev[t]] : mdl->lambda_s;
-      s_scale[t] = (real)(-1.0 / lam);
-    }
-  }
+  load_scales_fp64<real, PMAX>(pg, mdl, s_scale);
   __syncthreads();
 
-  auto scale = [&](int k) -> real {
-    if (sizeof(real) == 4) return (real)(k < 0 ? fc.cs : fc.c[k]);
-    return s_scale[k < 0 ? PMAX : k];
-  };
+  ScaleSrc<real, PMAX> scale;
+  scale = ScaleSrc<real, PMAX>{reinterpret_cast<const real*>(s_scale)};
 
   const long long gw = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * kWarps;
-  const uint32_t cw = a.cand_ctr[cand];
-  const int flip = fc.flip;
+  const int flip = mdl->flip;
 
   for (long long item = gw; item < a.n_items; item += nw) {
     const int i = (int)(item / a.chunks);
     const int ch = (int)(item - (long long)i * a.chunks);
-    const uint32_t yt = to_topo_bits<PMAX>(fc, p, a.obs_bits[i]);
+    const uint32_t yt = to_topo_bits<PMAX>(pg, a.obs_bits[i]);
     const real ts_given = TIMES_GIVEN ? (real)a.times[i] : (real)0;
     const uint32_t gi = (uint32_t)(a.obs_offset + i);
 
@@ -157,8 +200,8 @@ __global__ void __launch_bounds__(kFwdBlock) estep_forward_kernel(const FwdArgs 
       real Z[PMAX];
       uint32_t X;
       real Ts;
-      sample_forward<real, PMAX, TIMES_GIVEN>(fc, p, Tcol, (uint32_t)l, gi, a.key0, a.key1, cw, ts_given, scale, Z,
-                                              X, Ts);
+      sample_forward<real, PMAX, TIMES_GIVEN>(pg, Tcol, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given, scale, Z, X,
+                                              Ts);
       const int d = __popc(X ^ yt);
       const int de = flip ? p - d : d;  // weights decrease in `de`
       const int dmin = __reduce_min_sync(0xffffffffu, valid ? de : (1 << 19));
@@ -176,12 +219,11 @@ __global__ void __launch_bounds__(kFwdBlock) estep_forward_kernel(const FwdArgs 
       aw2 = fma(wr, wr, aw2);
       awd = fma(wr, (real)d, awd);
 #pragma unroll
-      for (int k = 0; k < PMAX; ++k)
-        if (k < p) acc[k] = fma(wr, Z[k], acc[k]);
+      for (int k = 0; k < PMAX; ++k) acc[k] = fma(wr, Z[k], acc[k]);
     }
 
-    // warp reduction in fp64 (all lanes share dref), lane s writes slot s
-    double* out = a.part + ((size_t)cand * a.n_items + item) * a.PS;
+    // warp reduction in fp64 (all lanes share dref), lane k writes slot kStatHdr + k
+    double* out = a.part + (size_t)item * a.PS;
     double v0 = (double)aw, v1 = (double)aw2, v2 = (double)awd;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -212,7 +254,7 @@ __global__ void __launch_bounds__(kFwdBlock) estep_forward_kernel(const FwdArgs 
 }
 
 // Per-sample dump for ONE observation (the `_importance_weight_genotype` seam, src/mcem_hcbn.cpp:866-912):
-// same Philox stream as the production kernel, writes raw Z (L x p, event-id columns), dist, weight pieces.
+// same Philox stream as the production kernel, writes raw Z (L x p, event-id columns), dist, X, T_s.
 struct FwdDumpArgs {
   uint64_t obs_word;
   double time;
@@ -227,36 +269,31 @@ struct FwdDumpArgs {
 };
 
 template <typename real, int PMAX, bool TIMES_GIVEN>
-__global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpArgs a) {
-  __shared__ real s_T[PMAX * kFwdBlock];
+__global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpArgs a,
+                                                                 const __grid_constant__ PosetProg pg) {
+  __shared__ real s_T[(PMAX + 1) * kFwdBlock];
   __shared__ real s_scale[PMAX + 1];
-  const FwdConst& fc = c_fwd[0];
-  const int p = fc.p;
-  if (sizeof(real) == 8) {
-    for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock) {
-      double lam = t < p ? a.model->lambda[fc.ev[t]] : a.model->lambda_s;
-      s_scale[t] = (real)(-1.0 / lam);
-    }
-  }
+  const int p = pg.p;
+  real* Tcol = s_T + threadIdx.x;
+  Tcol[PMAX * kFwdBlock] = (real)0;
+  load_scales_fp64<real, PMAX>(pg, a.model, s_scale);
   __syncthreads();
-  auto scale = [&](int k) -> real {
-    if (sizeof(real) == 4) return (real)(k < 0 ? fc.cs : fc.c[k]);
-    return s_scale[k < 0 ? PMAX : k];
-  };
-  const uint32_t yt = to_topo_bits<PMAX>(fc, p, a.obs_word);
+  ScaleSrc<real, PMAX> scale;
+  scale = ScaleSrc<real, PMAX>{reinterpret_cast<const real*>(s_scale)};
+  const uint32_t yt = to_topo_bits<PMAX>(pg, a.obs_word);
   for (int l = blockIdx.x * kFwdBlock + threadIdx.x; l < a.L; l += gridDim.x * kFwdBlock) {
     real Z[PMAX];
     uint32_t X;
     real Ts;
-    sample_forward<real, PMAX, TIMES_GIVEN>(fc, p, s_T + threadIdx.x, (uint32_t)l, a.gi, a.key0, a.key1, a.cw,
-                                            (real)a.time, scale, Z, X, Ts);
+    sample_forward<real, PMAX, TIMES_GIVEN>(pg, Tcol, (uint32_t)l, a.gi, a.key0, a.key1, a.cw, (real)a.time, scale, Z,
+                                            X, Ts);
     a.dist_out[l] = __popc(X ^ yt);
     uint32_t xe = 0u;
 #pragma unroll
     for (int k = 0; k < PMAX; ++k)
       if (k < p) {
-        a.Z_out[(size_t)fc.ev[k] * a.L + l] = (double)Z[k];
-        xe |= ((X >> k) & 1u) << fc.ev[k];
+        a.Z_out[(size_t)pg.ev[k] * a.L + l] = (double)Z[k];
+        xe |= ((X >> k) & 1u) << pg.ev[k];
       }
     a.X_out[l] = xe;
     a.Ts_out[l] = (double)Ts;

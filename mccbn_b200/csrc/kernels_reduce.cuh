@@ -19,12 +19,11 @@ constexpr int kFinWarps = kFinBlock / 32;
 constexpr int kMaxPS = kStatHdr + 64;
 
 struct FinArgs {
-  const double* part;       // n_cand x n_items x PS
-  const DevModel* models;   // n_cand
-  const DevPoset* posets;   // n_cand
+  const double* part;       // n_items x PS
+  const DevPoset* poset;    // this candidate
   const double* weights;    // N
-  double* blk_part;         // n_cand x gridDim.x x PS
-  double* w_sum;            // optional per-observation outputs (candidate 0 only)
+  double* blk_part;         // gridDim.x x PS
+  double* w_sum;            // optional per-observation outputs
   double* w_sum_sq;
   double* dist;
   double* Tdiff;            // N x p column-major by event id
@@ -42,15 +41,14 @@ struct FinArgs {
 // One warp per observation, lane s owns record slot s (and s+32): coalesced reads, no shuffles except broadcasts.
 __global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) {
   __shared__ double s_acc[kFinWarps][kMaxPS];
-  const int cand = blockIdx.y;
-  const DevPoset* __restrict__ pos = a.posets + cand;
+  const DevPoset* __restrict__ pos = a.poset;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int PS = a.PS;
   const int sA = lane, sB = lane + 32;
   double accA = 0.0, accB = 0.0;
 
   for (int i = blockIdx.x * kFinWarps + warp; i < a.N; i += gridDim.x * kFinWarps) {
-    const double* rec = a.part + ((size_t)cand * a.n_items + (size_t)i * a.chunks) * PS;
+    const double* rec = a.part + (size_t)i * a.chunks * PS;
     double M = rec[4];
     for (int c = 1; c < a.chunks; ++c) M = fmax(M, rec[(size_t)c * PS + 4]);
     const bool any = M > -INFINITY;
@@ -70,26 +68,26 @@ __global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) {
     const double Leff = a.L_eff > 0 ? (double)a.L_eff : npos;
     if (lane == 0) {
       accA += ok ? wt * (logW - log(Leff)) : 0.0;
-      if (a.w_sum && cand == 0) a.w_sum[i] = w_true;
-      if (a.L_eff_out && cand == 0) a.L_eff_out[i] = (int)npos;
+      if (a.w_sum) a.w_sum[i] = w_true;
+      if (a.L_eff_out) a.L_eff_out[i] = (int)npos;
     } else if (lane == 1) {
       accA += ok ? wt : 0.0;
-      if (a.w_sum_sq && cand == 0) a.w_sum_sq[i] = any ? vA * exp(2.0 * M) : 0.0;
+      if (a.w_sum_sq) a.w_sum_sq[i] = any ? vA * exp(2.0 * M) : 0.0;
     } else if (lane == 2) {
       const double ed = vA / W;
       accA += ok ? wt * ed : 0.0;
-      if (a.dist && cand == 0) a.dist[i] = ed;
+      if (a.dist) a.dist[i] = ed;
     } else if (lane == 3) {
       accA += ok ? 0.0 : 1.0;
     } else if (lane > 4 && sA < PS) {
       const double ez = vA / W;
       accA += ok ? wt * ez : 0.0;
-      if (a.Tdiff && cand == 0) a.Tdiff[(size_t)pos->ev[sA - kStatHdr] * a.N + i] = ez;
+      if (a.Tdiff) a.Tdiff[(size_t)pos->ev[sA - kStatHdr] * a.N + i] = ez;
     }
     if (sB < PS) {
       const double ez = vB / W;
       accB += ok ? wt * ez : 0.0;
-      if (a.Tdiff && cand == 0) a.Tdiff[(size_t)pos->ev[sB - kStatHdr] * a.N + i] = ez;
+      if (a.Tdiff) a.Tdiff[(size_t)pos->ev[sB - kStatHdr] * a.N + i] = ez;
     }
   }
   if (sA < PS) s_acc[warp][sA] = accA;
@@ -98,24 +96,23 @@ __global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) {
   for (int s = threadIdx.x; s < PS; s += kFinBlock) {
     double t = 0.0;
     for (int w = 0; w < kFinWarps; ++w) t += s_acc[w][s];
-    a.blk_part[((size_t)cand * gridDim.x + blockIdx.x) * PS + s] = t;
+    a.blk_part[(size_t)blockIdx.x * PS + s] = t;
   }
 }
 
-// second stage: fixed-order sum of the block partials -> stats[cand][PS]
+// second stage: fixed-order sum of the block partials -> stats[PS]
 __global__ void reduce_stats_kernel(const double* __restrict__ blk_part, double* __restrict__ stats, int n_blocks,
                                     int PS) {
-  const int cand = blockIdx.x;
   for (int s = threadIdx.x; s < PS; s += blockDim.x) {
     double t = 0.0;
-    for (int b = 0; b < n_blocks; ++b) t += blk_part[((size_t)cand * n_blocks + b) * PS + s];
-    stats[(size_t)cand * PS + s] = t;
+    for (int b = 0; b < n_blocks; ++b) t += blk_part[(size_t)b * PS + s];
+    stats[s] = t;
   }
 }
 
-// Derived tables for the next E-step (device function, one block per candidate).
+// Derived tables for the next E-step (device function, run by one block).
 __device__ inline void prepare_tables(const DevPoset* __restrict__ pos, DevModel* __restrict__ mdl,
-                                      FwdConst* __restrict__ fcs) {
+                                      FwdScale* __restrict__ sc) {
   const int p = pos->p;
   const double eps = mdl->eps;
   const double le = log(eps), l1 = log1p(-eps);
@@ -132,37 +129,25 @@ __device__ inline void prepare_tables(const DevPoset* __restrict__ pos, DevModel
     mdl->log_base = flip ? p * le : p * l1;
     mdl->log_r = flip ? (l1 - le) : (le - l1);
   }
-  if (fcs && p <= kFastMaxP) {
+  if (sc && p <= kFastMaxP) {
     const double kLn2 = 0.693147180559945309417;
-    for (int k = threadIdx.x; k < kFastMaxP; k += blockDim.x) {
-      fcs->c[k] = k < p ? (float)(-kLn2 / mdl->lambda[pos->ev[k]]) : 0.f;
-      fcs->ev[k] = k < p ? pos->ev[k] : 0;
-    }
-    for (int k = threadIdx.x; k < kFastMaxP + 4; k += blockDim.x) fcs->pstart[k] = pos->pstart[min(k, p)];
-    for (int e = threadIdx.x; e < kMaxEdgesFast; e += blockDim.x)
-      fcs->poff[e] = e < pos->n_edges ? (unsigned short)(pos->ppos[e] * kFwdBlock * 4) : 0;
+    for (int k = threadIdx.x; k < kFastMaxP; k += blockDim.x)
+      sc->c[k] = k < p ? (float)(-kLn2 / mdl->lambda[pos->ev[k]]) : 0.f;
     if (threadIdx.x == 0) {
-      fcs->cs = (float)(-kLn2 / mdl->lambda_s);
-      fcs->p = p;
-      fcs->store_mask = (unsigned)pos->has_children_pos;
-      fcs->flip = flip;
+      sc->cs = (float)(-kLn2 / mdl->lambda_s);
+      sc->flip = flip;
     }
   }
 }
 
-__global__ void prepare_kernel(const DevPoset* posets, DevModel* models, FwdConst* staging) {
-  prepare_tables(posets + blockIdx.x, models + blockIdx.x, staging ? staging + blockIdx.x : nullptr);
+__global__ void prepare_kernel(const DevPoset* poset, DevModel* model, FwdScale* scale) {
+  prepare_tables(poset, model, scale);
 }
 
-// Stage 6: M-step + trace row + tables for the next iteration.  One block per candidate.
+// Stage 6: M-step + trace row + tables for the next iteration.  One block.
 // stats may have been all-reduced across GPUs in between (identical on every rank => replicated M-step).
-__global__ void mstep_kernel(const double* __restrict__ stats, const DevPoset* posets, DevModel* models,
-                             FwdConst* staging, double* trace, int trace_stride, int max_trace_rows, int PS,
-                             int update_params) {
-  const int cand = blockIdx.x;
-  const DevPoset* pos = posets + cand;
-  DevModel* mdl = models + cand;
-  const double* st = stats + (size_t)cand * PS;
+__global__ void mstep_kernel(const double* __restrict__ st, const DevPoset* pos, DevModel* mdl, FwdScale* scale,
+                             double* trace, int trace_stride, int max_trace_rows, int PS, int update_params) {
   const int p = pos->p;
   const double LL = st[0], Neff = st[1], D = st[2], zero = st[3];
   if (update_params) {
@@ -183,7 +168,7 @@ __global__ void mstep_kernel(const double* __restrict__ stats, const DevPoset* p
   }
   const int it = mdl->iter;
   if (trace && it < max_trace_rows) {
-    double* row = trace + ((size_t)cand * max_trace_rows + it) * trace_stride;
+    double* row = trace + (size_t)it * trace_stride;
     if (threadIdx.x == 0) {
       row[0] = LL;
       row[1] = mdl->eps;
@@ -192,7 +177,7 @@ __global__ void mstep_kernel(const double* __restrict__ stats, const DevPoset* p
   }
   __syncthreads();
   if (threadIdx.x == 0) mdl->iter = it + 1;
-  if (update_params) prepare_tables(pos, mdl, staging ? staging + cand : nullptr);
+  if (update_params) prepare_tables(pos, mdl, scale);
 }
 
 // ---- indexing kernels ---------------------------------------------------------------------------------------

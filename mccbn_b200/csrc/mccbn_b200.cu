@@ -73,21 +73,53 @@ static void fill_dev_poset(const FlatPoset& f, DevPoset& d) {
 // ================================================================================================================
 // device-resident problem
 // ================================================================================================================
+namespace mccbn {
+
+// kernel-parameter program of a poset for a given unroll width and staging element size
+static PosetProg build_prog(const FlatPoset& f, int pmax, int elem_bytes) {
+  PosetProg g;
+  std::memset(&g, 0, sizeof(g));
+  g.p = f.p;
+  g.store_mask = (unsigned)f.has_children_pos;
+  g.valid_mask = f.p >= 32 ? 0xffffffffu : ((1u << f.p) - 1u);
+  const unsigned dummy = (unsigned)pmax * kFwdBlock * elem_bytes;
+  int x = 0;
+  for (int k = 0; k < kFastMaxP; ++k) {
+    g.off[k] = make_uint2(dummy, dummy);
+    g.xstart[k] = (unsigned short)x;
+    if (k >= f.p) continue;
+    g.ev[k] = (unsigned char)f.topo[k];
+    g.parent_mask[k] = (unsigned)f.parent_pos[k];
+    int n = 0;
+    for (uint64_t m = f.parent_pos[k]; m; m &= m - 1, ++n) {
+      const unsigned row = (unsigned)ctz64(m);
+      if (n == 0) g.off[k].x = row * kFwdBlock * elem_bytes;
+      else if (n == 1) g.off[k].y = row * kFwdBlock * elem_bytes;
+      else g.xoff[x++] = (unsigned short)(row * kFwdBlock * 4);
+    }
+    if (n > 2) g.multi_mask |= 1u << k;
+  }
+  g.xstart[kFastMaxP] = g.xstart[kFastMaxP + 1] = (unsigned short)x;
+  for (int k = f.p; k < kFastMaxP; ++k) g.xstart[k] = (unsigned short)x;
+  return g;
+}
+
+}  // namespace mccbn
+
 struct mccbn_problem {
   mccbn_ctx* ctx = nullptr;
   int N = 0, p = 0;
   int64_t obs_offset = 0, N_global = 0;
   DevBuf<uint64_t> bits;
   DevBuf<double> times, weights;
-  DevBuf<DevPoset> posets;
+  DevBuf<DevPoset> posets;    // kMaxCand candidate slots
   DevBuf<DevModel> models;
-  DevBuf<FwdConst> staging;
+  DevBuf<FwdScale> scales;
   DevBuf<double> part, blk, stats, trace;
   DevBuf<double> out_w, out_w2, out_dist, out_T;
   DevBuf<int> out_leff;
   DevBuf<uint64_t> ball;  // backward scheme: flip masks of the Hamming ball
   int ball_p = -1, ball_k = -1;
-  int n_cand = 1;
   int trace_rows = 0;
   FlatPoset flat[kMaxCand];
   int iter_host[kMaxCand];
@@ -95,6 +127,8 @@ struct mccbn_problem {
   int fin_blocks = 0;
 
   int PS() const { return kStatHdr + p; }
+  double* stats_of(int c) { return stats.ptr + (size_t)c * kMaxPS; }
+  double* trace_of(int c) { return trace.ptr + (size_t)c * trace_rows * (p + 2); }
 
   void upload(const int* obs, const double* t, const double* w) {
     cudaStream_t s = ctx->stream;
@@ -121,7 +155,7 @@ struct mccbn_problem {
     MCCBN_CUDA(cudaStreamSynchronize(s));  // host staging buffers go out of scope
     posets.ensure(kMaxCand);
     models.ensure(kMaxCand);
-    staging.ensure(kMaxCand);
+    scales.ensure(kMaxCand);
     stats.ensure((size_t)kMaxCand * kMaxPS);
     for (int c = 0; c < kMaxCand; ++c) {
       iter_host[c] = 0;
@@ -129,7 +163,7 @@ struct mccbn_problem {
     }
   }
 
-  // set poset + parameters of candidate slot `c`
+  // set poset + parameters of candidate slot `c` and derive its device tables
   void set_model(int c, const FlatPoset& f, const double* lambda, double eps, float lambda_s, float max_lambda) {
     cudaStream_t s = ctx->stream;
     flat[c] = f;
@@ -145,15 +179,9 @@ struct mccbn_problem {
     MCCBN_CUDA(cudaMemcpyAsync(models.ptr + c, &dm, sizeof(dm), cudaMemcpyHostToDevice, s));
     MCCBN_CUDA(cudaStreamSynchronize(s));  // dp/dm are stack objects
     iter_host[c] = 0;
-  }
-  // derived tables for slots [0, n) + refresh of the __constant__ copy
-  void prepare(int n) {
-    cudaStream_t s = ctx->stream;
-    prepare_kernel<<<n, 128, 0, s>>>(posets.ptr, models.ptr, staging.ptr);
+    prepare_kernel<<<1, 128, 0, s>>>(posets.ptr + c, models.ptr + c, scales.ptr + c);
     ctx->launches++;
-    if (p <= kFastMaxP)
-      MCCBN_CUDA(cudaMemcpyToSymbolAsync(c_fwd, staging.ptr, sizeof(FwdConst) * n, 0, cudaMemcpyDeviceToDevice, s));
-    n_cand = n;
+    MCCBN_CUDA(cudaGetLastError());
   }
   void ensure_trace(int rows) {
     if (rows > trace_rows || !trace.ptr) {
@@ -163,25 +191,27 @@ struct mccbn_problem {
   }
 
   template <typename real>
-  void launch_forward(const FwdArgs& a, bool times_given, dim3 grid) {
+  void launch_forward(const FwdArgs& a, const FlatPoset& f, bool times_given, int grid) {
     cudaStream_t s = ctx->stream;
-#define MCCBN_FWD(PM)                                                                        \
-  do {                                                                                       \
-    if (times_given)                                                                         \
-      estep_forward_kernel<real, PM, true><<<grid, kFwdBlock, 0, s>>>(a);                    \
-    else                                                                                     \
-      estep_forward_kernel<real, PM, false><<<grid, kFwdBlock, 0, s>>>(a);                   \
+#define MCCBN_FWD(PM)                                                              \
+  do {                                                                             \
+    const PosetProg pg = build_prog(f, PM, (int)sizeof(real));                     \
+    if (times_given)                                                               \
+      estep_forward_kernel<real, PM, true><<<grid, kFwdBlock, 0, s>>>(a, pg);      \
+    else                                                                           \
+      estep_forward_kernel<real, PM, false><<<grid, kFwdBlock, 0, s>>>(a, pg);     \
   } while (0)
-    if (sizeof(real) == 8) {
+    if constexpr (sizeof(real) == 8) {
       MCCBN_FWD(32);
-    } else if (p <= 8) {
-      MCCBN_FWD(8);
-    } else if (p <= 16) {
-      MCCBN_FWD(16);
-    } else if (p <= 24) {
-      MCCBN_FWD(24);
     } else {
-      MCCBN_FWD(32);
+      if (p <= 4) MCCBN_FWD(4);
+      else if (p <= 8) MCCBN_FWD(8);
+      else if (p <= 12) MCCBN_FWD(12);
+      else if (p <= 16) MCCBN_FWD(16);
+      else if (p <= 20) MCCBN_FWD(20);
+      else if (p <= 24) MCCBN_FWD(24);
+      else if (p <= 28) MCCBN_FWD(28);
+      else MCCBN_FWD(32);
     }
 #undef MCCBN_FWD
     ctx->launches++;
@@ -191,7 +221,7 @@ struct mccbn_problem {
   // chunking of the L samples of one observation over warps (see DESIGN.md "work decomposition")
   void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x) const {
     const int warps_per_block = kFwdBlock / 32;
-    const int resident_blocks = ctx->sm_count * 4;  // 4 blocks x 4 warps per SM (register bound, see -Xptxas -v)
+    const int resident_blocks = ctx->sm_count * 4;  // 4 blocks x 4 warps per SM (128 registers per thread)
     const long long total_warps = (long long)resident_blocks * warps_per_block;
     long long want_items = total_warps * 24;
     long long c = (want_items + N - 1) / std::max(1, N);
@@ -204,20 +234,19 @@ struct mccbn_problem {
     grid_x = (int)std::max(1LL, std::min(blocks, (long long)resident_blocks));
   }
 
-  // Enqueue one E-step (+ reduction, allreduce, M-step) for candidate slots [0, n_cand).  No host sync.
-  void enqueue_iteration(Scheme scheme, int L, unsigned neighborhood_dist, bool times_given, uint32_t seed,
+  // Enqueue one E-step (+ reduction, allreduce, M-step) for candidate slot c.  No host sync.
+  void enqueue_iteration(int c, Scheme scheme, int L, unsigned neighborhood_dist, bool times_given, uint32_t seed,
                          int update_params, bool per_obs_out, int precision);
 
-  void run_finalize(int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out) {
+  void run_finalize(int c, int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out) {
     cudaStream_t s = ctx->stream;
     FinArgs fa;
     std::memset(&fa, 0, sizeof(fa));
     fa.part = part.ptr;
-    fa.models = models.ptr;
-    fa.posets = posets.ptr;
+    fa.poset = posets.ptr + c;
     fa.weights = weights.ptr;
     fin_blocks = std::max(1, std::min((N + kFinWarps - 1) / kFinWarps, ctx->sm_count * 2));
-    fa.blk_part = blk.ensure((size_t)kMaxCand * fin_blocks * PS());
+    fa.blk_part = blk.ensure((size_t)fin_blocks * PS());
     if (per_obs_out) {
       fa.w_sum = out_w.ensure(N);
       fa.w_sum_sq = out_w2.ensure(N);
@@ -232,25 +261,28 @@ struct mccbn_problem {
     fa.n_items = n_items;
     fa.L_eff = L_eff;
     fa.uniform_fallback = uniform_fallback;
-    finalize_kernel<<<dim3(fin_blocks, n_cand), kFinBlock, 0, s>>>(fa);
-    reduce_stats_kernel<<<n_cand, 64, 0, s>>>(blk.ptr, stats.ptr, fin_blocks, PS());
+    finalize_kernel<<<fin_blocks, kFinBlock, 0, s>>>(fa);
+    reduce_stats_kernel<<<1, 64, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS());
     ctx->launches += 2;
     MCCBN_CUDA(cudaGetLastError());
   }
-  void run_mstep(int update_params) {
+  void run_mstep(int c, int update_params) {
     cudaStream_t s = ctx->stream;
     if (ctx->world > 1)
-      ctx->nccl.check(ctx->nccl.AllReduce(stats.ptr, stats.ptr, (size_t)n_cand * PS(), NcclApi::kDouble, NcclApi::kSum,
+      ctx->nccl.check(ctx->nccl.AllReduce(stats_of(c), stats_of(c), (size_t)PS(), NcclApi::kDouble, NcclApi::kSum,
                                           ctx->comm, s),
                       "ncclAllReduce");
-    mstep_kernel<<<n_cand, 64, 0, s>>>(stats.ptr, posets.ptr, models.ptr, staging.ptr, trace.ptr, p + 2, trace_rows,
-                                       PS(), update_params);
+    mstep_kernel<<<1, 64, 0, s>>>(stats_of(c), posets.ptr + c, models.ptr + c, scales.ptr + c,
+                                  trace.ptr ? trace_of(c) : nullptr, p + 2, trace_rows, PS(), update_params);
     ctx->launches++;
-    if (update_params && p <= kFastMaxP)
-      MCCBN_CUDA(
-          cudaMemcpyToSymbolAsync(c_fwd, staging.ptr, sizeof(FwdConst) * n_cand, 0, cudaMemcpyDeviceToDevice, s));
     MCCBN_CUDA(cudaGetLastError());
-    for (int c = 0; c < n_cand; ++c) iter_host[c]++;
+    iter_host[c]++;
+  }
+  // make candidate c's scales the __constant__ operands of the next sampling kernel (stream-ordered)
+  void bind_scales(int c) {
+    if (p <= kFastMaxP)
+      MCCBN_CUDA(cudaMemcpyToSymbolAsync(c_scale, scales.ptr + c, sizeof(FwdScale), 0, cudaMemcpyDeviceToDevice,
+                                         ctx->stream));
   }
 
   void read_model(int c, DevModel& dm) {

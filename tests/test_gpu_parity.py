@@ -1,0 +1,304 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tiers:
+  T-int  bit-exact     : flattening, compatibility, counts, hidden genotypes X, Hamming distances, ball enumeration
+  T-fp   <= 1e-10 rel. : weights, sum w, E[d], E[Z], log q, obs_llhood, M-step outputs from identical supplied draws
+  T-stat 3 s.e.        : independent RNG streams (Philox vs mt19937): P(Y), E[d], E[Z], converged lambda/eps/llhood,
+                         plus the model-derived exact answers K1/K2
+"""
+import math
+
+import numpy as np
+import pytest
+
+import exact
+import mccbn_b200 as mc
+from mccbn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL_FP = 1e-10  # fp64 tier tolerance stated by BASELINE.json north_star
+
+
+def _cfg(p=8, N=60, eps=0.08, seed=3, density=0.3):
+    return synth.make_config(p, N, eps=eps, seed=seed, density=density)
+
+
+# ---------------------------------------------------------------- T-int -------------------------------------------
+@pytest.mark.parametrize("p", [1, 5, 16, 30, 32])
+def test_forward_from_times_bit_exact(oracle, p):
+    rng = np.random.default_rng(p)
+    poset = synth.random_poset(p, 0.25, rng=rng)
+    lam = rng.uniform(0.3, 3.0, p)
+    L = 777  # ragged: not a multiple of any block size
+    Z = rng.exponential(1.0, (L, p)) / lam
+    Ts = rng.exponential(1.0, L)
+    y = rng.integers(0, 2, p)
+    a = mc.forward_from_times(y, poset, 0.07, Z, Ts)
+    b = oracle.forward_from_times(y, poset, 0.07, Z, Ts)
+    assert np.array_equal(a["T_sum"], b["T_sum"])  # pure fp64 add/max: bit-exact
+    assert np.array_equal(a["X"], b["X"])
+    assert np.array_equal(a["dist"], b["dist"])
+    assert np.array_equal(a["w"], b["w"])  # host-built pow table == reference pow
+
+
+def test_compatibility_and_counts_bit_exact(oracle):
+    rng = np.random.default_rng(0)
+    for p, N in ((3, 1), (12, 1000), (30, 5000), (40, 300), (64, 257)):
+        poset = synth.random_poset(p, 0.2, rng=rng)
+        obs = rng.integers(0, 2, (N, p)).astype(np.int32)
+        obs[: N // 3] = synth.sample_genotypes(max(N // 3, 1), poset, 1.0, rng.uniform(0.5, 2, p), 0.0, rng)[
+            "obs_events"][: N // 3]
+        r = mc.compatible_observations(obs, poset)
+        assert np.array_equal(r["compatible"], oracle.compatible_observations(obs, poset))
+        assert r["num_compatible"] == oracle.num_compatible_observations(obs, poset)
+        assert r["num_incompatible_events"] == oracle.num_incompatible_events(obs, poset)
+
+
+def test_initialize_lambda_matches_oracle(oracle):
+    for seed in range(3):
+        c = synth.make_config(12, 500, eps=0.05, seed=seed, density=0.25)
+        lam, eps = mc.initialize_lambda(c["obs"], c["poset"], lambda_s=1.0)
+        lam_o, eps_o = oracle.initialize_lambda(c["obs"], c["poset"], lambda_s=1.0)
+        assert np.array_equal(lam, lam_o)  # integer counts + the same float division
+        assert eps == eps_o
+
+
+def test_cyclic_poset_error():
+    poset = np.zeros((4, 4), np.int32)
+    poset[0, 1] = poset[1, 2] = poset[2, 0] = 1
+    with pytest.raises(mc.MccbnError) as e:
+        mc.obs_loglikelihood(np.zeros((3, 4), np.int32), poset, np.ones(4), 0.1, L=32, seed=1)
+    assert e.value.code == 1 and "acyclic" in str(e.value)
+
+
+# ---------------------------------------------------------------- T-fp --------------------------------------------
+@pytest.mark.parametrize("p,N,L,times", [(6, 15, 500, False), (16, 200, 1000, False), (30, 64, 333, True),
+                                         (32, 7, 64, False)])
+def test_estep_from_times_fp64(oracle, p, N, L, times):
+    c = _cfg(p=p, N=N, seed=p + N)
+    rng = np.random.default_rng(L)
+    Z = rng.exponential(1.0, (L, p)) / c["lambdas"]
+    Ts = rng.exponential(1.0, L)
+    t = c["times"] if times else None
+    wts = rng.uniform(0.5, 2.0, N)
+    a = mc.estep_forward_from_times(c["obs"], c["poset"], c["lambdas"], 0.1, Z, Ts, weights=wts, times=t)
+    b = oracle.estep_forward_from_times(c["obs"], c["poset"], c["lambdas"], 0.1, Z, Ts, weights=wts, times=t)
+    for k in ("w", "w_sqrt", "dist", "Tdiff", "Tdiff_colsum", "lambda_new"):
+        np.testing.assert_allclose(a[k], b[k], rtol=RTOL_FP, atol=1e-300, err_msg=k)
+    for k in ("obs_llhood", "expected_dist", "N_eff", "eps_new"):
+        assert abs(a[k] - b[k]) <= RTOL_FP * abs(b[k]), (k, a[k], b[k])
+
+
+def test_conditional_from_uniforms_fp64(oracle):
+    for p in (7, 25):
+        c = _cfg(p=p, N=10, seed=40 + p)
+        rng = np.random.default_rng(p)
+        L = 600
+        X = synth.sample_genotypes(L, c["poset"], 1.0, c["lambdas"], 0.0, rng)["hidden_genotypes"].copy()
+        X[L // 2:] = rng.integers(0, 2, (L - L // 2, p))  # second half: arbitrary (mostly incompatible) genotypes
+        u = rng.random((L, p))
+        Ts = rng.exponential(1.0, L) + 0.01
+        a = mc.conditional_from_uniforms(X, c["poset"], c["lambdas"], u, Ts)
+        b = oracle.conditional_from_uniforms(X, c["poset"], c["lambdas"], u, Ts)
+        assert np.array_equal(a["incompatible"], b["incompatible"])  # bit-exact flag
+        ok = b["incompatible"] == 0
+        assert ok.sum() > L // 3
+        np.testing.assert_allclose(a["Tdiff"][ok], b["Tdiff"][ok], rtol=RTOL_FP, atol=1e-14)
+        np.testing.assert_allclose(a["log_q"][ok], b["log_q"][ok], rtol=RTOL_FP, atol=1e-12)
+        np.testing.assert_allclose(a["log_pz"][ok], b["log_pz"][ok], rtol=RTOL_FP, atol=1e-12)
+
+
+# ----------------------------------------------------- production kernel vs its own per-sample dump ---------------
+@pytest.mark.parametrize("p,times", [(5, False), (13, True), (20, False), (30, False), (32, True)])
+def test_production_reduction_matches_dump(p, times):
+    """The Philox E-step kernel and the per-sample dump kernel share the stream (seed, iteration 0, observation i,
+    sample l): reducing the dump in numpy (fp64) must reproduce the kernel's per-observation statistics up to the
+    fp32 accumulation error of the fast path."""
+    c = _cfg(p=p, N=9, seed=p, density=0.2)
+    L = 700
+    eps = 0.07
+    t = c["times"] if times else None
+    r = mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], eps, time=t, seed=11)
+    for i in (0, 4, 8):
+        d = mc.importance_weight(c["obs"][i], L, c["poset"], c["lambdas"], eps, time=None if t is None else t[i],
+                                 seed=11, obs_offset=i)
+        w = d["w"]
+        assert d["Tdiff"].shape == (L, p) and (d["Tdiff"] >= 0).all()
+        assert abs(r["w"][i] - w.sum()) <= 2e-5 * w.sum()
+        assert abs(r["w_sqrt"][i] - (w * w).sum()) <= 1e-4 * (w * w).sum()
+        assert abs(r["dist"][i] - (w * d["dist"]).sum() / w.sum()) <= 1e-4 * max(1.0, r["dist"][i])
+        np.testing.assert_allclose(r["Tdiff"][i], (d["Tdiff"] * w[:, None]).sum(axis=0) / w.sum(), rtol=2e-4)
+
+
+def test_dump_marginals_are_exponential():
+    # raw waiting times of the Philox path: Z_j ~ Exp(lambda_j) (mean and variance), independent of the poset
+    c = _cfg(p=12, N=1, seed=5)
+    L = 200000
+    d = mc.importance_weight(c["obs"][0], L, c["poset"], c["lambdas"], 0.05, seed=99)
+    m = d["Tdiff"].mean(axis=0) * c["lambdas"]
+    v = d["Tdiff"].var(axis=0) * c["lambdas"] ** 2
+    assert np.abs(m - 1).max() < 5 / math.sqrt(L)
+    assert np.abs(v - 1).max() < 0.03
+    # different observation index / seed => different stream
+    d2 = mc.importance_weight(c["obs"][0], 1000, c["poset"], c["lambdas"], 0.05, seed=99, obs_offset=1)
+    assert not np.array_equal(d2["Tdiff"], d["Tdiff"][:1000])
+
+
+def test_shard_invariance():
+    """Philox counters use global observation indices: scoring a shard with obs_offset reproduces the rows of the
+    full run (up to fp32 summation order, which depends on the chunking chosen for N)."""
+    c = _cfg(p=10, N=300, seed=8)
+    full = mc.importance_weight(c["obs"], 640, c["poset"], c["lambdas"], 0.05, seed=5)
+    part = mc.importance_weight(c["obs"][100:220], 640, c["poset"], c["lambdas"], 0.05, seed=5, obs_offset=100)
+    np.testing.assert_allclose(part["w"], full["w"][100:220], rtol=1e-5)
+    np.testing.assert_allclose(part["Tdiff"], full["Tdiff"][100:220], rtol=1e-4)
+
+
+# ---------------------------------------------------------------- T-stat ------------------------------------------
+def _mean_se(fn, seeds):
+    v = np.array([fn(s) for s in seeds])
+    return v.mean(axis=0), v.std(axis=0, ddof=1) / math.sqrt(len(seeds))
+
+
+@pytest.mark.parametrize("sampling,kw,precision", [("forward", {}, 0), ("forward", {}, 1),
+                                                   ("backward", dict(neighborhood_dist=6), 0),
+                                                   ("backward", dict(neighborhood_dist=6), 1)])
+def test_k2_exact_probabilities(sampling, kw, precision):
+    """IS estimate of P(Y_i) and E[d | Y_i] against the exact lattice recursion (K2)."""
+    c = synth.make_config(6, 12, eps=0.1, seed=11, density=0.3)
+    p = 6
+    px = exact.genotype_probs_exp(c["poset"], c["lambdas"], 1.0)
+    ex = np.array([exact.obs_prob_and_dist(px, exact.mask_of(c["obs"][i]), 0.1, p) for i in range(12)])
+    L = 4096
+
+    def est(seed):
+        r = mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.1, sampling=sampling, seed=seed,
+                                 precision=precision, **kw)
+        Leff = r["L_eff"] if sampling == "backward" else L
+        return np.concatenate([r["w"] / Leff, r["dist"]])
+
+    mean, se = _mean_se(est, range(100, 124))
+    z = (mean - np.concatenate([ex[:, 0], ex[:, 1]])) / np.maximum(se, 1e-300)
+    assert np.abs(z).max() < 4.0, z
+
+
+def test_k1_empty_poset_given_times():
+    p, N = 5, 8
+    rng = np.random.default_rng(8)
+    lam = rng.uniform(0.5, 2.0, p)
+    poset = np.zeros((p, p), np.int32)
+    obs = rng.integers(0, 2, (N, p)).astype(np.int32)
+    times = rng.uniform(0.3, 2.0, N)
+    ex = np.array([exact.k1_empty_poset(obs[i], lam, 0.05, times[i]) for i in range(N)])
+
+    def est(seed):
+        r = mc.importance_weight(obs, 4096, poset, lam, 0.05, time=times, seed=seed)
+        return np.concatenate([r["w"] / 4096, r["dist"]])
+
+    mean, se = _mean_se(est, range(300, 324))
+    assert np.abs((mean - np.concatenate([ex[:, 0], ex[:, 1]])) / se).max() < 4.0
+
+
+@pytest.mark.parametrize("sampling,kw", [("forward", {}), ("backward", {}), ("bernoulli", {})])
+def test_estep_statistics_match_oracle(oracle, sampling, kw):
+    """Per-observation sum w / L_eff, E[d], E[Z] from independent streams: GPU (Philox) vs oracle (mt19937)."""
+    c = synth.make_config(8, 10, eps=0.1, seed=17, density=0.3)
+    L = 2048 if sampling != "backward" else 9 * 200
+
+    def run(fn):
+        def est(seed):
+            r = fn(seed)
+            Leff = r["L_eff"] if sampling == "backward" else L
+            good = r["w"] > 0
+            return np.concatenate([np.where(good, r["w"] / np.maximum(Leff, 1), 0.0), r["dist"], r["Tdiff"].ravel()])
+        return est
+
+    g = run(lambda s: mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.1, sampling=sampling, seed=s, **kw))
+    o = run(lambda s: oracle.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.1, sampling=sampling, seed=s,
+                                               thrds=4, **kw))
+    mg, sg = _mean_se(g, range(1, 25))
+    mo, so = _mean_se(o, range(1001, 1025))
+    z = (mg - mo) / np.sqrt(sg ** 2 + so ** 2 + 1e-300)
+    assert np.nanmax(np.abs(z)) < 4.5, (sampling, np.nanmax(np.abs(z)))
+
+
+@pytest.mark.parametrize("sampling,L", [("forward", 300), ("backward", 9 * 40)])
+def test_mcem_fixed_point_matches_oracle(oracle, sampling, L):
+    """Converged lambda, eps and observed log-likelihood from independent RNG streams agree with the reference
+    restatement within 3 Monte-Carlo standard errors (north_star), s.e. from replicate seeds on both sides."""
+    c = synth.make_config(8, 300, eps=0.05, seed=23, density=0.3)
+    kw = dict(L=L, eps=0.1, sampling=sampling, max_iter=60, update_step_size=20, tol=1e-3)
+
+    def pack(r):
+        return np.concatenate([r["lambda_"], [r["eps"], r["llhood"]]])
+
+    g = np.array([pack(mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], seed=s, **kw)) for s in range(1, 21)])
+    o = np.array([pack(oracle.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], seed=s, thrds=oracle.num_threads(), **kw))
+                  for s in range(101, 121)])
+    se = np.sqrt(g.var(axis=0, ddof=1) / g.shape[0] + o.var(axis=0, ddof=1) / o.shape[0])
+    z = (g.mean(axis=0) - o.mean(axis=0)) / se
+    assert np.abs(z).max() < 3.0 * 1.25, z  # 3 s.e. with head-room for 10 simultaneous comparisons
+    # recovery (reference validation method): estimates are close to the generating parameters
+    rel = np.abs(g.mean(axis=0)[:8] - c["lambdas"]).mean() / c["lambdas"].mean()
+    assert rel < 0.35 and abs(g.mean(axis=0)[8] - 0.05) < 0.03
+
+
+def test_mcem_trace_and_batch_average_rule():
+    c = synth.make_config(6, 100, eps=0.05, seed=2, density=0.3)
+    r = mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], L=128, eps=0.1, max_iter=50, update_step_size=20, seed=4,
+                     return_trace=True)
+    n = r["n_iter"]
+    assert n in (20, 40, 50) and r["trace"].shape == (n, 8)
+    last = r["trace"][40:50] if n == 50 else r["trace"][n - 20:n]
+    np.testing.assert_allclose(r["lambda_"], last[:, 2:].mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(r["eps"], last[:, 1].mean(), rtol=1e-12)
+    np.testing.assert_allclose(r["llhood"], last[:, 0].mean(), rtol=1e-12)
+    # reproducible for a fixed seed (deterministic reductions), different for another seed
+    r2 = mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], L=128, eps=0.1, max_iter=50, update_step_size=20, seed=4)
+    assert np.array_equal(r["lambda_"], r2["lambda_"]) and r["llhood"] == r2["llhood"]
+    r3 = mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], L=128, eps=0.1, max_iter=50, update_step_size=20, seed=5)
+    assert r3["llhood"] != r["llhood"]
+
+
+def test_zero_weight_error():
+    c = _cfg(p=6, N=5)
+    with pytest.raises(mc.MccbnError) as e:  # backward with L < 1 + p: no samples (src/mcem_hcbn.cpp:362-363)
+        mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], L=3, eps=0.1, sampling="backward", max_iter=2,
+                     update_step_size=1, seed=1)
+    assert e.value.code == 2 and "weight 0" in str(e.value)
+
+
+def test_extreme_epsilon_values():
+    c = _cfg(p=10, N=20, seed=6)
+    for eps in (1e-12, 0.5, 0.9):  # tiny eps: weights span hundreds of orders of magnitude; eps > 1/2: flipped table
+        ll = mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], eps, L=2048, seed=3)
+        assert np.isfinite(ll)
+    px = exact.genotype_probs_exp(c["poset"], c["lambdas"], 1.0)
+    ex = sum(math.log(exact.obs_prob_and_dist(px, exact.mask_of(c["obs"][i]), 0.9, 10)[0]) for i in range(20))
+    est = np.array([mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], 0.9, L=8192, seed=s) for s in range(16)])
+    assert abs(est.mean() - ex) < 5 * est.std(ddof=1) / 4 + 0.05
+
+
+# ---------------------------------------------------------------- full-size properties ----------------------------
+def test_full_size_config2_properties():
+    """BASELINE config 2 (p=16, N=10,000, L=1,000): size-independent properties on the full problem."""
+    c = synth.make_config(16, 10000, eps=0.05, seed=10)
+    r = mc.importance_weight(c["obs"], 1000, c["poset"], c["lambdas"], 0.05, seed=1)
+    assert np.all(r["w"] > 0) and np.all(np.isfinite(r["Tdiff"]))
+    assert np.all(r["dist"] >= 0) and np.all(r["dist"] <= 16)
+    # Cauchy-Schwarz: (sum w)^2 <= L sum w^2  (ESS <= L), and ESS >= 1
+    ess = r["w"] ** 2 / r["w_sqrt"]
+    assert np.all(ess <= 1000 * (1 + 1e-6)) and np.all(ess >= 1 - 1e-6)
+    # identical genotypes get statistically identical estimates; exact duplicates of the weight table bounds
+    lo, hi = 0.05 ** 16, 0.95 ** 16
+    assert np.all(r["w"] / 1000 >= lo * (1 - 1e-6)) and np.all(r["w"] / 1000 <= hi * (1 + 1e-6))
+    # observed log-likelihood equals the sum of per-observation logs
+    ll = mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], 0.05, L=1000, seed=1)
+    assert abs(ll - np.log(r["w"] / 1000).sum()) <= 1e-9 * abs(ll)
+    # one EM iteration from the truth stays near the truth (fixed point property, N = 10,000)
+    pb = mc.Problem(c["obs"])
+    pb.set_model(c["poset"], c["lambdas"], 0.05)
+    pb.em_iterations(1000, n_iter=3, seed=2)
+    out = pb.read()
+    assert np.abs(out["lambda_"] / c["lambdas"] - 1).max() < 0.25 and abs(out["eps"] - 0.05) < 0.01
