@@ -614,12 +614,16 @@ int mccbn_importance_weight_genotype(mccbn_ctx* c, const int* genotype, unsigned
   const int prec = opt ? opt->precision : 0;
   if (prec == 1) {
     const PosetProg pg = build_prog(f, 32, 8);
-    if (tg) forward_dump_kernel<double, 32, true><<<grid, kFwdBlock, 0, s>>>(a, pg);
-    else forward_dump_kernel<double, 32, false><<<grid, kFwdBlock, 0, s>>>(a, pg);
+    constexpr size_t sm = fwd_smem_bytes<double, 32>();
+    optin_smem(forward_dump_kernel<double, 32, true>, sm);
+    optin_smem(forward_dump_kernel<double, 32, false>, sm);
+    if (tg) forward_dump_kernel<double, 32, true><<<grid, kFwdBlock, sm, s>>>(a, pg);
+    else forward_dump_kernel<double, 32, false><<<grid, kFwdBlock, sm, s>>>(a, pg);
   } else {
     const PosetProg pg = build_prog(f, 32, 4);
-    if (tg) forward_dump_kernel<float, 32, true><<<grid, kFwdBlock, 0, s>>>(a, pg);
-    else forward_dump_kernel<float, 32, false><<<grid, kFwdBlock, 0, s>>>(a, pg);
+    constexpr size_t sm = fwd_smem_bytes<float, 32>();
+    if (tg) forward_dump_kernel<float, 32, true><<<grid, kFwdBlock, sm, s>>>(a, pg);
+    else forward_dump_kernel<float, 32, false><<<grid, kFwdBlock, sm, s>>>(a, pg);
   }
   c->launches++;
   MCCBN_CUDA(cudaGetLastError());

@@ -76,7 +76,7 @@ __device__ __forceinline__ real cond_uniform(const uint4& r, int w) {
 
 // One conditional draw.  Xt = hidden genotype (topological bit order).  Returns log2 of P(Z)/q_Z.
 template <typename real, int PMAX, bool TIMES_GIVEN>
-__device__ __forceinline__ real sample_conditional(const PosetProg& pg, real* __restrict__ Tcol,
+__device__ __forceinline__ real sample_conditional(const PosetProg& pg, const uint32_t tcol_s,
                                                    const real* __restrict__ s_lam2, const real* __restrict__ s_inv,
                                                    const uint32_t l, const uint32_t gi, const uint32_t k0,
                                                    const uint32_t k1, const uint32_t cw, const real ts_given,
@@ -97,7 +97,7 @@ __device__ __forceinline__ real sample_conditional(const PosetProg& pg, real* __
     const int ui = k + (TIMES_GIVEN ? 0 : 1);
     if (ui % UPB == 0) r = philox4x32_10(l, gi, (uint32_t)(ui / UPB), cw, k0, k1);
     const real u = cond_uniform<real>(r, ui % UPB);
-    const real m = parents_max<real>(pg, multi_mask, k, Tcol);
+    const real m = parents_max<real>(pg, multi_mask, k, tcol_s);
     const bool xk = (Xt >> k) & 1u;
     const real a = Ts - m;
     const real Fx = CondMath<real>::F_of(a, s_lam2[k]);
@@ -105,7 +105,7 @@ __device__ __forceinline__ real sample_conditional(const PosetProg& pg, real* __
     const real z = CondMath<real>::z_of(u, F, s_inv[k]);
     const real base = xk ? m : max(m, Ts);
     const real t = base + z;
-    Tcol[k * kFwdBlock] = t;
+    sts_at<real>(tcol_s + k * (uint32_t)(kFwdBlock * sizeof(real)), t);
     Z[k] = t - m;
     lw2 += xk ? CondMath<real>::lg2(Fx) : -s_lam2[k] * max(a, (real)0);
   }
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
   const int p = pg.p;
   const int lane = threadIdx.x & 31;
   constexpr int kWarps = kFwdBlock / 32;
-  real* Tcol = s_T + threadIdx.x;
-  Tcol[PMAX * kFwdBlock] = (real)0;  // dummy parent row
+  s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;  // dummy parent row
+  const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
   const double kLog2e = 1.44269504088896340736;
 
   for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock) {
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
     auto consume = [&](const uint32_t l, const uint32_t Xt, const int d, const bool valid) {
       real Z[PMAX];
       real Ts;
-      const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(pg, Tcol, s_lam2, s_inv, l, gi, a.key0, a.key1, cw,
+      const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(pg, tcol_s, s_lam2, s_inv, l, gi, a.key0, a.key1, cw,
                                                                     ts_given, Xt, Z, Ts);
       const real lw2 = lw2s + s_lpyx2[d];
       const bool ok = valid && (lw2 > (real)-1e30);  // F <= 0 (incompatible) gives NaN / -inf -> not ok

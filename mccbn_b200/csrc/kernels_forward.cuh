@@ -73,41 +73,59 @@ struct ScaleSrc<double, PMAX> {
   __device__ __forceinline__ double operator()(int k) const { return s[k < 0 ? PMAX : k]; }
 };
 
-// third and further parents of node k (cold path, kept out of line so the hot block stays compact)
+// shared-memory load through a 32-bit shared-space address (keeps LDS even where the compiler loses track of the
+// address space)
 template <typename real>
-__device__ __noinline__ real parents_extra(const PosetProg& pg, const int k, const real* __restrict__ Tcol, real m) {
-  const char* base = reinterpret_cast<const char*>(Tcol);
-#pragma unroll 1
-  for (int e = pg.xstart[k]; e < pg.xstart[k + 1]; ++e)
-    m = max(m, *reinterpret_cast<const real*>(base + (size_t)pg.xoff[e] * (sizeof(real) / 4)));
-  return m;
+__device__ __forceinline__ real lds_at(uint32_t saddr);
+template <>
+__device__ __forceinline__ float lds_at<float>(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+template <>
+__device__ __forceinline__ double lds_at<double>(uint32_t saddr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_at_f(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v)); }
+__device__ __forceinline__ void sts_at_d(uint32_t saddr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(saddr), "d"(v)); }
+template <typename real>
+__device__ __forceinline__ void sts_at(uint32_t saddr, real v) {
+  if (sizeof(real) == 4) sts_at_f(saddr, (float)v);
+  else sts_at_d(saddr, (double)v);
 }
 
 // max over the parents of node k (0 without parents): two unconditional loads (absent parents read the dummy
-// row, which holds 0) + a warp-uniform rare path for in-degree > 2
+// row, which holds 0) + a warp-uniform, non-unrolled loop over the third and further parents (in-degree > 2)
 template <typename real>
 __device__ __forceinline__ real parents_max(const PosetProg& pg, const unsigned multi_mask, const int k,
-                                            const real* __restrict__ Tcol) {
-  const char* base = reinterpret_cast<const char*>(Tcol);
+                                            const uint32_t tcol_s) {
   const uint2 o = pg.off[k];
-  real m = max(*reinterpret_cast<const real*>(base + o.x), *reinterpret_cast<const real*>(base + o.y));
-  if ((multi_mask >> k) & 1u) m = parents_extra<real>(pg, k, Tcol, m);
+  real m = max(lds_at<real>(tcol_s + o.x), lds_at<real>(tcol_s + o.y));
+  if ((multi_mask >> k) & 1u) {
+    const int e1 = pg.xstart[k + 1];
+#pragma unroll 1
+    for (int e = pg.xstart[k]; e < e1; ++e) m = max(m, lds_at<real>(tcol_s + (uint32_t)pg.xoff[e] * (sizeof(real) / 4)));
+  }
   return m;
 }
 
-// One forward draw for sample l of (global) observation gi.  Z[k] = waiting time of the event at topological
-// position k, X = hidden genotype in topological-position space.  `Tcol` is this thread's staging column
-// (element k at Tcol[k * kFwdBlock]).  All PMAX slots are executed unconditionally (no per-node branch): slots
-// k >= p have scale 0 and no parents, so their T is 0; the caller masks X with pg.valid_mask.
+// One forward draw for sample l of (global) observation gi.  The waiting time Z_k and the event time T_k of the
+// node at topological position k are staged in this thread's shared-memory columns (element k at
+// col[k * kFwdBlock]; `tcol_s` / `zcol_s` are 32-bit shared-space addresses); X = hidden genotype in
+// topological-position space.  All PMAX slots run unconditionally (no per-node branch): slots k >= p have scale 0
+// and no parents, so their T is 0 and the caller's valid_mask removes them from X.
 // Random stream of a sample: node k consumes word k%4 of Philox block k/4 (23 high bits); the sampling time
 // consumes the otherwise unused 9 low bits of the first three words of block 0 (independent of the high bits).
 template <typename real, int PMAX, bool TIMES_GIVEN>
-__device__ __forceinline__ void sample_forward(const PosetProg& pg, real* __restrict__ Tcol, const uint32_t l,
-                                               const uint32_t gi, const uint32_t k0, const uint32_t k1,
-                                               const uint32_t cw, const real ts_given,
-                                               const ScaleSrc<real, PMAX> scale, real (&Z)[PMAX], uint32_t& X,
-                                               real& Ts_out) {
+__device__ __forceinline__ void sample_forward(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zcol_s,
+                                               const uint32_t l, const uint32_t gi, const uint32_t k0,
+                                               const uint32_t k1, const uint32_t cw, const real ts_given,
+                                               const ScaleSrc<real, PMAX> scale, uint32_t& X, real& Ts_out) {
   constexpr int UPB = RealTraits<real>::kUniPerBlock;
+  constexpr uint32_t kRow = kFwdBlock * sizeof(real);
   const unsigned multi_mask = pg.multi_mask;
   uint4 r = make_uint4(0, 0, 0, 0);
   real Ts = ts_given;
@@ -126,9 +144,9 @@ __device__ __forceinline__ void sample_forward(const PosetProg& pg, real* __rest
       }
     }
     const real z = RealTraits<real>::expo(r, k % UPB, scale(k));
-    const real t = z + parents_max<real>(pg, multi_mask, k, Tcol);
-    Tcol[k * kFwdBlock] = t;
-    Z[k] = z;
+    const real t = z + parents_max<real>(pg, multi_mask, k, tcol_s);
+    sts_at<real>(tcol_s + k * kRow, t);
+    sts_at<real>(zcol_s + k * kRow, z);
     if (t <= Ts) X |= (1u << k);
   }
   X &= pg.valid_mask;
@@ -153,10 +171,25 @@ __device__ __forceinline__ void load_scales_fp64(const PosetProg& pg, const DevM
   }
 }
 
+#ifndef MCCBN_FWD_BIGP
+#define MCCBN_FWD_BIGP 28       // PMAX >= this: 5 blocks/SM (102 registers), below: 6 blocks/SM (85 registers)
+#endif
+#ifndef MCCBN_FWD_MINB_BIG
+#define MCCBN_FWD_MINB_BIG 5
+#endif
+template <typename real, int PMAX>
+constexpr size_t fwd_smem_bytes() {
+  return sizeof(real) * (size_t)(2 * PMAX + 1) * kFwdBlock;
+}
+
 template <typename real, int PMAX, bool TIMES_GIVEN>
-__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 4 : 1)
+__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? (PMAX >= MCCBN_FWD_BIGP ? MCCBN_FWD_MINB_BIG : 6) : 1)
     estep_forward_kernel(const FwdArgs a, const __grid_constant__ PosetProg pg) {
-  __shared__ real s_T[(PMAX + 1) * kFwdBlock];  // rows 0..PMAX-1: staged T_k; row PMAX: the dummy row (0)
+  // dynamic shared memory (fwd_smem_bytes): rows 0..PMAX-1 staged T_k, row PMAX the dummy row (0), then PMAX rows
+  // of staged waiting times Z_k (frees PMAX registers per thread)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* s_T = reinterpret_cast<real*>(smem_raw);
+  real* s_Z = s_T + (PMAX + 1) * kFwdBlock;
   __shared__ real s_rtab[kRtabN];
   __shared__ real s_scale[PMAX + 1];  // fp64 mode only
 
@@ -164,8 +197,10 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 4 : 1)
   const int p = pg.p;
   const int lane = threadIdx.x & 31;
   constexpr int kWarps = kFwdBlock / 32;
-  real* Tcol = s_T + threadIdx.x;
-  Tcol[PMAX * kFwdBlock] = (real)0;
+  s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;
+  const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
+  const uint32_t zcol_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x);
+  constexpr uint32_t kRow = kFwdBlock * sizeof(real);
 
   for (int t = threadIdx.x; t < kRtabN; t += kFwdBlock)
     s_rtab[t] = sizeof(real) == 4 ? (real)mdl->rtab[t] : (real)mdl->rtab_d[t];
@@ -197,11 +232,10 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 4 : 1)
     for (int l0 = l_begin; l0 < l_end; l0 += 32) {
       const int l = l0 + lane;
       const bool valid = l < l_end;
-      real Z[PMAX];
       uint32_t X;
       real Ts;
-      sample_forward<real, PMAX, TIMES_GIVEN>(pg, Tcol, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given, scale, Z, X,
-                                              Ts);
+      sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zcol_s, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given,
+                                              scale, X, Ts);
       const int d = __popc(X ^ yt);
       const int de = flip ? p - d : d;  // weights decrease in `de`
       const int dmin = __reduce_min_sync(0xffffffffu, valid ? de : (1 << 19));
@@ -219,7 +253,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 4 : 1)
       aw2 = fma(wr, wr, aw2);
       awd = fma(wr, (real)d, awd);
 #pragma unroll
-      for (int k = 0; k < PMAX; ++k) acc[k] = fma(wr, Z[k], acc[k]);
+      for (int k = 0; k < PMAX; ++k) acc[k] = fma(wr, lds_at<real>(zcol_s + k * kRow), acc[k]);
     }
 
     // warp reduction in fp64 (all lanes share dref), lane k writes slot kStatHdr + k
@@ -271,28 +305,30 @@ struct FwdDumpArgs {
 template <typename real, int PMAX, bool TIMES_GIVEN>
 __global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpArgs a,
                                                                  const __grid_constant__ PosetProg pg) {
-  __shared__ real s_T[(PMAX + 1) * kFwdBlock];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* s_T = reinterpret_cast<real*>(smem_raw);
+  real* s_Z = s_T + (PMAX + 1) * kFwdBlock;
   __shared__ real s_scale[PMAX + 1];
   const int p = pg.p;
-  real* Tcol = s_T + threadIdx.x;
-  Tcol[PMAX * kFwdBlock] = (real)0;
+  s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;
+  const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
+  const uint32_t zcol_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x);
   load_scales_fp64<real, PMAX>(pg, a.model, s_scale);
   __syncthreads();
   ScaleSrc<real, PMAX> scale;
   scale = ScaleSrc<real, PMAX>{reinterpret_cast<const real*>(s_scale)};
   const uint32_t yt = to_topo_bits<PMAX>(pg, a.obs_word);
   for (int l = blockIdx.x * kFwdBlock + threadIdx.x; l < a.L; l += gridDim.x * kFwdBlock) {
-    real Z[PMAX];
     uint32_t X;
     real Ts;
-    sample_forward<real, PMAX, TIMES_GIVEN>(pg, Tcol, (uint32_t)l, a.gi, a.key0, a.key1, a.cw, (real)a.time, scale, Z,
-                                            X, Ts);
+    sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zcol_s, (uint32_t)l, a.gi, a.key0, a.key1, a.cw, (real)a.time,
+                                            scale, X, Ts);
     a.dist_out[l] = __popc(X ^ yt);
     uint32_t xe = 0u;
 #pragma unroll
     for (int k = 0; k < PMAX; ++k)
       if (k < p) {
-        a.Z_out[(size_t)pg.ev[k] * a.L + l] = (double)Z[k];
+        a.Z_out[(size_t)pg.ev[k] * a.L + l] = (double)s_Z[k * kFwdBlock + threadIdx.x];
         xe |= ((X >> k) & 1u) << pg.ev[k];
       }
     a.X_out[l] = xe;

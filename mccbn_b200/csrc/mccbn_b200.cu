@@ -106,6 +106,14 @@ static PosetProg build_prog(const FlatPoset& f, int pmax, int elem_bytes) {
 
 }  // namespace mccbn
 
+namespace mccbn {
+template <typename K>
+static void optin_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    MCCBN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+}  // namespace mccbn
+
 struct mccbn_problem {
   mccbn_ctx* ctx = nullptr;
   int N = 0, p = 0;
@@ -193,13 +201,19 @@ struct mccbn_problem {
   template <typename real>
   void launch_forward(const FwdArgs& a, const FlatPoset& f, bool times_given, int grid) {
     cudaStream_t s = ctx->stream;
-#define MCCBN_FWD(PM)                                                              \
-  do {                                                                             \
-    const PosetProg pg = build_prog(f, PM, (int)sizeof(real));                     \
-    if (times_given)                                                               \
-      estep_forward_kernel<real, PM, true><<<grid, kFwdBlock, 0, s>>>(a, pg);      \
-    else                                                                           \
-      estep_forward_kernel<real, PM, false><<<grid, kFwdBlock, 0, s>>>(a, pg);     \
+#define MCCBN_FWD(PM)                                                                                   \
+  do {                                                                                                  \
+    const PosetProg pg = build_prog(f, PM, (int)sizeof(real));                                          \
+    constexpr size_t sm = fwd_smem_bytes<real, PM>();                                                   \
+    if (times_given) {                                                                                  \
+      static bool once = (optin_smem(estep_forward_kernel<real, PM, true>, sm), true);                  \
+      (void)once;                                                                                       \
+      estep_forward_kernel<real, PM, true><<<grid, kFwdBlock, sm, s>>>(a, pg);                          \
+    } else {                                                                                            \
+      static bool once = (optin_smem(estep_forward_kernel<real, PM, false>, sm), true);                 \
+      (void)once;                                                                                       \
+      estep_forward_kernel<real, PM, false><<<grid, kFwdBlock, sm, s>>>(a, pg);                         \
+    }                                                                                                   \
   } while (0)
     if constexpr (sizeof(real) == 8) {
       MCCBN_FWD(32);
@@ -221,7 +235,7 @@ struct mccbn_problem {
   // chunking of the L samples of one observation over warps (see DESIGN.md "work decomposition")
   void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x) const {
     const int warps_per_block = kFwdBlock / 32;
-    const int resident_blocks = ctx->sm_count * 4;  // 4 blocks x 4 warps per SM (128 registers per thread)
+    const int resident_blocks = ctx->sm_count * (p > MCCBN_FWD_BIGP - 4 ? MCCBN_FWD_MINB_BIG : 6);  // blocks of 4 warps per SM
     const long long total_warps = (long long)resident_blocks * warps_per_block;
     long long want_items = total_warps * 24;
     long long c = (want_items + N - 1) / std::max(1, N);

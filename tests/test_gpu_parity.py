@@ -223,12 +223,15 @@ def test_estep_statistics_match_oracle(oracle, sampling, kw):
     assert np.nanmax(np.abs(z)) < 4.5, (sampling, np.nanmax(np.abs(z)))
 
 
-@pytest.mark.parametrize("sampling,L", [("forward", 300), ("backward", 9 * 40)])
-def test_mcem_fixed_point_matches_oracle(oracle, sampling, L):
+@pytest.mark.parametrize("sampling,L,k,eps_true", [("forward", 300, 1, 0.05), ("backward", 37 * 10, 2, 0.05),
+                                                   ("bernoulli", 300, 1, 0.0)])
+def test_mcem_fixed_point_matches_oracle(oracle, sampling, L, k, eps_true):
     """Converged lambda, eps and observed log-likelihood from independent RNG streams agree with the reference
-    restatement within 3 Monte-Carlo standard errors (north_star), s.e. from replicate seeds on both sides."""
-    c = synth.make_config(8, 300, eps=0.05, seed=23, density=0.3)
-    kw = dict(L=L, eps=0.1, sampling=sampling, max_iter=60, update_step_size=20, tol=1e-3)
+    restatement within 3 Monte-Carlo standard errors (north_star), s.e. from replicate seeds on both sides.
+    (bernoulli runs on noise-free data: with noisy data the reference itself aborts with "all samples have weight
+    0" as soon as one observation has no compatible genotype among its L coin-flip proposals.)"""
+    c = synth.make_config(8, 300, eps=eps_true, seed=23, density=0.3)
+    kw = dict(L=L, eps=0.1, sampling=sampling, max_iter=60, update_step_size=20, tol=1e-3, neighborhood_dist=k)
 
     def pack(r):
         return np.concatenate([r["lambda_"], [r["eps"], r["llhood"]]])
@@ -237,11 +240,11 @@ def test_mcem_fixed_point_matches_oracle(oracle, sampling, L):
     o = np.array([pack(oracle.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], seed=s, thrds=oracle.num_threads(), **kw))
                   for s in range(101, 121)])
     se = np.sqrt(g.var(axis=0, ddof=1) / g.shape[0] + o.var(axis=0, ddof=1) / o.shape[0])
-    z = (g.mean(axis=0) - o.mean(axis=0)) / se
+    z = (g.mean(axis=0) - o.mean(axis=0)) / np.maximum(se, 1e-12 * np.abs(o.mean(axis=0)))
     assert np.abs(z).max() < 3.0 * 1.25, z  # 3 s.e. with head-room for 10 simultaneous comparisons
     # recovery (reference validation method): estimates are close to the generating parameters
     rel = np.abs(g.mean(axis=0)[:8] - c["lambdas"]).mean() / c["lambdas"].mean()
-    assert rel < 0.35 and abs(g.mean(axis=0)[8] - 0.05) < 0.03
+    assert rel < 0.35 and abs(g.mean(axis=0)[8] - eps_true) < 0.03
 
 
 def test_mcem_trace_and_batch_average_rule():
@@ -259,6 +262,18 @@ def test_mcem_trace_and_batch_average_rule():
     assert np.array_equal(r["lambda_"], r2["lambda_"]) and r["llhood"] == r2["llhood"]
     r3 = mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], L=128, eps=0.1, max_iter=50, update_step_size=20, seed=5)
     assert r3["llhood"] != r["llhood"]
+
+
+def test_backward_empty_ball_raises_like_the_reference(oracle):
+    """Some noisy observations have no poset-compatible genotype within Hamming distance 1: the reference aborts the
+    run with "all samples have weight 0" (src/mcem_hcbn.cpp:695-699) and so must the device path."""
+    c = synth.make_config(8, 300, eps=0.05, seed=23, density=0.3)
+    kw = dict(L=360, eps=0.1, sampling="backward", max_iter=5, update_step_size=5, seed=1)
+    with pytest.raises(oracle.OracleError) as eo:
+        oracle.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], thrds=4, **kw)
+    with pytest.raises(mc.MccbnError) as eg:
+        mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], **kw)
+    assert eo.value.code == 2 and eg.value.code == 2 and str(eo.value) == str(eg.value)
 
 
 def test_zero_weight_error():
