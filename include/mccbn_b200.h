@@ -204,6 +204,14 @@ int mccbn_problem_read(mccbn_problem* pb, double* lambda, double* eps, double* l
 /* the CUDA stream the problem's work is enqueued on (for event timing by the caller) */
 void* mccbn_problem_stream(mccbn_problem* pb);
 
+/* Host-only test seam for the poset edit operations the annealer uses (Model::add_edge, remove_edge, add_relation,
+ * remove_relation, transitive_reduction_dag, swap_node; src/model_impl.cpp:145-316; the reference exposes the
+ * debug exports `_remove_test` / `_transitive_reduction_dag`, src/asa.cpp:667-735).  op: 0 add_edge, 1 remove_edge,
+ * 2 add_relation, 3 remove_relation, 4 transitive_reduction_dag, 5 swap_node.  *flags: bit 0 = edge inserted,
+ * bit 1 = cycle, bit 2 = reduction_flag.  poset_out = adjacency over event ids (adjacency_list2mat). */
+int mccbn_poset_edit(const int* poset, int p, int op, int u, int v, int* poset_out, int* flags, char* err,
+                     size_t errlen);
+
 /* ---- measurement helper ------------------------------------------------------------------------------------ */
 /* 32-bit random words per second of a pure Philox4x32-10 generator kernel on this GPU: the INT32 ceiling against
  * which bench.py reports the E-step kernels (the path is instruction-issue bound, not HBM/tensor bound). */

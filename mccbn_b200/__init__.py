@@ -6,8 +6,9 @@ Python mirror of the reference's R entry points (see api.py) over the C ABI of l
 from . import synth  # noqa: F401
 from ._capi import LIB_PATH, MccbnError  # noqa: F401
 from .api import (Context, Problem, MCEM_hcbn, adaptive_simulated_annealing, compatible_observations,  # noqa: F401
-                  conditional_from_uniforms, device_count, estep_forward_from_times, flatten_poset,
+                  conditional_from_uniforms, device_count, estep_forward_from_times, estimate_mutation_rates,
+                  flatten_poset,
                   forward_from_times, importance_weight, initialize_lambda, neighbors, nccl_unique_id,
-                  obs_loglikelihood)
+                  obs_loglikelihood, poset_edit)
 
 __version__ = "0.1.0"

@@ -241,6 +241,54 @@ def adaptive_simulated_annealing(poset, obs, times=None, lambda_s=1.0, weights=N
     return dict(lambda_=out_l, eps=out_e.value, poset=out_p, llhood=out_ll.value)
 
 
+def _initialize_lambda_otcbn(obs, average_sampling_times, poset):
+    """initialize_lambda of the OT-CBN wrapper (R/mcem_param_est.r:2-36): direct parents only."""
+    N, p = obs.shape
+    if p == 1:
+        return np.array([1.0 / average_sampling_times])
+    theta = np.zeros(p)
+    for i in range(p):
+        parents = np.nonzero(poset[:, i] == 1)[0]
+        if parents.size == 0:
+            theta[i] = obs[:, i].sum() / N
+        else:
+            idx = np.all(obs[:, parents] == 1, axis=1)
+            theta[i] = 0.000001 if idx.sum() == 0 else obs[idx, i].sum() / idx.sum()
+    return -np.log(np.maximum(1 - theta, 0.00001)) / average_sampling_times
+
+
+def estimate_mutation_rates(poset, genotypes, sampling_times=None, weights=None, max_iter=100, zeta=0.2, ilambda=None,
+                            nrOfSamples=5, verbose=False, maxLambdaValue=1e6, lambda_s=1.0, seed=None, ctx=None):
+    """estimate_mutation_rates / MCEM (R/mcem_param_est.r:40-72) -> `MCEM` (src/mcem.cpp:307-335), the legacy
+    noise-free OT-CBN fit.  Returns dict(lambda_, llhood)."""
+    obs, poset = i32(genotypes), i32(poset)
+    N, p = obs.shape
+    avail = sampling_times is not None
+    if not avail:
+        average_sampling_times = lambda_s  # sic (R/mcem_param_est.r:50-52)
+        t = np.zeros(N)
+    else:
+        t = f64(sampling_times)
+        average_sampling_times = float(np.mean(t))
+    wt = np.ones(N) if weights is None else f64(weights)
+    if ilambda is None:
+        ilambda = _initialize_lambda_otcbn(obs, average_sampling_times, poset)
+        ilambda[ilambda == 0] = 1e-7
+    lam = f64(ilambda)
+    from .synth import topological_sort
+    topo = i32(np.array(topological_sort(poset)))
+    if seed is None:
+        seed = int(np.random.randint(1, 30001))
+    out_l = np.zeros(p)
+    out_ll = C.c_double(0)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_MCEM(_ctx(ctx), ptr(lam), ptr(poset), ptr(obs), ptr(t), int(max_iter), C.c_float(zeta),
+                                  ptr(topo), ptr(wt), int(nrOfSamples), int(bool(verbose)), C.c_float(maxLambdaValue),
+                                  C.c_float(lambda_s), int(avail), int(seed), N, p, ptr(out_l), C.byref(out_ll),
+                                  *e.args))
+    return dict(lambda_=out_l, llhood=out_ll.value)
+
+
 # ---- indexing and supplied-randomness seams -----------------------------------------------------------------------
 def flatten_poset(poset):
     poset = i32(poset)
@@ -272,6 +320,22 @@ def neighbors(p, k, genotype):
     ring = np.zeros(n.value, np.int32)
     e.check(capi.lib().mccbn_neighbors(p, k, ptr(g), ptr(out), ptr(ring), C.byref(n), *e.args))
     return out, ring
+
+
+POSET_OPS = dict(add_edge=0, remove_edge=1, add_relation=2, remove_relation=3, transitive_reduction=4, swap_node=5)
+
+
+def poset_edit(poset, op, u=0, v=0):
+    """Host-only seam for the annealer's poset edit operations (src/model_impl.cpp:145-316)."""
+    poset = i32(poset)
+    p = poset.shape[0]
+    out = np.zeros((p, p), np.int32, order="F")
+    flags = C.c_int(0)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_poset_edit(ptr(poset), p, POSET_OPS[op], int(u), int(v), ptr(out), C.byref(flags),
+                                        *e.args))
+    return dict(poset=out, added=bool(flags.value & 1), cycle=bool(flags.value & 2),
+                reduction_flag=bool(flags.value & 4))
 
 
 def initialize_lambda(obs, poset, lambda_s=1.0, max_lambda=1e6, ctx=None):

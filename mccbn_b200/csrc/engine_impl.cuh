@@ -73,10 +73,10 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
       launch_forward<double>(a, flat[c], times_given, grid_x);
     else
       launch_forward<float>(a, flat[c], times_given, grid_x);
-  } else if (scheme == kBackward || scheme == kBernoulli) {
+  } else if (scheme == kBackward || scheme == kBernoulli || scheme == kOtcbn) {
     CondArgs a;
     std::memset(&a, 0, sizeof(a));
-    int mode = scheme == kBackward ? kCondBackward : kCondBernoulli;
+    int mode = scheme == kBackward ? kCondBackward : (scheme == kBernoulli ? kCondBernoulli : kCondOtcbn);
     if (scheme == kBackward) {
       BackwardPlan bp = plan_backward(p, neighborhood_dist, (unsigned)L);
       if (bp.reps == 0) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);  // L < nrows_sum: no samples at all
@@ -118,7 +118,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.chunk_len = chunk_len;
     a.n_items = n_items;
     a.obs_offset = obs_offset;
-    const PhiloxKey key = make_key(seed, (uint32_t)iter, scheme == kBackward ? 1u : 2u);
+    const PhiloxKey key = make_key(seed, (uint32_t)iter, scheme == kBackward ? 1u : (scheme == kBernoulli ? 2u : 5u));
     a.key0 = key.k0;
     a.key1 = key.k1;
     a.cw = eval_id[c];
@@ -137,9 +137,59 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     }
     ctx->launches++;
     MCCBN_CUDA(cudaGetLastError());
+  } else if (scheme == kPool) {
+    // pool of K = p * L prior draws shared by all observations, regenerated every EM iteration (:606, :650-654)
+    const int K = p * L;
+    const int PM = p <= 8 ? 8 : (p <= 16 ? 16 : (p <= 24 ? 24 : 32));
+    float* Tp = pool_T.ensure((size_t)K * PM);
+    float* Zp = pool_Z.ensure((size_t)K * PM);
+    const PhiloxKey kgen = make_key(seed, (uint32_t)iter, 3u);
+    const PhiloxKey kts = make_key(seed, (uint32_t)iter, 4u);
+    const int ggen = std::max(1, std::min((K + kFwdBlock - 1) / kFwdBlock, ctx->sm_count * 6));
+    const int nb = (N + kPoolBlock - 1) / kPoolBlock;
+    long long want = ((long long)ctx->sm_count * 6 + nb - 1) / nb;
+    chunks = (int)std::max(1LL, std::min<long long>(want, std::max(1, K / (4 * kPoolTile))));
+    chunk_len = ((K + chunks - 1) / chunks + kPoolTile - 1) / kPoolTile * kPoolTile;
+    chunks = (K + chunk_len - 1) / chunk_len;
+    n_items = (long long)N * chunks;
+    PoolArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.obs_bits = bits.ptr;
+    a.times = times.ptr;
+    a.model = models.ptr + c;
+    a.Tp = Tp;
+    a.Zp = Zp;
+    a.part = part.ensure((size_t)n_items * PS());
+    a.N = N;
+    a.K = K;
+    a.chunks = chunks;
+    a.chunk_len = chunk_len;
+    a.obs_offset = obs_offset;
+    a.key0 = kts.k0;
+    a.key1 = kts.k1;
+    a.cw = eval_id[c];
+    a.PS = PS();
+    const dim3 grid(nb, chunks);
+#define MCCBN_POOL(PMX)                                                                                         \
+  do {                                                                                                          \
+    const PosetProg pg = build_prog(flat[c], PMX, 4);                                                           \
+    pool_generate_kernel<PMX><<<ggen, kFwdBlock, fwd_smem_bytes<float, PMX>(), s>>>(Tp, Zp, K, kgen.k0, kgen.k1, \
+                                                                                    eval_id[c], pg);            \
+    if (times_given)                                                                                            \
+      estep_pool_kernel<PMX, true><<<grid, kPoolBlock, 0, s>>>(a, pg);                                          \
+    else                                                                                                        \
+      estep_pool_kernel<PMX, false><<<grid, kPoolBlock, 0, s>>>(a, pg);                                         \
+  } while (0)
+    if (PM == 8) MCCBN_POOL(8);
+    else if (PM == 16) MCCBN_POOL(16);
+    else if (PM == 24) MCCBN_POOL(24);
+    else MCCBN_POOL(32);
+#undef MCCBN_POOL
+    ctx->launches += 2;
+    MCCBN_CUDA(cudaGetLastError());
+    L_eff = K;  // obs_llhood_i = log(sum_k q_k / K)  (w_l = sum q / K for all L resampled rows, :491)
   } else {
-    throw Error(MCCBN_ERR_ARG, scheme == kPool ? "sampling scheme 'pool' is not implemented in this build"
-                                               : "sampling scheme 'add-remove' is not implemented in this build");
+    throw Error(MCCBN_ERR_ARG, "sampling scheme 'add-remove' is not implemented in this build");
   }
   run_finalize(c, chunks, n_items, L_eff, 0, per_obs_out);
   run_mstep(c, update_params);
@@ -163,87 +213,122 @@ struct EmResult {
   int n_iter = 0;
 };
 
-// Runs MCEM on slot 0 (single poset).  trace_out (optional) receives the per-iteration rows.
-static EmResult run_mcem(mccbn_problem& pb, Scheme scheme, unsigned L, const EmControl& ctl, bool times_given,
-                         uint32_t seed, bool verbose, int precision, double* trace_out, int* n_iter_out) {
-  const int p = pb.p;
-  EmResult res;
-  res.lambda.assign(p, 0.0);
-  if (ctl.update_step_size == 0) throw Error(MCCBN_ERR_ARG, "update_step_size must be >= 1");
-  std::vector<double> avg_lambda(p, 0.0), avg_lambda_current(p, 0.0);
+// Host-side state of one MCEM run (the batch-average / convergence bookkeeping of :583-642, :711-721)
+struct EmRun {
+  int slot = 0;
+  std::vector<double> avg_lambda, avg_lambda_current;
   double avg_eps = 0.0, avg_eps_current = 0.0, avg_llhood = 0.0;
-  unsigned boundary = ctl.update_step_size;
+  unsigned boundary = 0, iter = 0;
+  bool done = false;
+  double* trace_out = nullptr;
+};
+
+// Runs MCEM concurrently on several candidate slots (one poset each) of the same observation shard: every round
+// enqueues, for every still-active slot, the iterations up to its next batch boundary, then synchronises ONCE and
+// applies the reference's batch-average / convergence rule per slot.  With one slot this is exactly MCEM_hcbn.
+static std::vector<EmResult> run_mcem_multi(mccbn_problem& pb, const std::vector<int>& slots, Scheme scheme,
+                                            unsigned L, const EmControl& ctl, bool times_given, uint32_t seed,
+                                            bool verbose, int precision, double* trace_out, int* n_iter_out) {
+  const int p = pb.p;
+  if (ctl.update_step_size == 0) throw Error(MCCBN_ERR_ARG, "update_step_size must be >= 1");
   const int stride = p + 2;
   pb.ensure_trace((int)std::max(1u, ctl.max_iter));
-  std::vector<double> rows;
-
+  std::vector<EmRun> runs(slots.size());
+  for (size_t r = 0; r < slots.size(); ++r) {
+    runs[r].slot = slots[r];
+    runs[r].avg_lambda.assign(p, 0.0);
+    runs[r].avg_lambda_current.assign(p, 0.0);
+    runs[r].boundary = ctl.update_step_size;
+    runs[r].done = ctl.max_iter == 0;
+    runs[r].trace_out = (r == 0) ? trace_out : nullptr;
+  }
   if (verbose) {
     DevModel dm;
-    pb.read_model(0, dm);
+    pb.read_model(slots[0], dm);
     std::printf("Initial value of the error rate - epsilon: %g\n", dm.eps);
     std::printf("Initial value of the rate parameters - lambda:");
     for (int j = 0; j < p; ++j) std::printf(" %g", dm.lambda[j]);
     std::printf("\n");
   }
-
-  unsigned iter = 0;
-  bool converged = false;
-  while (iter < ctl.max_iter) {
-    if (iter == boundary) {  // :622-642
-      for (auto& x : avg_lambda_current) x /= ctl.update_step_size;
-      avg_eps_current /= ctl.update_step_size;
-      avg_llhood /= ctl.update_step_size;
-      bool ok = std::abs(avg_eps - avg_eps_current) <= ctl.tol;
-      for (int j = 0; j < p && ok; ++j) ok = std::abs(avg_lambda[j] - avg_lambda_current[j]) <= ctl.tol;
-      if (ok) {
-        converged = true;
-        break;
+  std::vector<std::vector<double>> rows(slots.size());
+  std::vector<DevModel> dms(slots.size());
+  for (;;) {
+    bool any = false;
+    std::vector<unsigned> n_run(slots.size(), 0);
+    for (size_t r = 0; r < runs.size(); ++r) {
+      EmRun& R = runs[r];
+      if (R.done) continue;
+      if (R.iter == R.boundary) {  // :622-642
+        for (auto& x : R.avg_lambda_current) x /= ctl.update_step_size;
+        R.avg_eps_current /= ctl.update_step_size;
+        R.avg_llhood /= ctl.update_step_size;
+        bool ok = std::abs(R.avg_eps - R.avg_eps_current) <= ctl.tol;
+        for (int j = 0; j < p && ok; ++j) ok = std::abs(R.avg_lambda[j] - R.avg_lambda_current[j]) <= ctl.tol;
+        if (ok) {
+          R.done = true;
+          continue;
+        }
+        R.avg_lambda = R.avg_lambda_current;
+        R.avg_eps = R.avg_eps_current;
+        R.boundary += ctl.update_step_size;
+        std::fill(R.avg_lambda_current.begin(), R.avg_lambda_current.end(), 0.0);
+        R.avg_eps_current = 0.0;
+        R.avg_llhood = 0.0;
       }
-      avg_lambda = avg_lambda_current;
-      avg_eps = avg_eps_current;
-      boundary += ctl.update_step_size;
-      std::fill(avg_lambda_current.begin(), avg_lambda_current.end(), 0.0);
-      avg_eps_current = 0.0;
-      avg_llhood = 0.0;
+      n_run[r] = std::min(R.boundary, ctl.max_iter) - R.iter;
+      for (unsigned t = 0; t < n_run[r]; ++t)
+        pb.enqueue_iteration(R.slot, scheme, (int)L, ctl.neighborhood_dist, times_given, seed, 1, false, precision);
+      rows[r].resize((size_t)n_run[r] * stride);
+      MCCBN_CUDA(cudaMemcpyAsync(rows[r].data(), pb.trace_of(R.slot) + (size_t)R.iter * stride,
+                                 sizeof(double) * rows[r].size(), cudaMemcpyDeviceToHost, pb.ctx->stream));
+      MCCBN_CUDA(cudaMemcpyAsync(&dms[r], pb.models.ptr + R.slot, sizeof(DevModel), cudaMemcpyDeviceToHost,
+                                 pb.ctx->stream));
+      any = true;
     }
-    const unsigned n_run = std::min(boundary, ctl.max_iter) - iter;
-    for (unsigned t = 0; t < n_run; ++t)
-      pb.enqueue_iteration(0, scheme, (int)L, ctl.neighborhood_dist, times_given, seed, 1, false, precision);
-    // one host sync per batch: fetch the trace rows of this batch
-    rows.resize((size_t)n_run * stride);
-    MCCBN_CUDA(cudaMemcpyAsync(rows.data(), pb.trace_of(0) + (size_t)iter * stride, sizeof(double) * rows.size(),
-                               cudaMemcpyDeviceToHost, pb.ctx->stream));
-    DevModel dm;
-    pb.read_model(0, dm);  // synchronises the stream
-    if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
-    for (unsigned t = 0; t < n_run; ++t) {
-      const double* row = rows.data() + (size_t)t * stride;
-      for (int j = 0; j < p; ++j) avg_lambda_current[j] += row[2 + j];  // :711-713
-      avg_eps_current += row[1];
-      avg_llhood += row[0];
-      if (verbose) {
-        if (iter + t == 0) std::printf("llhood\tepsilon\tlambdas\n");
-        std::printf("%g\t%g\t", row[0], row[1]);
-        for (int j = 0; j < p; ++j) std::printf(" %g", row[2 + j]);
-        std::printf("\n");
+    if (!any) break;
+    MCCBN_CUDA(cudaStreamSynchronize(pb.ctx->stream));  // one host sync per round
+    for (size_t r = 0; r < runs.size(); ++r) {
+      EmRun& R = runs[r];
+      if (R.done || n_run[r] == 0) continue;
+      if (dms[r].zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
+      for (unsigned t = 0; t < n_run[r]; ++t) {
+        const double* row = rows[r].data() + (size_t)t * stride;
+        for (int j = 0; j < p; ++j) R.avg_lambda_current[j] += row[2 + j];  // :711-713
+        R.avg_eps_current += row[1];
+        R.avg_llhood += row[0];
+        if (verbose && r == 0) {
+          if (R.iter + t == 0) std::printf("llhood\tepsilon\tlambdas\n");
+          std::printf("%g\t%g\t", row[0], row[1]);
+          for (int j = 0; j < p; ++j) std::printf(" %g", row[2 + j]);
+          std::printf("\n");
+        }
+        if (R.trace_out) std::memcpy(R.trace_out + (size_t)(R.iter + t) * stride, row, sizeof(double) * stride);
       }
-      if (trace_out) std::memcpy(trace_out + (size_t)(iter + t) * stride, row, sizeof(double) * stride);
-    }
-    iter += n_run;
-    if (iter == ctl.max_iter) {  // :715-721
-      const unsigned num_iter = ctl.max_iter - boundary + ctl.update_step_size;
-      for (auto& x : avg_lambda_current) x /= num_iter;
-      avg_eps_current /= num_iter;
-      avg_llhood /= num_iter;
+      R.iter += n_run[r];
+      if (R.iter == ctl.max_iter) {  // :715-721
+        const unsigned num_iter = ctl.max_iter - R.boundary + ctl.update_step_size;
+        for (auto& x : R.avg_lambda_current) x /= num_iter;
+        R.avg_eps_current /= num_iter;
+        R.avg_llhood /= num_iter;
+        R.done = true;
+      }
     }
   }
-  (void)converged;
-  res.lambda = avg_lambda_current;  // :731-735: the batch averages are the result
-  res.eps = avg_eps_current;
-  res.llhood = avg_llhood;
-  res.n_iter = (int)iter;
-  if (n_iter_out) *n_iter_out = (int)iter;
-  return res;
+  std::vector<EmResult> out(slots.size());
+  for (size_t r = 0; r < runs.size(); ++r) {
+    out[r].lambda = runs[r].avg_lambda_current;  // :731-735: the batch averages are the result
+    out[r].eps = runs[r].avg_eps_current;
+    out[r].llhood = runs[r].avg_llhood;
+    out[r].n_iter = (int)runs[r].iter;
+  }
+  if (n_iter_out) *n_iter_out = out[0].n_iter;
+  return out;
+}
+
+static EmResult run_mcem(mccbn_problem& pb, Scheme scheme, unsigned L, const EmControl& ctl, bool times_given,
+                         uint32_t seed, bool verbose, int precision, double* trace_out, int* n_iter_out) {
+  return run_mcem_multi(pb, std::vector<int>{0}, scheme, L, ctl, times_given, seed, verbose, precision, trace_out,
+                        n_iter_out)[0];
 }
 
 static std::mutex g_default_mu;
@@ -318,6 +403,30 @@ static uint64_t pack_genotype(const int* g, int p) {
   }                                                           \
   catch (const std::exception& e) { return report(e, err, errlen); } \
   return MCCBN_OK;
+
+namespace mccbn {
+// initialize_lambda from device counts (src/asa.cpp:92-128): float arithmetic reproduced on the host
+static void lambda_from_counts(const FlatPoset& f, const unsigned long long* cnt, int N, float lambda_s,
+                               float max_lambda, double* lambda_out) {
+  for (int j = 0; j < f.p; ++j) {
+    unsigned count = 1;
+    float mutated = 1e-7f;
+    if (f.ancestor_ev[j]) {
+      count += (unsigned)cnt[j * 2 + 0];
+      mutated += (int)cnt[j * 2 + 1];
+    } else {
+      count += (unsigned)N;
+      mutated += (int)cnt[j * 2 + 1];
+    }
+    const float aux = mutated / count;
+    double lam = aux * lambda_s / (1.0 - aux);
+    if (lam > max_lambda || !std::isfinite(lam)) lam = max_lambda;
+    lambda_out[j] = lam;
+  }
+}
+}  // namespace mccbn
+
+#include "engine_asa.cuh"
 
 // ================================================================================================================
 // C ABI
@@ -564,6 +673,14 @@ int mccbn_importance_weight(mccbn_ctx* c, const int* obs, unsigned L, const int*
   if (dist) MCCBN_CUDA(cudaMemcpyAsync(dist, pb.out_dist.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
   if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, pb.out_T.ptr, sizeof(double) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
   MCCBN_CUDA(cudaStreamSynchronize(s));
+  if (parse_scheme(sampling) == kPool) {
+    // every resampled row carries the weight sum_k q_k / K (src/mcem_hcbn.cpp:491): sum_l w_l = L sum(q)/K
+    const double K = (double)p * (double)L;
+    for (int i = 0; i < N; ++i) {
+      if (w_sum) w_sum[i] = w_sum[i] * (double)L / K;
+      if (w_sum_sq && w_sum) w_sum_sq[i] = w_sum[i] * w_sum[i] / (double)L;
+    }
+  }
   MCCBN_CATCH
 }
 
@@ -700,27 +817,6 @@ int mccbn_compatible_observations(mccbn_ctx* c, const int* obs, const int* poset
   MCCBN_CATCH
 }
 
-namespace mccbn {
-// initialize_lambda from device counts (src/asa.cpp:92-128): float arithmetic reproduced on the host
-static void lambda_from_counts(const FlatPoset& f, const unsigned long long* cnt, int N, float lambda_s,
-                               float max_lambda, double* lambda_out) {
-  for (int j = 0; j < f.p; ++j) {
-    unsigned count = 1;
-    float mutated = 1e-7f;
-    if (f.ancestor_ev[j]) {
-      count += (unsigned)cnt[j * 2 + 0];
-      mutated += (int)cnt[j * 2 + 1];
-    } else {
-      count += (unsigned)N;
-      mutated += (int)cnt[j * 2 + 1];
-    }
-    const float aux = mutated / count;
-    double lam = aux * lambda_s / (1.0 - aux);
-    if (lam > max_lambda || !std::isfinite(lam)) lam = max_lambda;
-    lambda_out[j] = lam;
-  }
-}
-}  // namespace mccbn
 
 int mccbn_initialize_lambda(mccbn_ctx* c, const int* obs, const int* poset, int N, int p, float lambda_s,
                             float max_lambda, double* lambda_out, double* eps_out, char* err, size_t errlen) {
@@ -931,20 +1027,160 @@ double mccbn_microbench_philox(mccbn_ctx* c, int reps) {
   }
 }
 
-// ---- not yet implemented in this build (declared by the header; they fail loudly) ---------------------------------
-int mccbn_adaptive_simulated_annealing(mccbn_ctx*, const int*, const int*, const double*, float, const double*,
-                                       unsigned, const char*, unsigned, unsigned, double, float, float, float, float,
-                                       int, unsigned, unsigned, int, const char*, int, int, int, int, int, int, double*,
-                                       double*, int*, double*, char* err, size_t errlen) {
+// ---- host-only test seam for the poset edit operations of the annealer (src/model_impl.cpp:145-316) --------------
+int mccbn_poset_edit(const int* poset, int p, int op, int u, int v, int* poset_out, int* flags, char* err,
+                     size_t errlen) {
   MCCBN_TRY
-  throw Error(MCCBN_ERR_ARG, "adaptive_simulated_annealing is not implemented in this build");
+  if (p < 1 || p > kMaxP || u < 0 || v < 0 || u >= p || v >= p) throw Error(MCCBN_ERR_ARG, "invalid p, u or v");
+  Poset P = Poset::from_adjacency(poset, p);
+  if (!P.sort()) throw Error(MCCBN_ERR_NOT_ACYCLIC, kMsgNotAcyclic);
+  P.set_children();
+  bool added = false;
+  switch (op) {
+    case 0: added = P.add_edge(u, v); break;
+    case 1: P.remove_edge(u, v); break;
+    case 2: added = P.add_relation(u, v); break;
+    case 3: P.remove_relation(u, v); break;
+    case 4: P.transitive_reduction_dag(); break;
+    case 5: P.swap_node(u, v); break;
+    default: throw Error(MCCBN_ERR_ARG, "unknown poset edit operation");
+  }
+  if (flags) *flags = (added ? 1 : 0) | (P.cycle ? 2 : 0) | (P.reduction_flag ? 4 : 0);
+  if (poset_out) P.to_adjacency(poset_out);
   MCCBN_CATCH
 }
 
-int mccbn_MCEM(mccbn_ctx*, const double*, const int*, const int*, const double*, int, float, const int*, const double*,
-               int, int, float, float, int, int, int, int, double*, double*, char* err, size_t errlen) {
+// ---- adaptive simulated annealing --------------------------------------------------------------------------------
+int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int* obs, const double* times,
+                                       float lambda_s, const double* weights, unsigned L, const char* sampling,
+                                       unsigned max_iter_EM, unsigned update_step_size, double tol, float max_lambda,
+                                       float T0, float adap_rate, float acceptance_rate, int step_size,
+                                       unsigned max_iter_ASA, unsigned neighborhood_dist, int adaptive,
+                                       const char* outdir, int sampling_times_available, int thrds, int verbose,
+                                       int seed, int N, int p, double* lambda_out, double* eps_out, int* poset_out,
+                                       double* llhood_out, char* err, size_t errlen) {
+  (void)thrds;
   MCCBN_TRY
-  throw Error(MCCBN_ERR_ARG, "OT-CBN MCEM is not implemented in this build");
+  c = get_ctx(c);
+  const Scheme sc = parse_scheme(sampling);
+  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  Candidate M;
+  {
+    FlatPoset f;
+    flatten_or_throw(poset, p, M.poset, f);
+  }
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.upload(obs, times, weights);
+  initialize_candidate(pb, M, lambda_s, max_lambda);  // src/asa.cpp:640-642
+  EmControl ctl;
+  ctl.max_iter = max_iter_EM;
+  ctl.update_step_size = update_step_size;
+  ctl.tol = tol;
+  ctl.max_lambda = max_lambda;
+  ctl.neighborhood_dist = neighborhood_dist;
+  AsaControl actl;
+  actl.T = T0;
+  actl.outdir = outdir ? outdir : "";
+  actl.acceptance_rate = acceptance_rate;
+  actl.adap_rate = adap_rate;
+  actl.step_size = (unsigned)std::max(0, step_size);
+  actl.max_iter = max_iter_ASA;
+  actl.adaptive = adaptive != 0;
+  int batch = 8;
+  if (const char* b = std::getenv("MCCBN_ASA_BATCH")) batch = std::max(1, std::min(kMaxCand - 1, std::atoi(b)));
+  const double ll = simulated_annealing(pb, M, actl, L, sc, ctl, sampling_times_available != 0, (uint32_t)seed,
+                                        lambda_s, verbose != 0, batch);
+  std::copy(M.lambda.begin(), M.lambda.end(), lambda_out);
+  *eps_out = M.eps;
+  M.poset.to_adjacency(poset_out);
+  *llhood_out = ll;
+  MCCBN_CATCH
+}
+
+// ---- legacy OT-CBN MCEM (src/mcem.cpp:149-210, :307-335) ---------------------------------------------------------
+int mccbn_MCEM(mccbn_ctx* c, const double* ilambda, const int* poset, const int* O, const double* times, int max_iter,
+               float alpha, const int* topo_path, const double* weights, int nrOfSamples, int verbose,
+               float max_lambda, float lambda_s, int sampling_time_available, int seed, int N, int p,
+               double* lambda_out, double* llhood_out, char* err, size_t errlen) {
+  (void)topo_path;  // R passes my.topological.sort(poset) - 1; any valid order is equivalent, we derive our own
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.upload(O, times, weights);
+  cudaStream_t s = c->stream;
+  // is_all_genotypes_compatible_with_poset (R/mcem_param_est.r:57-59, :75-87)
+  {
+    DevPoset dp;
+    fill_dev_poset(f, dp);
+    MCCBN_CUDA(cudaMemcpyAsync(pb.posets.ptr, &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
+    DevBuf<int> flags;
+    flags.ensure(N);
+    unsigned long long* cnt = pb.counts.ensure(2);
+    MCCBN_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
+    compat_kernel<<<dim3(std::min(1024, (N + 255) / 256), 1), 256, 0, s>>>(pb.bits.ptr, N, pb.posets.ptr, flags.ptr,
+                                                                            cnt);
+    c->launches++;
+    std::vector<int> hf(N);
+    MCCBN_CUDA(cudaMemcpyAsync(hf.data(), flags.ptr, sizeof(int) * N, cudaMemcpyDeviceToHost, s));
+    MCCBN_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < N; ++i)
+      if (!hf[i] && (!weights || weights[i] > 0))
+        throw Error(MCCBN_ERR_ARG,
+                    "Error in the function MCEM: Some genotypes with non-zero weights are incompatible with the poset!");
+  }
+  std::vector<double> lambda(ilambda, ilambda + p), avg_lambda(p, 0.0), T_colsum(p);
+  float W = 0.f;  // `float W = sum(weights)` (src/mcem.cpp:160)
+  {
+    double sw = 0;
+    for (int i = 0; i < N; ++i) sw += weights ? weights[i] : 1.0;
+    W = (float)sw;
+  }
+  float avg_llhood = 0.f, llhood = 0.f;  // float in the reference (:163)
+  const int record_iter = std::max((int)((1 - alpha) * max_iter), 1);
+  pb.ensure_trace(1);
+  pb.set_model(0, f, lambda.data(), 0.5, lambda_s, max_lambda);
+  if (verbose) {
+    std::printf("Initial value for rate parameters - lambda:");
+    for (double l : lambda) std::printf(" %g", l);
+    std::printf("\n");
+  }
+  std::vector<double> st(pb.PS());
+  for (int iter = 0; iter < max_iter; ++iter) {
+    MCCBN_CUDA(cudaMemcpyAsync(pb.models.ptr, lambda.data(), sizeof(double) * p, cudaMemcpyHostToDevice, s));
+    pb.enqueue_iteration(0, kOtcbn, nrOfSamples, 0, sampling_time_available != 0, (uint32_t)seed, 0, false, 0);
+    MCCBN_CUDA(cudaMemcpyAsync(st.data(), pb.stats_of(0), sizeof(double) * pb.PS(), cudaMemcpyDeviceToHost, s));
+    MCCBN_CUDA(cudaStreamSynchronize(s));
+    double sumlog = 0.0, dot = 0.0;
+    for (int j = 0; j < p; ++j) {
+      T_colsum[j] = st[kStatHdr + f.pos_of_event[j]];  // sum_i wt_i E[Z_ij]
+      lambda[j] = W / T_colsum[j];
+      if (lambda[j] > max_lambda) lambda[j] = max_lambda;  // :189-191
+      sumlog += std::log(lambda[j]);
+      dot += lambda[j] * T_colsum[j];
+    }
+    llhood = (float)(W * sumlog - dot);  // :193
+    if (verbose) {
+      std::printf("Lambda update:");
+      for (double l : lambda) std::printf(" %g", l);
+      std::printf(" - Log-likelihood: %g\n", llhood);
+    }
+    if (iter >= record_iter) {
+      for (int j = 0; j < p; ++j) avg_lambda[j] += lambda[j];
+      avg_llhood += llhood;
+    }
+  }
+  for (int j = 0; j < p; ++j) lambda_out[j] = avg_lambda[j] / (max_iter - record_iter);  // :206-207
+  *llhood_out = (double)(avg_llhood / (max_iter - record_iter));
   MCCBN_CATCH
 }
 

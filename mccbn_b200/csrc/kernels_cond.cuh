@@ -47,7 +47,8 @@ template <>
 struct CondMath<float> {
   // scale constants per node: lam2 = lambda * log2(e), inv = ln2 / lambda
   static __device__ __forceinline__ float u01(uint32_t b) { return __uint_as_float((b >> 9) | 0x3f800000u) - 1.0f; }  // [0,1)
-  static __device__ __forceinline__ float F_of(float a, float lam2) { return 1.0f - fast_ex2(-a * lam2); }
+  // F(a) = 1 - exp(-lambda a); clamped away from 0 so that a compatible sample never loses its (tiny) weight to rounding
+  static __device__ __forceinline__ float F_of(float a, float lam2) { return fmaxf(1.0f - fast_ex2(-a * lam2), 1.17549435e-38f); }
   static __device__ __forceinline__ float z_of(float u, float F, float inv) { return -fast_lg2(1.0f - u * F) * inv; }
   static __device__ __forceinline__ float lg2(float x) { return fast_lg2(x); }
   static __device__ __forceinline__ float ex2(float x) { return fast_ex2(x); }

@@ -1,0 +1,152 @@
+// kernels_pool.cuh -- the reference's "pool" scheme (src/mcem_hcbn.cpp:460-491, :650-654, :668-677) for sm_100a.
+//
+// Reference: once per EM iteration a pool of K = p*L prior draws (Z_k, T_k) is generated (sample_times :184-213);
+// for every observation i the pool genotypes X_k = [T_k <= T_s,ik] are formed with K fresh sampling times (or the
+// given t_i) (generate_genotypes :215-236), q_k = eps^d (1-eps)^(p-d) with d = d(X_k, Y_i), and L indices are
+// resampled with replacement from Discrete(q) (rdiscrete_std :44-54); all L samples get the weight sum(q)/K.
+// Hence  P^(Y_i) = sum_k q_k / K  deterministically given the pool, and the resampled means of d and Z are
+// unbiased estimates of  sum_k q_k g_k / sum_k q_k.  The device path evaluates those conditional expectations
+// directly (Rao-Blackwellisation of the resampling step: same estimand, less Monte-Carlo noise; documented in
+// DESIGN.md) -- the O(N K p) comparison work is the reference's.
+//
+// Mapping: pool entries are staged tile by tile in shared memory ([j][k] so that a whole warp reads one float4 of
+// an entry as a broadcast); one THREAD per observation sweeps the tile with its p+2 running sums in registers.
+#pragma once
+#include "device_types.cuh"
+#include "kernels_forward.cuh"
+#include "philox.cuh"
+
+namespace mccbn {
+
+constexpr int kPoolBlock = 128;  // observations per block
+constexpr int kPoolTile = 64;    // pool entries per shared-memory tile
+
+// Pool generation: entry k draws Z_j ~ Exp(lambda_j) and propagates T_j.  Output layout [k][PMAX] (row per entry,
+// topological-position order, padded with +inf for T so that padded events are never mutated, 0 for Z).
+template <int PMAX>
+__global__ void __launch_bounds__(kFwdBlock) pool_generate_kernel(float* __restrict__ Tp, float* __restrict__ Zp, int K,
+                                                                  uint32_t key0, uint32_t key1, uint32_t cw,
+                                                                  const __grid_constant__ PosetProg pg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_T = reinterpret_cast<float*>(smem_raw);
+  float* s_Z = s_T + (PMAX + 1) * kFwdBlock;
+  s_T[PMAX * kFwdBlock + threadIdx.x] = 0.f;
+  const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
+  const uint32_t zcol_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x);
+  ScaleSrc<float, PMAX> scale;
+  scale = ScaleSrc<float, PMAX>{nullptr};
+  for (int k = blockIdx.x * kFwdBlock + threadIdx.x; k < K; k += gridDim.x * kFwdBlock) {
+    uint32_t X;
+    float Ts;
+    // TIMES_GIVEN = true: no sampling time is drawn here (it is drawn per (observation, entry) later)
+    sample_forward<float, PMAX, true>(pg, tcol_s, zcol_s, (uint32_t)k, 0xffffffffu, key0, key1, cw, 0.f, scale, X, Ts);
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j) {
+      Tp[(size_t)k * PMAX + j] = j < pg.p ? s_T[j * kFwdBlock + threadIdx.x] : __int_as_float(0x7f800000);
+      Zp[(size_t)k * PMAX + j] = j < pg.p ? s_Z[j * kFwdBlock + threadIdx.x] : 0.f;
+    }
+  }
+}
+
+struct PoolArgs {
+  const uint64_t* obs_bits;
+  const double* times;
+  const DevModel* model;
+  const float* Tp;  // K x PMAX
+  const float* Zp;  // K x PMAX
+  double* part;     // N x chunks x PS
+  int N, K, chunks, chunk_len;  // chunk over pool entries (multiple of kPoolTile)
+  long long obs_offset;
+  uint32_t key0, key1, cw;
+  int PS;
+};
+
+template <int PMAX, bool TIMES_GIVEN>
+__global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a, const __grid_constant__ PosetProg pg) {
+  __shared__ __align__(16) float s_Tt[kPoolTile * PMAX];
+  __shared__ __align__(16) float s_Zt[kPoolTile * PMAX];
+  __shared__ float s_rtab[kRtabN];
+  const DevModel* __restrict__ mdl = a.model;
+  const int p = pg.p;
+  for (int t = threadIdx.x; t < kRtabN; t += kPoolBlock) s_rtab[t] = mdl->rtab[t];
+  const int flip = mdl->flip;
+  const int ch = blockIdx.y;
+  const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+  const bool live = i < a.N;
+  const uint32_t yt = live ? to_topo_bits<PMAX>(pg, a.obs_bits[i]) : 0u;
+  const float ts_given = (TIMES_GIVEN && live) ? (float)a.times[i] : 0.f;
+  const uint32_t gi = (uint32_t)(a.obs_offset + i);
+  const float cs = c_scale.cs;
+
+  float acc[PMAX];
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) acc[j] = 0.f;
+  float aw = 0.f, aw2 = 0.f, awd = 0.f;
+  int dref = 1 << 20;
+
+  const int k_begin = ch * a.chunk_len, k_end = min(a.K, k_begin + a.chunk_len);
+  for (int k0 = k_begin; k0 < k_end; k0 += kPoolTile) {
+    __syncthreads();
+    const int nk = min(kPoolTile, k_end - k0);
+    for (int t = threadIdx.x; t < nk * PMAX / 4; t += kPoolBlock) {  // coalesced float4 copy of the tile
+      reinterpret_cast<float4*>(s_Tt)[t] = reinterpret_cast<const float4*>(a.Tp + (size_t)k0 * PMAX)[t];
+      reinterpret_cast<float4*>(s_Zt)[t] = reinterpret_cast<const float4*>(a.Zp + (size_t)k0 * PMAX)[t];
+    }
+    __syncthreads();
+    uint4 r = make_uint4(0, 0, 0, 0);
+    for (int kk = 0; kk < nk; ++kk) {
+      float Ts = ts_given;
+      if (!TIMES_GIVEN) {
+        const int k = k0 + kk;
+        if ((kk & 3) == 0) r = philox4x32_10((uint32_t)(k >> 2), gi, 0u, a.cw, a.key0, a.key1);
+        const uint32_t bits = (kk & 3) == 0 ? r.x : ((kk & 3) == 1 ? r.y : ((kk & 3) == 2 ? r.z : r.w));
+        Ts = fast_lg2(u01_open0(bits)) * cs;
+      }
+      uint32_t X = 0u;
+      const float4* Tk = reinterpret_cast<const float4*>(s_Tt + kk * PMAX);
+#pragma unroll
+      for (int q = 0; q < PMAX / 4; ++q) {
+        const float4 t4 = Tk[q];  // warp-wide broadcast
+        X |= (t4.x <= Ts ? 1u : 0u) << (4 * q) | (t4.y <= Ts ? 1u : 0u) << (4 * q + 1) |
+             (t4.z <= Ts ? 1u : 0u) << (4 * q + 2) | (t4.w <= Ts ? 1u : 0u) << (4 * q + 3);
+      }
+      const int d = __popc(X ^ yt);
+      const int de = flip ? p - d : d;
+      if (de < dref) {  // per-thread running reference (lanes are different observations); rare
+        const float s = s_rtab[min(dref - de, kRtabN - 1)];
+        aw *= s;
+        aw2 *= s * s;
+        awd *= s;
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j) acc[j] *= s;
+        dref = de;
+      }
+      const float wr = s_rtab[min(de - dref, kRtabN - 1)];
+      aw += wr;
+      aw2 = fmaf(wr, wr, aw2);
+      awd = fmaf(wr, (float)d, awd);
+      const float4* Zk = reinterpret_cast<const float4*>(s_Zt + kk * PMAX);
+#pragma unroll
+      for (int q = 0; q < PMAX / 4; ++q) {
+        const float4 z4 = Zk[q];
+        acc[4 * q] = fmaf(wr, z4.x, acc[4 * q]);
+        acc[4 * q + 1] = fmaf(wr, z4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(wr, z4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(wr, z4.w, acc[4 * q + 3]);
+      }
+    }
+  }
+  if (live) {
+    double* out = a.part + ((size_t)i * a.chunks + ch) * a.PS;
+    out[0] = (double)aw;
+    out[1] = (double)aw2;
+    out[2] = (double)awd;
+    out[3] = (double)(k_end - k_begin);
+    out[4] = mdl->log_base + (dref > 0 ? (double)dref * mdl->log_r : 0.0);
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j)
+      if (j < p) out[kStatHdr + j] = (double)acc[j];
+  }
+}
+
+}  // namespace mccbn

@@ -18,13 +18,14 @@
 #include "kernels_cond.cuh"
 #include "kernels_forward.cuh"
 #include "kernels_fp64.cuh"
+#include "kernels_pool.cuh"
 #include "kernels_reduce.cuh"
 
 using namespace mccbn;
 
 namespace mccbn {
 
-enum Scheme { kForward = 0, kAddRemove = 1, kBackward = 2, kBernoulli = 3, kPool = 4 };
+enum Scheme { kForward = 0, kAddRemove = 1, kBackward = 2, kBernoulli = 3, kPool = 4, kOtcbn = 5 };
 
 static Scheme parse_scheme(const char* s) {
   if (!s) throw Error(MCCBN_ERR_ARG, "sampling scheme is NULL");
@@ -127,6 +128,8 @@ struct mccbn_problem {
   DevBuf<double> out_w, out_w2, out_dist, out_T;
   DevBuf<int> out_leff;
   DevBuf<uint64_t> ball;  // backward scheme: flip masks of the Hamming ball
+  DevBuf<float> pool_T, pool_Z;  // pool scheme: K x PMAX event / waiting times
+  DevBuf<unsigned long long> counts;  // compatibility / initialize_lambda counters
   int ball_p = -1, ball_k = -1;
   int trace_rows = 0;
   FlatPoset flat[kMaxCand];

@@ -1022,7 +1022,132 @@ static void initialize_lambda(Model& model, const MatB& obs, float max_lambda) {
   model.update_lambda(lambda, max_lambda);
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// legacy OT-CBN MCEM (src/mcem.cpp:30-210).  The reference draws from R's global RNG (runif / rexp sugar);
+// here the same formulas are driven by StdRng -- the stream differs, the distribution does not.
+// ----------------------------------------------------------------------------------------------
+static double ot_runif(StdRng& rng) {
+  std::uniform_real_distribution<double> U(0.0, 1.0);
+  return U(rng.eng);
+}
+static double ot_rtexp(double m, double t, StdRng& rng) {  // :30-33
+  double u = ot_runif(rng);
+  return -std::log(1 - u * (1 - std::exp(-t * m))) / m;
+}
+static double ot_rexp(double rate, StdRng& rng) { return -std::log1p(-ot_runif(rng)) / rate; }
+static double ot_dexp_log(double x, double rate) { return std::log(rate) - rate * x; }
+static double ot_pexp_log(double x, double rate) { return std::log1p(-std::exp(-rate * x)); }
+
+// drawHiddenVarsSample (:52-92)
+static std::vector<double> drawHiddenVarsSample(const std::vector<int>& O_vec, double time,
+                                                const std::vector<double>& lambda, const std::vector<int>& topo_path,
+                                                const std::vector<std::vector<int>>& parents, double& dens,
+                                                float lambda_s, bool time_available, StdRng& rng) {
+  const int p = (int)lambda.size();
+  std::vector<double> T(p, 0.0), T_sum(p, 0.0);
+  dens = 0.0;
+  if (!time_available) time = ot_rexp(lambda_s, rng);
+  for (int k = 0; k < p; ++k) {
+    const int e = topo_path[k];
+    double max_parents_t = 0.0;
+    for (int u : parents[e])
+      if (T_sum[u] > max_parents_t) max_parents_t = T_sum[u];
+    if (O_vec[e] == 1) {
+      double tmp = ot_rtexp(lambda[e], time - max_parents_t, rng);
+      dens += ot_dexp_log(tmp, lambda[e]) - ot_pexp_log(time - max_parents_t, lambda[e]);
+      T_sum[e] = max_parents_t + tmp;
+    } else {
+      double tmp = ot_rexp(lambda[e], rng);
+      T_sum[e] = std::max(time, max_parents_t) + tmp;
+      dens += ot_dexp_log(tmp, lambda[e]);
+    }
+    T[e] = T_sum[e] - max_parents_t;
+  }
+  return T;
+}
+
+// _expectedTimeDifference (:105-146)
+static std::vector<double> expectedTimeDifference(const std::vector<int>& O_vec, double time,
+                                                  const std::vector<double>& lambda, const std::vector<int>& topo_path,
+                                                  const std::vector<std::vector<int>>& parents, int nrOfSamples,
+                                                  float lambda_s, bool time_available, StdRng& rng) {
+  const int p = (int)lambda.size();
+  std::vector<std::vector<double>> samples(nrOfSamples);
+  std::vector<double> w(nrOfSamples);
+  double wsum = 0;
+  for (int i = 0; i < nrOfSamples; ++i) {
+    double proposal_density;
+    samples[i] = drawHiddenVarsSample(O_vec, time, lambda, topo_path, parents, proposal_density, lambda_s,
+                                      time_available, rng);
+    double org = 0.0;
+    for (int j = 0; j < p; ++j) org += ot_dexp_log(samples[i][j], lambda[j]);  // log_cbn_density_ (:94-102)
+    w[i] = std::exp(org - proposal_density);
+    wsum += w[i];
+  }
+  if (wsum == 0)
+    for (auto& x : w) x = 1.0 / nrOfSamples;
+  else
+    for (auto& x : w) x /= wsum;
+  std::vector<double> td(p, 0.0);
+  for (int j = 0; j < p; ++j)
+    for (int i = 0; i < nrOfSamples; ++i) td[j] += samples[i][j] * w[i];
+  return td;
+}
+
 }  // namespace ref
+
+extern "C" int ref_MCEM_otcbn(const double* ilambda, const int* poset, const int* O, const double* times, int max_iter,
+                              float alpha, const int* topo_path, const double* weights, int nrOfSamples,
+                              float max_lambda, float lambda_s, int time_available, int seed, int N, int p,
+                              double* lambda_out, double* llhood_out) {
+  using namespace ref;
+  try {
+    // _MCEM (:149-210)
+    StdRng rng((unsigned)seed);
+    std::vector<std::vector<int>> parents(p);
+    for (int k = 0; k < p; ++k)
+      for (int i = 0; i < p; ++i)
+        if (poset[(size_t)k * p + i] == 1) parents[k].push_back(i);
+    std::vector<int> topo(topo_path, topo_path + p);
+    float W = 0;
+    {
+      double s = 0;
+      for (int i = 0; i < N; ++i) s += weights[i];
+      W = (float)s;
+    }
+    std::vector<double> lambda(ilambda, ilambda + p), avg_lambda(p, 0.0), T_colsum(p);
+    float avg_llhood = 0, llhood = 0;
+    const int record_iter = std::max((int)((1 - alpha) * max_iter), 1);
+    std::vector<int> O_vec(p);
+    for (int iter = 0; iter < max_iter; ++iter) {
+      std::fill(T_colsum.begin(), T_colsum.end(), 0.0);
+      for (int i = 0; i < N; ++i) {  // generateMutationTimes (:280-304)
+        for (int j = 0; j < p; ++j) O_vec[j] = O[(size_t)j * N + i];
+        std::vector<double> td = expectedTimeDifference(O_vec, times[i], lambda, topo, parents, nrOfSamples, lambda_s,
+                                                        time_available != 0, rng);
+        for (int j = 0; j < p; ++j) T_colsum[j] += weights[i] * td[j];
+      }
+      double sumlog = 0, dot = 0;
+      for (int j = 0; j < p; ++j) {
+        lambda[j] = W / T_colsum[j];
+        if (lambda[j] > max_lambda) lambda[j] = max_lambda;
+        sumlog += std::log(lambda[j]);
+        dot += lambda[j] * T_colsum[j];
+      }
+      llhood = (float)(W * sumlog - dot);
+      if (iter >= record_iter) {
+        for (int j = 0; j < p; ++j) avg_lambda[j] += lambda[j];
+        avg_llhood += llhood;
+      }
+    }
+    for (int j = 0; j < p; ++j) lambda_out[j] = avg_lambda[j] / (max_iter - record_iter);
+    *llhood_out = (double)(avg_llhood / (max_iter - record_iter));
+  } catch (const std::exception& e) {
+    return 9;
+  }
+  return 0;
+}
 
 // ================================================================================================
 // C interface (ctypes).  Return 0 = ok, 1 = not acyclic, 2 = zero weight, 9 = other error.

@@ -326,3 +326,28 @@ def rexp(n, rate, seed):
     out = np.zeros(n)
     _chk(lib().ref_rexp(n, C.c_double(rate), seed, _p(out)))
     return out
+
+
+def MCEM_otcbn(ilambda, poset, obs, times=None, max_iter=100, alpha=0.2, weights=None, nrOfSamples=5, max_lambda=1e6,
+               lambda_s=1.0, seed=1):
+    """legacy OT-CBN `MCEM` (src/mcem.cpp:307-335) with the topological order of R's my.topological.sort"""
+    obs, poset, lam = _i32(obs), _i32(poset), _f64(ilambda)
+    N, p = obs.shape
+    t = np.zeros(N) if times is None else _f64(times)
+    wt = np.ones(N) if weights is None else _f64(weights)
+    indeg = poset.sum(axis=0).astype(int)
+    order, ready = [], [j for j in range(p) if indeg[j] == 0]
+    while ready:
+        j = ready.pop(0)
+        order.append(j)
+        for c in np.nonzero(poset[j])[0]:
+            indeg[c] -= 1
+            if indeg[c] == 0:
+                ready.append(int(c))
+    topo = _i32(np.array(order))
+    out_l = np.zeros(p)
+    out_ll = C.c_double(0)
+    _chk(lib().ref_MCEM_otcbn(_p(lam), _p(poset), _p(obs), _p(t), int(max_iter), C.c_float(alpha), _p(topo), _p(wt),
+                              int(nrOfSamples), C.c_float(max_lambda), C.c_float(lambda_s), int(times is not None),
+                              int(seed), N, p, _p(out_l), C.byref(out_ll)))
+    return dict(lambda_=out_l, llhood=out_ll.value)

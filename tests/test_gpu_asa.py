@@ -1,0 +1,65 @@
+"""adaptive.simulated.annealing on the device (BASELINE config 4 path): speculative batched scoring must not change the
+result, outputs follow the reference's file formats, and the search behaves like the reference's (score never
+decreases for the tracked ML poset; the returned poset is a transitively reduced DAG)."""
+import os
+
+import numpy as np
+import pytest
+
+import mccbn_b200 as mc
+from mccbn_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(tmp, batch, seed=7, **kw):
+    os.environ["MCCBN_ASA_BATCH"] = str(batch)
+    out = os.path.join(tmp, f"b{batch}_")
+    c = synth.make_config(8, 400, eps=0.05, seed=5, density=0.3)
+    start = np.zeros((8, 8), np.int32)  # empty poset as the initial guess
+    r = mc.adaptive_simulated_annealing(start, c["obs"], L=64, max_iter=40, update_step_size=20, max_iter_asa=30,
+                                        outdir=out, seed=seed, **kw)
+    return c, r, out
+
+
+def test_asa_batched_equals_sequential(tmp_path):
+    c, r1, o1 = _run(str(tmp_path), 1)
+    _, r8, o8 = _run(str(tmp_path), 8)
+    assert np.array_equal(r1["poset"], r8["poset"])
+    assert np.array_equal(r1["lambda_"], r8["lambda_"]) and r1["eps"] == r8["eps"] and r1["llhood"] == r8["llhood"]
+    for name in ("asa.txt", "params.txt", "poset.txt"):
+        assert open(o1 + name).read() == open(o8 + name).read(), name
+
+
+def test_asa_outputs_and_search(tmp_path):
+    c, r, out = _run(str(tmp_path), 8, seed=11)
+    P = r["poset"]
+    assert P.shape == (8, 8) and set(np.unique(P)) <= {0, 1}
+    synth.topological_sort(P)  # raises if cyclic
+    assert np.array_equal(synth.transitive_reduction(P), P)
+    assert np.all(r["lambda_"] > 0) and 0 < r["eps"] < 0.5 and np.isfinite(r["llhood"])
+    par = open(out + "params.txt").read().strip().split("\n")
+    assert par[0] == "step\t llhood\t epsilon\t lambdas"
+    assert len(par) == 1 + 30  # step 0 .. max_iter_asa - 1 (src/asa.cpp:527-552)
+    assert [int(l.split("\t")[0]) for l in par[1:]] == list(range(30))
+    asa = open(out + "asa.txt").read().strip().split("\n")
+    assert asa[0] == "step\t llhood\t temperature\t acceptance rate"
+    assert [int(l.split("\t")[0]) for l in asa[1:]] == [3, 6, 9, 12, 15, 18, 21, 24, 27]  # every step.size = 30 / 10
+    lls = np.array([float(l.split("\t")[1]) for l in par[1:]])
+    # learning from the empty poset: the best score seen improves on the start
+    assert lls.max() > lls[0]
+    # poset.txt holds the cover relations of the best poset seen ("u\tv" per line, event ids)
+    edges = [tuple(map(int, l.split("\t"))) for l in open(out + "poset.txt").read().strip().split("\n") if l]
+    assert all(0 <= u < 8 and 0 <= v < 8 for u, v in edges)
+    # the final fit scores the ML poset: it is at least as good as the empty poset's fit (up to MC noise)
+    ll0 = mc.MCEM_hcbn(*mc.initialize_lambda(c["obs"], np.zeros((8, 8), np.int32))[:1], np.zeros((8, 8), np.int32),
+                       c["obs"], L=64, eps=0.05, max_iter=40, seed=3)["llhood"]
+    assert r["llhood"] > ll0 - 5.0
+
+
+def test_asa_not_acyclic_start():
+    start = np.zeros((4, 4), np.int32)
+    start[0, 1] = start[1, 0] = 1
+    with pytest.raises(mc.MccbnError) as e:
+        mc.adaptive_simulated_annealing(start, np.zeros((5, 4), np.int32), L=16, max_iter_asa=3, seed=1)
+    assert e.value.code == 1

@@ -163,14 +163,14 @@ def _mean_se(fn, seeds):
 
 @pytest.mark.parametrize("sampling,kw,precision", [("forward", {}, 0), ("forward", {}, 1),
                                                    ("backward", dict(neighborhood_dist=6), 0),
-                                                   ("backward", dict(neighborhood_dist=6), 1)])
+                                                   ("backward", dict(neighborhood_dist=6), 1), ("pool", {}, 0)])
 def test_k2_exact_probabilities(sampling, kw, precision):
     """IS estimate of P(Y_i) and E[d | Y_i] against the exact lattice recursion (K2)."""
     c = synth.make_config(6, 12, eps=0.1, seed=11, density=0.3)
     p = 6
     px = exact.genotype_probs_exp(c["poset"], c["lambdas"], 1.0)
     ex = np.array([exact.obs_prob_and_dist(px, exact.mask_of(c["obs"][i]), 0.1, p) for i in range(12)])
-    L = 4096
+    L = 4096 if sampling != "pool" else 512  # pool: K = p L entries
 
     def est(seed):
         r = mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.1, sampling=sampling, seed=seed,
@@ -200,11 +200,11 @@ def test_k1_empty_poset_given_times():
     assert np.abs((mean - np.concatenate([ex[:, 0], ex[:, 1]])) / se).max() < 4.0
 
 
-@pytest.mark.parametrize("sampling,kw", [("forward", {}), ("backward", {}), ("bernoulli", {})])
+@pytest.mark.parametrize("sampling,kw", [("forward", {}), ("backward", {}), ("bernoulli", {}), ("pool", {})])
 def test_estep_statistics_match_oracle(oracle, sampling, kw):
     """Per-observation sum w / L_eff, E[d], E[Z] from independent streams: GPU (Philox) vs oracle (mt19937)."""
     c = synth.make_config(8, 10, eps=0.1, seed=17, density=0.3)
-    L = 2048 if sampling != "backward" else 9 * 200
+    L = {"backward": 9 * 200, "pool": 256}.get(sampling, 2048)
 
     def run(fn):
         def est(seed):
@@ -224,7 +224,7 @@ def test_estep_statistics_match_oracle(oracle, sampling, kw):
 
 
 @pytest.mark.parametrize("sampling,L,k,eps_true", [("forward", 300, 1, 0.05), ("backward", 37 * 10, 2, 0.05),
-                                                   ("bernoulli", 300, 1, 0.0)])
+                                                   ("bernoulli", 300, 1, 0.0), ("pool", 100, 1, 0.05)])
 def test_mcem_fixed_point_matches_oracle(oracle, sampling, L, k, eps_true):
     """Converged lambda, eps and observed log-likelihood from independent RNG streams agree with the reference
     restatement within 3 Monte-Carlo standard errors (north_star), s.e. from replicate seeds on both sides.
@@ -317,3 +317,47 @@ def test_full_size_config2_properties():
     pb.em_iterations(1000, n_iter=3, seed=2)
     out = pb.read()
     assert np.abs(out["lambda_"] / c["lambdas"] - 1).max() < 0.25 and abs(out["eps"] - 0.05) < 0.01
+
+
+def test_pool_given_times_matches_forward_exact():
+    """pool with sampling times available: X_k = [T_k <= t_i]; estimate against the K2' matrix-exponential answer."""
+    c = synth.make_config(6, 10, eps=0.1, seed=31, density=0.3)
+    ex = []
+    for i in range(10):
+        px = exact.genotype_probs_time(c["poset"], c["lambdas"], c["times"][i])
+        ex.append(exact.obs_prob_and_dist(px, exact.mask_of(c["obs"][i]), 0.1, 6))
+    ex = np.array(ex)
+    L = 512
+
+    def est(seed):
+        r = mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.1, time=c["times"], sampling="pool", seed=seed)
+        return np.concatenate([r["w"] / L, r["dist"]])
+
+    mean, se = _mean_se(est, range(500, 524))
+    assert np.abs((mean - np.concatenate([ex[:, 0], ex[:, 1]])) / se).max() < 4.0
+
+
+def test_otcbn_mcem_matches_oracle(oracle):
+    """Legacy OT-CBN entry (`MCEM`, src/mcem.cpp:307-335): noise-free model, conditional proposal with X == Y."""
+    c = synth.make_config(7, 300, eps=0.0, seed=41, density=0.3)
+    kw = dict(max_iter=40, nrOfSamples=16)
+    g = np.array([np.concatenate([r["lambda_"], [r["llhood"]]]) for r in
+                  (mc.estimate_mutation_rates(c["poset"], c["obs"], ilambda=c["lambda0"], zeta=0.2, seed=s, **kw)
+                   for s in range(1, 17))])
+    o = np.array([np.concatenate([r["lambda_"], [r["llhood"]]]) for r in
+                  (oracle.MCEM_otcbn(c["lambda0"], c["poset"], c["obs"], alpha=0.2, seed=s, **kw)
+                   for s in range(101, 117))])
+    se = np.sqrt(g.var(axis=0, ddof=1) / 16 + o.var(axis=0, ddof=1) / 16)
+    z = (g.mean(axis=0) - o.mean(axis=0)) / se
+    assert np.abs(z).max() < 3.75, z
+    # with sampling times given
+    g2 = mc.estimate_mutation_rates(c["poset"], c["obs"], sampling_times=c["times"], ilambda=c["lambda0"], seed=3, **kw)
+    o2 = oracle.MCEM_otcbn(c["lambda0"], c["poset"], c["obs"], times=c["times"], seed=3, **kw)
+    assert np.abs(g2["lambda_"] / o2["lambda_"] - 1).max() < 0.1
+    # incompatible genotype with non-zero weight: the R wrapper's error (R/mcem_param_est.r:57-59)
+    bad = c["obs"].copy()
+    u, v = [int(a[0]) for a in np.nonzero(c["poset"])]
+    bad[0, u], bad[0, v] = 0, 1
+    with pytest.raises(mc.MccbnError) as e:
+        mc.estimate_mutation_rates(c["poset"], bad, ilambda=c["lambda0"], seed=1, **kw)
+    assert "incompatible with the poset" in str(e.value)
