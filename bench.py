@@ -33,7 +33,9 @@ CONFIGS = {
     "cfg1": (10, 100, 100, 0.01, "forward", "README H-CBN2 example p=10 N=100 L=100"),
     "cfg2": (16, 10000, 1000, 0.05, "forward", "MCEM.hcbn p=16 N=10,000 L=1,000"),
     "cfg3": (30, 100000, 10000, 0.05, "forward", "MCEM.hcbn p=30 N=100,000 L=10,000"),
+    "cfg4": (20, 10000, 1000, 0.05, "forward", "ASA-sized E-step p=20 N=10,000 L=1,000"),
     "cfg5": (25, 50000, 5000, 0.05, "backward", "MCEM.hcbn backward k=1 p=25 N=50,000 L=5,000 eps=0.05"),
+    "cfg5pool": (25, 50000, 5000, 0.05, "pool", "MCEM.hcbn pool K=125,000 p=25 N=50,000 L=5,000 eps=0.05"),
 }
 
 

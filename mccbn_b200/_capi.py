@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmccbn_b200.so")
+LIB_PATH = os.environ.get("MCCBN_B200_LIB") or os.path.join(_HERE, "libmccbn_b200.so")  # override: kernel-variant experiments
 
 OK, ERR_NOT_ACYCLIC, ERR_ZERO_WEIGHT, ERR_CUDA, ERR_ARG, ERR_IO = 0, 1, 2, 3, 4, 5
 NCCL_ID_BYTES = 128
