@@ -62,12 +62,15 @@ struct DevModel {
 struct PosetProg {
   int p;
   unsigned store_mask;   // bit k: T_k has children -> stage it
-  unsigned multi_mask;   // bit k: node k has more than two parents -> rare path below
+  unsigned multi_mask;   // bit k: node k has more than two parents -> `xo[k]` holds parents 3..6
   unsigned valid_mask;   // (1 << p) - 1
+  unsigned huge_mask;    // bit k: node k has more than six parents -> CSR loop over the rest
+  unsigned pad[3];
   uint2 off[kFastMaxP];            // byte offsets (within the thread's column) of the first two parents' rows
+  uint4 xo[kFastMaxP];             // parents 3..6 of nodes with in-degree > 2 (dummy row where absent)
   unsigned char ev[kFastMaxP];     // event id at position k
   unsigned parent_mask[kFastMaxP]; // parents of k as a bitmask over positions (compatibility checks)
-  unsigned short xstart[kFastMaxP + 2];  // CSR over `xoff`: third and further parents of node k
+  unsigned short xstart[kFastMaxP + 2];  // CSR over `xoff`: seventh and further parents of node k
   unsigned short xoff[kMaxEdgesFast];
 };
 

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
       for (int l0 = l_begin; l0 < l_end; l0 += 32) {
         const int l = l0 + lane;
         uint32_t Xt = yt;
-        if (MODE == kCondBernoulli) {
+        if constexpr (MODE == kCondBernoulli) {
           // coin_tossing: flip each bit independently with probability eps (32 random bits per coin)
           uint4 rc = make_uint4(0, 0, 0, 0);
 #pragma unroll

@@ -98,16 +98,23 @@ __device__ __forceinline__ void sts_at(uint32_t saddr, real v) {
 }
 
 // max over the parents of node k (0 without parents): two unconditional loads (absent parents read the dummy
-// row, which holds 0) + a warp-uniform, non-unrolled loop over the third and further parents (in-degree > 2)
+// row, which holds 0); nodes with in-degree > 2 (warp-uniform test) read four more rows unconditionally, and only
+// in-degree > 6 falls back to a loop.
 template <typename real>
 __device__ __forceinline__ real parents_max(const PosetProg& pg, const unsigned multi_mask, const int k,
                                             const uint32_t tcol_s) {
   const uint2 o = pg.off[k];
   real m = max(lds_at<real>(tcol_s + o.x), lds_at<real>(tcol_s + o.y));
   if ((multi_mask >> k) & 1u) {
-    const int e1 = pg.xstart[k + 1];
+    const uint4 x = pg.xo[k];
+    m = max(m, max(max(lds_at<real>(tcol_s + x.x), lds_at<real>(tcol_s + x.y)),
+                   max(lds_at<real>(tcol_s + x.z), lds_at<real>(tcol_s + x.w))));
+    if ((pg.huge_mask >> k) & 1u) {
+      const int e1 = pg.xstart[k + 1];
 #pragma unroll 1
-    for (int e = pg.xstart[k]; e < e1; ++e) m = max(m, lds_at<real>(tcol_s + (uint32_t)pg.xoff[e] * (sizeof(real) / 4)));
+      for (int e = pg.xstart[k]; e < e1; ++e)
+        m = max(m, lds_at<real>(tcol_s + (uint32_t)pg.xoff[e] * (sizeof(real) / 4)));
+    }
   }
   return m;
 }

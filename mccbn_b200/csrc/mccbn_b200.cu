@@ -87,6 +87,7 @@ static PosetProg build_prog(const FlatPoset& f, int pmax, int elem_bytes) {
   int x = 0;
   for (int k = 0; k < kFastMaxP; ++k) {
     g.off[k] = make_uint2(dummy, dummy);
+    g.xo[k] = make_uint4(dummy, dummy, dummy, dummy);
     g.xstart[k] = (unsigned short)x;
     if (k >= f.p) continue;
     g.ev[k] = (unsigned char)f.topo[k];
@@ -94,11 +95,19 @@ static PosetProg build_prog(const FlatPoset& f, int pmax, int elem_bytes) {
     int n = 0;
     for (uint64_t m = f.parent_pos[k]; m; m &= m - 1, ++n) {
       const unsigned row = (unsigned)ctz64(m);
-      if (n == 0) g.off[k].x = row * kFwdBlock * elem_bytes;
-      else if (n == 1) g.off[k].y = row * kFwdBlock * elem_bytes;
-      else g.xoff[x++] = (unsigned short)(row * kFwdBlock * 4);
+      const unsigned o = row * kFwdBlock * elem_bytes;
+      switch (n) {
+        case 0: g.off[k].x = o; break;
+        case 1: g.off[k].y = o; break;
+        case 2: g.xo[k].x = o; break;
+        case 3: g.xo[k].y = o; break;
+        case 4: g.xo[k].z = o; break;
+        case 5: g.xo[k].w = o; break;
+        default: g.xoff[x++] = (unsigned short)(row * kFwdBlock * 4); break;
+      }
     }
     if (n > 2) g.multi_mask |= 1u << k;
+    if (n > 6) g.huge_mask |= 1u << k;
   }
   g.xstart[kFastMaxP] = g.xstart[kFastMaxP + 1] = (unsigned short)x;
   for (int k = f.p; k < kFastMaxP; ++k) g.xstart[k] = (unsigned short)x;
