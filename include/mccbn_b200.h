@@ -204,6 +204,15 @@ int mccbn_problem_read(mccbn_problem* pb, double* lambda, double* eps, double* l
 /* the CUDA stream the problem's work is enqueued on (for event timing by the caller) */
 void* mccbn_problem_stream(mccbn_problem* pb);
 
+/* Poset-specialised forward kernels (NVRTC, csrc/jit.cuh).  mode: -1 auto (only when N*L >= 2e8 samples per
+ * E-step, default; env MCCBN_JIT=0/1 overrides), 0 never, 1 always.  The specialised and the generic kernel draw the
+ * same random stream and produce the same records. */
+int mccbn_set_jit(mccbn_ctx* ctx, int mode);
+/* host-only: generate and compile (no device needed) the specialised kernel of `poset`; log = NVRTC / ptxas -v
+ * output, source = generated CUDA text (either may be NULL) */
+int mccbn_jit_compile_forward(const int* poset, int p, int times_given, size_t* cubin_bytes, double* compile_ms,
+                              char* log, size_t loglen, char* source, size_t sourcelen, char* err, size_t errlen);
+
 /* Host-only test seam for the poset edit operations the annealer uses (Model::add_edge, remove_edge, add_relation,
  * remove_relation, transitive_reduction_dag, swap_node; src/model_impl.cpp:145-316; the reference exposes the
  * debug exports `_remove_test` / `_transitive_reduction_dag`, src/asa.cpp:667-735).  op: 0 add_edge, 1 remove_edge,

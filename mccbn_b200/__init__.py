@@ -9,6 +9,6 @@ from .api import (Context, Problem, MCEM_hcbn, adaptive_simulated_annealing, com
                   conditional_from_uniforms, device_count, estep_forward_from_times, estimate_mutation_rates,
                   flatten_poset,
                   forward_from_times, importance_weight, initialize_lambda, neighbors, nccl_unique_id,
-                  obs_loglikelihood, poset_edit)
+                  obs_loglikelihood, poset_edit, set_jit, jit_compile_forward)
 
 __version__ = "0.1.0"

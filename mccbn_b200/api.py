@@ -322,6 +322,23 @@ def neighbors(p, k, genotype):
     return out, ring
 
 
+def set_jit(mode, ctx=None):
+    """-1 auto, 0 never, 1 always use the NVRTC poset-specialised forward kernel (csrc/jit.cuh)."""
+    capi.lib().mccbn_set_jit(_ctx(ctx), int(mode))
+
+
+def jit_compile_forward(poset, times_given=False):
+    """Host-only: generate + compile the specialised kernel of a poset; returns dict(cubin_bytes, ms, log, source)."""
+    poset = i32(poset)
+    n, ms = C.c_size_t(0), C.c_double(0)
+    log = C.create_string_buffer(1 << 16)
+    src = C.create_string_buffer(1 << 18)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_jit_compile_forward(ptr(poset), poset.shape[0], int(times_given), C.byref(n), C.byref(ms),
+                                                 log, C.c_size_t(len(log)), src, C.c_size_t(len(src)), *e.args))
+    return dict(cubin_bytes=n.value, ms=ms.value, log=log.value.decode(), source=src.value.decode())
+
+
 POSET_OPS = dict(add_edge=0, remove_edge=1, add_relation=2, remove_relation=3, transitive_reduction=4, swap_node=5)
 
 

@@ -12,7 +12,15 @@
 // The static poset program is a __grid_constant__ kernel parameter (PosetProg); the lambda-derived scales live
 // in __constant__ memory (FwdScale), refreshed by a device-to-device copy after every on-device M-step.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#else  // NVRTC (poset-specialised kernels, jit.cuh): no standard headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#endif
 
 namespace mccbn {
 

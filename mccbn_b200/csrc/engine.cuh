@@ -92,6 +92,10 @@ struct DevBuf {  // grow-only device buffer
 
 }  // namespace mccbn
 
+namespace mccbn {
+struct JitCache;
+}
+
 struct mccbn_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -101,4 +105,6 @@ struct mccbn_ctx {
   mccbn::NcclApi::comm_t comm = nullptr;
   int rank = 0, world = 1;
   uint64_t launches = 0;
+  mccbn::JitCache* jit = nullptr;  // poset-specialised kernels (jit.cuh)
+  int jit_mode = -1;               // -1 auto (large problems only), 0 off, 1 always
 };

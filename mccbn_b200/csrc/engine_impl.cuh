@@ -70,9 +70,9 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.cw = eval_id[c];
     a.PS = PS();
     if (precision == 1)
-      launch_forward<double>(a, flat[c], times_given, grid_x);
+      launch_forward<double>(a, flat[c], times_given, grid_x, c);
     else
-      launch_forward<float>(a, flat[c], times_given, grid_x);
+      launch_forward<float>(a, flat[c], times_given, grid_x, c);
   } else if (scheme == kBackward || scheme == kBernoulli || scheme == kOtcbn) {
     CondArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -457,6 +457,7 @@ int mccbn_ctx_create(mccbn_ctx** out, int device, char* err, size_t errlen) {
 void mccbn_ctx_destroy(mccbn_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  delete c->jit;
   if (c->comm) c->nccl.CommDestroy(c->comm);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -1025,6 +1026,37 @@ double mccbn_microbench_philox(mccbn_ctx* c, int reps) {
   } catch (...) {
     return 0.0;
   }
+}
+
+// ---- poset-specialised kernels (NVRTC) ---------------------------------------------------------------------------
+int mccbn_set_jit(mccbn_ctx* c, int mode) {
+  char* err = nullptr;
+  size_t errlen = 0;
+  MCCBN_TRY
+  c = get_ctx(c);
+  c->jit_mode = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  MCCBN_CATCH
+}
+
+// host-only: generate + compile the specialised forward kernel of a poset (no device needed); log receives the
+// NVRTC / ptxas -v output, source (optional) the generated CUDA text
+int mccbn_jit_compile_forward(const int* poset, int p, int times_given, size_t* cubin_bytes, double* compile_ms,
+                              char* log, size_t loglen, char* source, size_t sourcelen, char* err, size_t errlen) {
+  MCCBN_TRY
+  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  static NvrtcApi rtc;
+  const std::string src = generate_forward_source(f, times_given != 0, 6);
+  if (source && sourcelen) std::snprintf(source, sourcelen, "%s", src.c_str());
+  JitCompiled cc;
+  const bool ok = jit_compile(rtc, src, cc);
+  if (log && loglen) std::snprintf(log, loglen, "%s", cc.log.c_str());
+  if (cubin_bytes) *cubin_bytes = cc.cubin.size();
+  if (compile_ms) *compile_ms = cc.compile_ms;
+  if (!ok) throw Error(MCCBN_ERR_CUDA, "NVRTC compilation failed: " + cc.log);
+  MCCBN_CATCH
 }
 
 // ---- host-only test seam for the poset edit operations of the annealer (src/model_impl.cpp:145-316) --------------

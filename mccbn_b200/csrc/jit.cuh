@@ -1,0 +1,236 @@
+// jit.cuh -- poset-specialised forward E-step kernels through NVRTC.
+//
+// The poset is a run-time input, but it is constant for a whole MCEM run (hundreds of E-steps over 1e7..1e9 samples
+// each).  The generic kernel (kernels_forward.cuh) interprets the poset program per sample: event times live in a
+// shared-memory column, every node pays two unconditional LDS + one STS + constant-bank loads + a warp-uniform test
+// for further parents (ncu r1b: 1167 instructions per sample for p = 30).  When the sampling work is large enough to
+// amortise a compilation, the same hand-written kernel body (estep_forward_body, #included verbatim from the embedded
+// headers) is instantiated with a sampler in which the poset is unrolled into straight-line code: event times in
+// registers, exactly |E| FMNMX, immediate bit masks, no parent loads / stores / tests.  The random stream, the weight
+// handling, the reduction and the output records are those of the generic kernel, so both produce the same
+// per-sample values (tests/test_gpu_jit.py compares them bit for bit on the dump seam and to 1e-6 on the sums).
+//
+// NVRTC (libnvrtc.so.12) and the loaded module are reached through dlopen / the CUDA runtime library-management API;
+// if NVRTC is unavailable or compilation fails the generic kernel is used (still the device path, never the CPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <chrono>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "_embedded_sources.inc"
+#include "engine.cuh"
+
+namespace mccbn {
+
+struct NvrtcApi {
+  typedef struct _nvrtcProgram* program_t;
+  void* lib = nullptr;
+  int (*CreateProgram)(program_t*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(program_t, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(program_t, size_t*) = nullptr;
+  int (*GetCUBIN)(program_t, char*) = nullptr;
+  int (*GetProgramLogSize)(program_t, size_t*) = nullptr;
+  int (*GetProgramLog)(program_t, char*) = nullptr;
+  int (*DestroyProgram)(program_t*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool tried = false;
+
+  bool load() {
+    if (lib) return true;
+    if (tried) return false;
+    tried = true;
+    const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
+    for (const char* n : names)
+      if ((lib = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!lib) return false;
+    bool ok = true;
+    auto sym = [&](const char* s) {
+      void* f = dlsym(lib, s);
+      if (!f) ok = false;
+      return f;
+    };
+    CreateProgram = (decltype(CreateProgram))sym("nvrtcCreateProgram");
+    CompileProgram = (decltype(CompileProgram))sym("nvrtcCompileProgram");
+    GetCUBINSize = (decltype(GetCUBINSize))sym("nvrtcGetCUBINSize");
+    GetCUBIN = (decltype(GetCUBIN))sym("nvrtcGetCUBIN");
+    GetProgramLogSize = (decltype(GetProgramLogSize))sym("nvrtcGetProgramLogSize");
+    GetProgramLog = (decltype(GetProgramLog))sym("nvrtcGetProgramLog");
+    DestroyProgram = (decltype(DestroyProgram))sym("nvrtcDestroyProgram");
+    GetErrorString = (decltype(GetErrorString))sym("nvrtcGetErrorString");
+    if (!ok) lib = nullptr;
+    return ok;
+  }
+};
+
+// ---- source generation ------------------------------------------------------------------------------------------
+static int jit_pmax(int p) { return (p + 3) / 4 * 4; }
+
+static std::string jit_key(const FlatPoset& f, bool times_given, int minb) {
+  std::ostringstream k;
+  k << f.p << (times_given ? "t" : "s") << minb;
+  for (int i = 0; i < f.p; ++i) k << ":" << std::hex << f.parent_pos[i];
+  return k.str();
+}
+
+static std::string generate_forward_source(const FlatPoset& f, bool times_given, int minb) {
+  const int p = f.p, pmax = jit_pmax(p);
+  std::ostringstream s;
+  s << "#include \"kernels_forward.cuh\"\n"
+       "namespace mccbn {\n"
+       "// generated for one poset: node k = topological position k, t<k> = event time, parents unrolled\n"
+       "struct SpecSampler {\n"
+       "  static constexpr bool kStagesT = false;\n"
+       "  __device__ __forceinline__ void operator()(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zcol_s,\n"
+       "      const uint32_t l, const uint32_t gi, const uint32_t k0, const uint32_t k1, const uint32_t cw,\n"
+       "      const float ts_given, const ScaleSrc<float, "
+    << pmax
+    << "> scale, uint32_t& X, float& Ts_out) const {\n"
+       "    constexpr uint32_t kRow = kFwdBlock * 4u;\n"
+       "    uint4 r;\n"
+       "    float Ts = ts_given;\n"
+       "    uint32_t x = 0u;\n";
+  const char* word[4] = {"r.x", "r.y", "r.z", "r.w"};
+  for (int k = 0; k < p; ++k) {
+    if (k % 4 == 0) {
+      s << "    r = philox4x32_10(l, gi, " << (k / 4) << "u, cw, k0, k1);\n";
+      if (k == 0 && !times_given)
+        s << "    {\n"
+             "      const uint32_t low = (r.x & 0x1ffu) | ((r.y & 0x1ffu) << 9) | ((r.z & 0x1fu) << 18);\n"
+             "      Ts = fast_lg2(2.0f - __uint_as_float(low | 0x3f800000u)) * c_scale.cs;\n"
+             "    }\n";
+    }
+    s << "    const float z" << k << " = fast_lg2(u01_open0(" << word[k % 4] << ")) * c_scale.c[" << k << "];";
+    // max over parents, balanced so that the compiler can form FMNMX3
+    std::vector<std::string> terms;
+    for (uint64_t m = f.parent_pos[k]; m; m &= m - 1) terms.push_back("t" + std::to_string(ctz64(m)));
+    while (terms.size() > 1) {
+      std::vector<std::string> nxt;
+      for (size_t i = 0; i + 1 < terms.size(); i += 2) nxt.push_back("fmaxf(" + terms[i] + ", " + terms[i + 1] + ")");
+      if (terms.size() & 1) nxt.push_back(terms.back());
+      terms.swap(nxt);
+    }
+    s << "  const float t" << k << " = z" << k;
+    if (!terms.empty()) s << " + " << terms[0];
+    s << ";  sts_at_f(zcol_s + " << k << "u * kRow, z" << k << ");  if (t" << k << " <= Ts) x |= 0x" << std::hex
+      << (1u << k) << std::dec << "u;\n";
+  }
+  s << "    X = x;\n"
+       "    Ts_out = Ts;\n"
+       "  }\n"
+       "};\n"
+       "}  // namespace mccbn\n"
+       "extern \"C\" __global__ void __launch_bounds__(mccbn::kFwdBlock, "
+    << minb
+    << ") mccbn_fwd_spec(const mccbn::FwdArgs a,\n"
+       "    const __grid_constant__ mccbn::PosetProg pg) {\n"
+       "  mccbn::estep_forward_body<float, "
+    << pmax << ", " << (times_given ? "true" : "false")
+    << ">(a, pg, mccbn::SpecSampler{});\n"
+       "}\n";
+  return s.str();
+}
+
+struct JitCompiled {
+  std::vector<char> cubin;
+  std::string log;
+  double compile_ms = 0;
+};
+
+// compile only (no device needed): returns false + log on failure
+static bool jit_compile(NvrtcApi& rtc, const std::string& src, JitCompiled& out) {
+  if (!rtc.load()) {
+    out.log = "libnvrtc.so.12 could not be loaded";
+    return false;
+  }
+  const char* hdr_src[] = {kSrc_device_types_cuh, kSrc_philox_cuh, kSrc_kernels_forward_cuh};
+  const char* hdr_name[] = {"device_types.cuh", "philox.cuh", "kernels_forward.cuh"};
+  NvrtcApi::program_t prog = nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = rtc.CreateProgram(&prog, src.c_str(), "mccbn_fwd_spec.cu", 3, hdr_src, hdr_name);
+  if (rc != 0) {
+    out.log = std::string("nvrtcCreateProgram: ") + rtc.GetErrorString(rc);
+    return false;
+  }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--ptxas-options=-v"};
+  rc = rtc.CompileProgram(prog, 4, opts);
+  size_t ls = 0;
+  rtc.GetProgramLogSize(prog, &ls);
+  if (ls > 1) {
+    out.log.resize(ls);
+    rtc.GetProgramLog(prog, &out.log[0]);
+  }
+  bool ok = rc == 0;
+  if (ok) {
+    size_t n = 0;
+    ok = rtc.GetCUBINSize(prog, &n) == 0 && n > 0;
+    if (ok) {
+      out.cubin.resize(n);
+      ok = rtc.GetCUBIN(prog, out.cubin.data()) == 0;
+    }
+  } else {
+    out.log = std::string("nvrtcCompileProgram: ") + rtc.GetErrorString(rc) + "\n" + out.log;
+  }
+  rtc.DestroyProgram(&prog);
+  out.compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return ok;
+}
+
+struct JitKernel {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kern = nullptr;
+  void* scale_sym = nullptr;
+  size_t smem = 0;
+  int pmax = 0;
+  bool ok = false;
+  double compile_ms = 0;
+};
+
+struct JitCache {
+  NvrtcApi rtc;
+  std::map<std::string, JitKernel> kernels;
+  int minb = 5;
+
+  JitCache() {
+    if (const char* e = std::getenv("MCCBN_JIT_MINB")) minb = std::max(1, std::min(8, std::atoi(e)));
+  }
+
+  JitKernel* get(const FlatPoset& f, bool times_given) {
+    const std::string key = jit_key(f, times_given, minb);
+    auto it = kernels.find(key);
+    if (it != kernels.end()) return it->second.ok ? &it->second : nullptr;
+    JitKernel jk;
+    JitCompiled cc;
+    const std::string src = generate_forward_source(f, times_given, minb);
+    if (jit_compile(rtc, src, cc)) {
+      cudaError_t e = cudaLibraryLoadData(&jk.lib, cc.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+      if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.kern, jk.lib, "mccbn_fwd_spec");
+      size_t bytes = 0;
+      if (e == cudaSuccess) e = cudaLibraryGetGlobal(&jk.scale_sym, &bytes, jk.lib, "_ZN5mccbn7c_scaleE");
+      if (e == cudaSuccess && bytes == sizeof(FwdScale)) {
+        jk.ok = true;
+        jk.pmax = jit_pmax(f.p);
+        jk.smem = sizeof(float) * (size_t)jk.pmax * kFwdBlock;
+        jk.compile_ms = cc.compile_ms;
+      } else {
+        std::fprintf(stderr, "mccbn_b200: loading the specialised kernel failed (%s); using the generic kernel\n",
+                     cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    } else {
+      std::fprintf(stderr, "mccbn_b200: NVRTC specialisation failed, using the generic kernel\n%s\n", cc.log.c_str());
+    }
+    if (std::getenv("MCCBN_JIT_VERBOSE"))
+      std::fprintf(stderr, "mccbn_b200: specialised forward kernel p=%d %s: %s in %.0f ms\n%s\n", f.p,
+                   times_given ? "times given" : "times sampled", jk.ok ? "compiled" : "FAILED", cc.compile_ms,
+                   cc.log.c_str());
+    auto res = kernels.emplace(key, jk);
+    return res.first->second.ok ? &res.first->second : nullptr;
+  }
+};
+
+}  // namespace mccbn

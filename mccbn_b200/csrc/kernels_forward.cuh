@@ -185,18 +185,31 @@ __device__ __forceinline__ void load_scales_fp64(const PosetProg& pg, const DevM
 #define MCCBN_FWD_MINB_BIG 5
 #endif
 template <typename real, int PMAX>
-constexpr size_t fwd_smem_bytes() {
-  return sizeof(real) * (size_t)(2 * PMAX + 1) * kFwdBlock;
+__host__ __device__ constexpr size_t fwd_smem_bytes(bool stages_t = true) {
+  return sizeof(real) * (size_t)(stages_t ? 2 * PMAX + 1 : PMAX) * kFwdBlock;
 }
 
+// The generic sampler interprets the poset program at run time (event times staged in shared memory).  A
+// poset-specialised sampler generated by jit.cuh has the same call signature with the poset unrolled into
+// straight-line code (event times in registers).
 template <typename real, int PMAX, bool TIMES_GIVEN>
-__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? (PMAX >= MCCBN_FWD_BIGP ? MCCBN_FWD_MINB_BIG : 6) : 1)
-    estep_forward_kernel(const FwdArgs a, const __grid_constant__ PosetProg pg) {
-  // dynamic shared memory (fwd_smem_bytes): rows 0..PMAX-1 staged T_k, row PMAX the dummy row (0), then PMAX rows
+struct GenericSampler {
+  static constexpr bool kStagesT = true;
+  __device__ __forceinline__ void operator()(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zcol_s,
+                                             const uint32_t l, const uint32_t gi, const uint32_t k0,
+                                             const uint32_t k1, const uint32_t cw, const real ts_given,
+                                             const ScaleSrc<real, PMAX> scale, uint32_t& X, real& Ts_out) const {
+    sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zcol_s, l, gi, k0, k1, cw, ts_given, scale, X, Ts_out);
+  }
+};
+
+template <typename real, int PMAX, bool TIMES_GIVEN, typename Sampler>
+__device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const PosetProg& pg, const Sampler sampler) {
+  // dynamic shared memory (fwd_smem_bytes): [rows 0..PMAX-1 staged T_k, row PMAX the dummy row (0),] then PMAX rows
   // of staged waiting times Z_k (frees PMAX registers per thread)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* s_T = reinterpret_cast<real*>(smem_raw);
-  real* s_Z = s_T + (PMAX + 1) * kFwdBlock;
+  real* s_Z = s_T + (Sampler::kStagesT ? (PMAX + 1) * kFwdBlock : 0);
   __shared__ real s_rtab[kRtabN];
   __shared__ real s_scale[PMAX + 1];  // fp64 mode only
 
@@ -204,7 +217,8 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? (PMAX >= MCCBN_
   const int p = pg.p;
   const int lane = threadIdx.x & 31;
   constexpr int kWarps = kFwdBlock / 32;
-  s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;
+  if (Sampler::kStagesT) s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;
+  for (int k = pg.p; k < PMAX; ++k) s_Z[k * kFwdBlock + threadIdx.x] = (real)0;  // unused node slots
   const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
   const uint32_t zcol_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x);
   constexpr uint32_t kRow = kFwdBlock * sizeof(real);
@@ -241,8 +255,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? (PMAX >= MCCBN_
       const bool valid = l < l_end;
       uint32_t X;
       real Ts;
-      sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zcol_s, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given,
-                                              scale, X, Ts);
+      sampler(pg, tcol_s, zcol_s, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given, scale, X, Ts);
       const int d = __popc(X ^ yt);
       const int de = flip ? p - d : d;  // weights decrease in `de`
       const int dmin = __reduce_min_sync(0xffffffffu, valid ? de : (1 << 19));
@@ -292,6 +305,12 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? (PMAX >= MCCBN_
     }
     if (lane < p) out[kStatHdr + lane] = mine;
   }
+}
+
+template <typename real, int PMAX, bool TIMES_GIVEN>
+__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? (PMAX >= MCCBN_FWD_BIGP ? MCCBN_FWD_MINB_BIG : 6) : 1)
+    estep_forward_kernel(const FwdArgs a, const __grid_constant__ PosetProg pg) {
+  estep_forward_body<real, PMAX, TIMES_GIVEN>(a, pg, GenericSampler<real, PMAX, TIMES_GIVEN>{});
 }
 
 // Per-sample dump for ONE observation (the `_importance_weight_genotype` seam, src/mcem_hcbn.cpp:866-912):

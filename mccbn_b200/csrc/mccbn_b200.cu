@@ -15,6 +15,7 @@
 #include <mutex>
 
 #include "engine.cuh"
+#include "jit.cuh"
 #include "kernels_cond.cuh"
 #include "kernels_forward.cuh"
 #include "kernels_fp64.cuh"
@@ -210,9 +211,33 @@ struct mccbn_problem {
     }
   }
 
-  template <typename real>
-  void launch_forward(const FwdArgs& a, const FlatPoset& f, bool times_given, int grid) {
+  // poset-specialised kernel (jit.cuh) when the sampling work amortises a compilation
+  bool launch_forward_jit(const FwdArgs& a, const FlatPoset& f, int c, bool times_given, int grid) {
+    int mode = ctx->jit_mode;
+    if (mode < 0) {
+      const char* e = std::getenv("MCCBN_JIT");
+      if (e && std::strcmp(e, "0") == 0) mode = 0;
+      else if (e && std::strcmp(e, "1") == 0) mode = 1;
+    }
+    if (mode == 0) return false;
+    if (mode < 0 && (double)N * (double)a.L < 2e8) return false;  // auto: large E-steps only
+    if (!ctx->jit) ctx->jit = new JitCache();
+    JitKernel* jk = ctx->jit->get(f, times_given);
+    if (!jk) return false;
     cudaStream_t s = ctx->stream;
+    MCCBN_CUDA(cudaMemcpyAsync(jk->scale_sym, scales.ptr + c, sizeof(FwdScale), cudaMemcpyDeviceToDevice, s));
+    PosetProg pg = build_prog(f, jk->pmax, 4);
+    FwdArgs args = a;
+    void* params[] = {(void*)&args, (void*)&pg};
+    MCCBN_CUDA(cudaLaunchKernel((const void*)jk->kern, dim3(grid), dim3(kFwdBlock), params, jk->smem, s));
+    ctx->launches++;
+    return true;
+  }
+
+  template <typename real>
+  void launch_forward(const FwdArgs& a, const FlatPoset& f, bool times_given, int grid, int c = 0) {
+    cudaStream_t s = ctx->stream;
+    if (sizeof(real) == 4 && launch_forward_jit(a, f, c, times_given, grid)) return;
 #define MCCBN_FWD(PM)                                                                                   \
   do {                                                                                                  \
     const PosetProg pg = build_prog(f, PM, (int)sizeof(real));                                          \

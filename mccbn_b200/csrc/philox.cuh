@@ -7,7 +7,7 @@
 // so a draw depends only on (seed, iteration, i, l, b): independent of grid shape, chunking and of how the
 // observations are sharded over GPUs.
 #pragma once
-#include <cstdint>
+#include "device_types.cuh"
 
 namespace mccbn {
 

@@ -88,3 +88,20 @@ def test_r_wrapper_argument_rules():
                              sampling="naive")
     with pytest.raises(TypeError):
         mc.MCEM_hcbn(np.ones(3), np.zeros((3, 3), np.int32), np.zeros((2, 3), np.int32))
+
+
+def test_jit_source_generation_and_nvrtc_compile():
+    """The NVRTC specialisation is a pure compiler step: it can be checked without a GPU."""
+    c = synth.make_config(9, 5, seed=2, density=0.3)
+    try:
+        r = mc.jit_compile_forward(c["poset"])
+    except mc.MccbnError as e:
+        if "could not be loaded" in str(e):
+            pytest.skip("libnvrtc not available")
+        raise
+    assert r["cubin_bytes"] > 10000
+    assert "mccbn_fwd_spec" in r["source"] and "estep_forward_body<float, 12, false>" in r["source"]
+    topo, _ = mc.flatten_poset(c["poset"])
+    assert r["source"].count("fast_lg2(u01_open0(") == 9  # one exponential per event
+    assert r["source"].count("fmaxf(") == sum(max(0, int(d) - 1) for d in c["poset"].sum(axis=0))  # |E| - #non-roots
+    assert "registers" in r["log"]
