@@ -162,6 +162,8 @@ def run_ours(args):
     ctx = mc.Context(local)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
+    # forward scheme: NVRTC poset-specialised kernel (csrc/jit.cuh); compiled once during warm-up
+    mc.set_jit(0 if args.no_jit else 1, ctx=ctx)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -239,7 +241,9 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32 sampling / f64 reduction", "data": "synthetic",
         "config": {"workload": f"{args.config}: {desc}", "sampling": sampling, "p": p, "N": N, "L": L,
                    "sec_per_mcem_iteration": ms * 1e-3, "l2": "256 MiB buffer written between timed iterations",
-                   "parallelism": f"observations sharded over {world} rank(s), 1 allreduce of p+5 doubles / iteration"},
+                   "parallelism": f"observations sharded over {world} rank(s), 1 allreduce of p+5 doubles / iteration",
+                   "kernel": ("generic estep_forward_kernel" if args.no_jit or sampling != "forward" else
+                              "NVRTC poset-specialised estep_forward_body (compiled during warm-up)")},
         "e2e": {"value": N * L_eff / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "call": "mccbn_obs_log_likelihood (host buffers, one E-step)"},
         "gpu_launches": int(launches),
@@ -308,6 +312,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-jit", action="store_true", help="time the generic (poset-interpreting) forward kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -233,6 +233,7 @@ static std::vector<EmResult> run_mcem_multi(mccbn_problem& pb, const std::vector
   if (ctl.update_step_size == 0) throw Error(MCCBN_ERR_ARG, "update_step_size must be >= 1");
   const int stride = p + 2;
   pb.ensure_trace((int)std::max(1u, ctl.max_iter));
+  pb.expected_esteps = (int)std::max(1u, ctl.max_iter / 2);
   std::vector<EmRun> runs(slots.size());
   for (size_t r = 0; r < slots.size(); ++r) {
     runs[r].slot = slots[r];

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <map>
@@ -190,23 +191,78 @@ struct JitKernel {
   double compile_ms = 0;
 };
 
+static uint64_t fnv1a64(const std::string& s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char c : s) {
+    h ^= c;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+// optional on-disk cubin cache ($MCCBN_CACHE_DIR, default ~/.cache/mccbn_b200): makes the compilation a one-time cost
+static std::string jit_cache_path(const std::string& src) {
+  std::string dir;
+  if (const char* e = std::getenv("MCCBN_CACHE_DIR")) dir = e;
+  else if (const char* h = std::getenv("HOME")) dir = std::string(h) + "/.cache/mccbn_b200";
+  if (dir.empty() || dir == "off") return "";
+  (void)!system(("mkdir -p '" + dir + "' 2>/dev/null").c_str());
+  char name[64];
+  std::snprintf(name, sizeof name, "/fwd_%016llx.cubin", (unsigned long long)fnv1a64(src + kSrc_kernels_forward_cuh));
+  return dir + name;
+}
+
 struct JitCache {
   NvrtcApi rtc;
   std::map<std::string, JitKernel> kernels;
-  int minb = 5;
+  int minb = 4;  // 116 registers: best of {4,5,6} resident blocks on B200 (profiles/README.md)
 
   JitCache() {
     if (const char* e = std::getenv("MCCBN_JIT_MINB")) minb = std::max(1, std::min(8, std::atoi(e)));
   }
 
-  JitKernel* get(const FlatPoset& f, bool times_given) {
+  // `only_if_cached`: do not compile, return the kernel only if it is already in memory or on disk
+  JitKernel* get(const FlatPoset& f, bool times_given, bool only_if_cached = false) {
     const std::string key = jit_key(f, times_given, minb);
     auto it = kernels.find(key);
     if (it != kernels.end()) return it->second.ok ? &it->second : nullptr;
+    if (only_if_cached) {
+      const std::string p0 = jit_cache_path(generate_forward_source(f, times_given, minb));
+      if (p0.empty()) return nullptr;
+      FILE* fp = std::fopen(p0.c_str(), "rb");
+      if (!fp) return nullptr;
+      std::fclose(fp);
+    }
     JitKernel jk;
     JitCompiled cc;
     const std::string src = generate_forward_source(f, times_given, minb);
-    if (jit_compile(rtc, src, cc)) {
+    const std::string path = jit_cache_path(src);
+    bool have = false;
+    if (!path.empty()) {
+      if (FILE* fp = std::fopen(path.c_str(), "rb")) {
+        std::fseek(fp, 0, SEEK_END);
+        const long n = std::ftell(fp);
+        std::fseek(fp, 0, SEEK_SET);
+        if (n > 0) {
+          cc.cubin.resize((size_t)n);
+          have = std::fread(cc.cubin.data(), 1, (size_t)n, fp) == (size_t)n;
+        }
+        std::fclose(fp);
+      }
+    }
+    if (!have && jit_compile(rtc, src, cc)) {
+      have = true;
+      if (!path.empty()) {  // write-then-rename: safe with several ranks compiling the same kernel
+        const std::string tmp = path + "." + std::to_string((long)getpid());
+        if (FILE* fp = std::fopen(tmp.c_str(), "wb")) {
+          const bool okw = std::fwrite(cc.cubin.data(), 1, cc.cubin.size(), fp) == cc.cubin.size();
+          std::fclose(fp);
+          if (okw) std::rename(tmp.c_str(), path.c_str());
+          else std::remove(tmp.c_str());
+        }
+      }
+    }
+    if (have) {
       cudaError_t e = cudaLibraryLoadData(&jk.lib, cc.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
       if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.kern, jk.lib, "mccbn_fwd_spec");
       size_t bytes = 0;
