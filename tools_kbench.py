@@ -28,8 +28,11 @@ def run(name, steps=5):
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     Leff = L if sampling != "backward" else (L // (p + 1)) * (p + 1)
-    out = pb.read()
-    print(f"{os.environ.get('MCCBN_B200_LIB','default'):40s} {name:10s} {sampling:9s} {ms:9.3f} ms/iter  {N*Leff/ms/1e6:10.1f} Msamples/s  eps={out['eps']:.4f}", flush=True)
+    try:
+        eps = "%.4f" % pb.read()["eps"]
+    except mc.MccbnError as e:
+        eps = "ERR(" + str(e)[:30] + ")"
+    print(f"{os.environ.get('MCCBN_B200_LIB','default')[-20:]:20s} jit={os.environ.get('MCCBN_JIT','auto'):4s} {name:9s} {sampling:9s} {ms:9.3f} ms/iter  {N*Leff/ms/1e6:9.2f} Gsamples/s  eps={eps}", flush=True)
 
 if __name__ == "__main__":
     for n in sys.argv[1:]:
