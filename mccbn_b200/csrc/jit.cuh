@@ -92,20 +92,27 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
     << pmax
     << "> scale, uint32_t& X, float& Ts_out) const {\n"
        "    constexpr uint32_t kRow = kFwdBlock * 4u;\n"
-       "    uint4 r;\n"
        "    float Ts = ts_given;\n"
        "    uint32_t x = 0u;\n";
-  const char* word[4] = {"r.x", "r.y", "r.z", "r.w"};
+  // G Philox blocks are generated in lock-step (philox4x32_10_multi) to expose ILP inside the RNG
+  int G = 2;
+  if (const char* e = std::getenv("MCCBN_JIT_PHILOX_ILP")) G = std::max(1, std::min(8, std::atoi(e)));
+  const int nblocks = (p + 3) / 4;
+  const char* comp[4] = {".x", ".y", ".z", ".w"};
   for (int k = 0; k < p; ++k) {
-    if (k % 4 == 0) {
-      s << "    r = philox4x32_10(l, gi, " << (k / 4) << "u, cw, k0, k1);\n";
+    if (k % (4 * G) == 0) {
+      const int b0 = k / 4, g = std::min(G, nblocks - b0);
+      s << "    uint4 r" << b0 << "[" << g << "];\n"
+        << "    philox4x32_10_multi<" << g << ">(l, gi, " << b0 << "u, cw, k0, k1, r" << b0 << ");\n";
       if (k == 0 && !times_given)
         s << "    {\n"
-             "      const uint32_t low = (r.x & 0x1ffu) | ((r.y & 0x1ffu) << 9) | ((r.z & 0x1fu) << 18);\n"
+             "      const uint32_t low = (r0[0].x & 0x1ffu) | ((r0[0].y & 0x1ffu) << 9) | ((r0[0].z & 0x1fu) << 18);\n"
              "      Ts = fast_lg2(2.0f - __uint_as_float(low | 0x3f800000u)) * c_scale.cs;\n"
              "    }\n";
     }
-    s << "    const float z" << k << " = fast_lg2(u01_open0(" << word[k % 4] << ")) * c_scale.c[" << k << "];";
+    const int b0 = (k / (4 * G)) * G;
+    const std::string w = "r" + std::to_string(b0) + "[" + std::to_string(k / 4 - b0) + "]" + comp[k % 4];
+    s << "    const float z" << k << " = fast_lg2(u01_open0(" << w << ")) * c_scale.c[" << k << "];";
     // max over parents, balanced so that the compiler can form FMNMX3
     std::vector<std::string> terms;
     for (uint64_t m = f.parent_pos[k]; m; m &= m - 1) terms.push_back("t" + std::to_string(ctz64(m)));

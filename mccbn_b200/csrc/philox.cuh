@@ -41,6 +41,41 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
   return make_uint4(c0, c1, c2, c3);
 }
 
+// N independent Philox blocks that differ only in counter word 2, advanced round by round in lock-step: the 2N
+// multiplies of a round are independent, which hides the IMAD.WIDE -> LOP3 dependency latency of a single chain
+// (used by the poset-specialised kernels, jit.cuh).
+template <int N>
+__device__ __forceinline__ void philox4x32_10_multi(const uint32_t c0, const uint32_t c1, const uint32_t c2_first,
+                                                    const uint32_t c3, uint32_t k0, uint32_t k1, uint4 (&out)[N]) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t a0[N], a1[N], a2[N], a3[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    a0[i] = c0;
+    a1[i] = c1;
+    a2[i] = c2_first + (uint32_t)i;
+    a3[i] = c3;
+  }
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const uint64_t p0 = (uint64_t)M0 * a0[i];
+      const uint64_t p1 = (uint64_t)M1 * a2[i];
+      const uint32_t n0 = (uint32_t)(p1 >> 32) ^ a1[i] ^ k0;
+      const uint32_t n2 = (uint32_t)(p0 >> 32) ^ a3[i] ^ k1;
+      a1[i] = (uint32_t)p1;
+      a3[i] = (uint32_t)p0;
+      a0[i] = n0;
+      a2[i] = n2;
+    }
+    k0 += W0;
+    k1 += W1;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = make_uint4(a0[i], a1[i], a2[i], a3[i]);
+}
+
 // 32 random bits -> u in (0, 1] with 23 random mantissa bits: u = 2 - [1,2)
 __device__ __forceinline__ float u01_open0(uint32_t bits) { return 2.0f - __uint_as_float((bits >> 9) | 0x3f800000u); }
 
