@@ -73,7 +73,8 @@ struct PosetProg {
   unsigned multi_mask;   // bit k: node k has more than two parents -> `xo[k]` holds parents 3..6
   unsigned valid_mask;   // (1 << p) - 1
   unsigned huge_mask;    // bit k: node k has more than six parents -> CSR loop over the rest
-  unsigned pad[3];
+  unsigned one_bits;     // 0x3f800000 as a run-time value: lets (x & mask) | one compile to a single LOP3
+  unsigned pad[2];
   uint2 off[kFastMaxP];            // byte offsets (within the thread's column) of the first two parents' rows
   uint4 xo[kFastMaxP];             // parents 3..6 of nodes with in-degree > 2 (dummy row where absent)
   unsigned char ev[kFastMaxP];     // event id at position k

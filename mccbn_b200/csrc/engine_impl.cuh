@@ -1049,7 +1049,7 @@ int mccbn_jit_compile_forward(const int* poset, int p, int times_given, size_t* 
   FlatPoset f;
   flatten_or_throw(poset, p, P, f);
   static NvrtcApi rtc;
-  const std::string src = generate_forward_source(f, times_given != 0, 6);
+  const std::string src = generate_forward_source(f, times_given != 0, jit_default_minb());
   if (source && sourcelen) std::snprintf(source, sourcelen, "%s", src.c_str());
   JitCompiled cc;
   const bool ok = jit_compile(rtc, src, cc);

@@ -25,6 +25,7 @@
 
 #include "_embedded_sources.inc"
 #include "engine.cuh"
+#include "kernels_forward.cuh"
 
 namespace mccbn {
 
@@ -81,38 +82,61 @@ static std::string jit_key(const FlatPoset& f, bool times_given, int minb) {
 static std::string generate_forward_source(const FlatPoset& f, bool times_given, int minb) {
   const int p = f.p, pmax = jit_pmax(p);
   std::ostringstream s;
+  if (const char* e = std::getenv("MCCBN_JIT_DIAG_ROUNDS"))  // profiling experiments only (see philox.cuh)
+    s << "#define MCCBN_PHILOX_ROUNDS " << std::max(1, std::min(10, std::atoi(e))) << "\n";
   s << "#include \"kernels_forward.cuh\"\n"
        "namespace mccbn {\n"
        "// generated for one poset: node k = topological position k, t<k> = event time, parents unrolled\n"
        "struct SpecSampler {\n"
        "  static constexpr bool kStagesT = false;\n"
-       "  __device__ __forceinline__ void operator()(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zcol_s,\n"
+       "  __device__ __forceinline__ void operator()(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zrow_s,\n"
        "      const uint32_t l, const uint32_t gi, const uint32_t k0, const uint32_t k1, const uint32_t cw,\n"
        "      const float ts_given, const ScaleSrc<float, "
     << pmax
     << "> scale, uint32_t& X, float& Ts_out) const {\n"
-       "    constexpr uint32_t kRow = kFwdBlock * 4u;\n"
        "    float Ts = ts_given;\n"
-       "    uint32_t x = 0u;\n";
-  // G Philox blocks are generated in lock-step (philox4x32_10_multi) to expose ILP inside the RNG
-  int G = 2;
-  if (const char* e = std::getenv("MCCBN_JIT_PHILOX_ILP")) G = std::max(1, std::min(8, std::atoi(e)));
-  const int nblocks = (p + 3) / 4;
-  const char* comp[4] = {".x", ".y", ".z", ".w"};
-  for (int k = 0; k < p; ++k) {
-    if (k % (4 * G) == 0) {
-      const int b0 = k / 4, g = std::min(G, nblocks - b0);
-      s << "    uint4 r" << b0 << "[" << g << "];\n"
-        << "    philox4x32_10_multi<" << g << ">(l, gi, " << b0 << "u, cw, k0, k1, r" << b0 << ");\n";
-      if (k == 0 && !times_given)
-        s << "    {\n"
-             "      const uint32_t low = (r0[0].x & 0x1ffu) | ((r0[0].y & 0x1ffu) << 9) | ((r0[0].z & 0x1fu) << 18);\n"
-             "      Ts = fast_lg2(2.0f - __uint_as_float(low | 0x3f800000u)) * c_scale.cs;\n"
-             "    }\n";
-    }
-    const int b0 = (k / (4 * G)) * G;
-    const std::string w = "r" + std::to_string(b0) + "[" + std::to_string(k / 4 - b0) + "]" + comp[k % 4];
-    s << "    const float z" << k << " = fast_lg2(u01_open0(" << w << ")) * c_scale.c[" << k << "];";
+       "    uint32_t x = 0u;\n"
+       "    const uint32_t one = pg.one_bits;\n";
+  // Same stream layout as sample_forward (kernels_forward.cuh): field 0 = sampling time, field k + 1 = node k, 24-bit
+  // fields packed back to back; stream word 4 b + i is state word i of Philox block b (variable a<i>_<b>).
+  const int nblocks = fwd_blocks_for_fields(p + 1);
+  auto word = [&](int wi) { return "a" + std::to_string(wi % 4) + "_" + std::to_string(wi / 4); };
+  auto field = [&](int f) {  // the expression field_u01 folds to
+    const int st = 24 * f, wi = st / 32, o = st % 32;
+    std::string m;
+    if (o == 0) m = "((" + word(wi) + " & 0x7fffffu) | one)";
+    else if (o == 8) m = "((" + word(wi) + " >> 9) | 0x3f800000u)";
+    else m = "((__funnelshift_r(" + word(wi) + ", " + word(wi + 1) + ", " + std::to_string(o) + ") & 0x7fffffu) | one)";
+    return "fast_lg2(2.0f - __uint_as_float(" + m + "))";
+  };
+  // genotype bits: 0 = predicated integer add (ALU pipe), 1 = FSET + FFMA into two fp32 accumulators of 16 bits each
+  int xmode = 0;
+  if (const char* e = std::getenv("MCCBN_JIT_XMODE")) xmode = std::atoi(e);
+  if (xmode == 1) s << "    float xlo = 0.0f, xhi = 0.0f;\n";
+  // 2 (experiment): not-X_k = sat(2^100 (T_k - T_s)) by FFMA.SAT, bits collected by Horner FFMAs (FP32 pipe only)
+  if (xmode == 2) s << "    float xlo = 0.0f, xhi = 0.0f;\n";
+
+  // ---- statements -------------------------------------------------------------------------------------------------
+  // Philox4x32-10 block b, written out round by round (same arithmetic as philox4x32_10) so that the rounds of one
+  // block can be interleaved with the node code that consumes the previous block
+  auto philox_init = [&](int b) {
+    std::ostringstream o;
+    o << "    uint32_t a0_" << b << " = l, a1_" << b << " = gi, a2_" << b << " = " << b << "u, a3_" << b << " = cw;\n";
+    return o.str();
+  };
+  auto philox_round = [&](int b, int r) {
+    std::ostringstream o;
+    o << "    { const uint64_t p0 = (uint64_t)0xD2511F53u * a0_" << b << ", p1 = (uint64_t)0xCD9E8D57u * a2_" << b << ";"
+      << " a0_" << b << " = (uint32_t)(p1 >> 32) ^ a1_" << b << " ^ (k0 + " << (uint32_t)(0x9E3779B9u * (uint32_t)r) << "u);"
+      << " a2_" << b << " = (uint32_t)(p0 >> 32) ^ a3_" << b << " ^ (k1 + " << (uint32_t)(0xBB67AE85u * (uint32_t)r) << "u);"
+      << " a1_" << b << " = (uint32_t)p1; a3_" << b << " = (uint32_t)p0; }\n";
+    return o.str();
+  };
+  const int rounds = MCCBN_PHILOX_ROUNDS;
+  // node k: waiting time, event time, genotype bit, staged e_k (one 16-byte store per four nodes)
+  auto node_stmt = [&](int k) {
+    std::ostringstream o;
+    o << "    const float e" << k << " = " << field(k + 1) << ";";
     // max over parents, balanced so that the compiler can form FMNMX3
     std::vector<std::string> terms;
     for (uint64_t m = f.parent_pos[k]; m; m &= m - 1) terms.push_back("t" + std::to_string(ctz64(m)));
@@ -122,10 +146,79 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
       if (terms.size() & 1) nxt.push_back(terms.back());
       terms.swap(nxt);
     }
-    s << "  const float t" << k << " = z" << k;
-    if (!terms.empty()) s << " + " << terms[0];
-    s << ";  sts_at_f(zcol_s + " << k << "u * kRow, z" << k << ");  if (t" << k << " <= Ts) x |= 0x" << std::hex
-      << (1u << k) << std::dec << "u;\n";
+    o << "  const float t" << k << " = fmaf(e" << k << ", c_scale.c[" << k << "], " << (terms.empty() ? "0.0f" : terms[0])
+      << ");  ";
+    if (xmode == 2)
+      o << (k < 16 ? "xlo" : "xhi") << " = fmaf(" << (k < 16 ? "xlo" : "xhi") << ", 2.0f, __saturatef(fmaf(t" << k
+        << ", 1.2676506e30f, nbts)));\n";
+    else if (xmode == 1)
+      o << (k < 16 ? "xlo" : "xhi") << " = fmaf(t" << k << " <= Ts ? 1.0f : 0.0f, " << (1u << (k & 15)) << ".0f, "
+        << (k < 16 ? "xlo" : "xhi") << ");\n";
+    else
+      o << "if (t" << k << " <= Ts) x |= 0x" << std::hex << (1u << k) << std::dec << "u;\n";
+    if (k % 4 == 3 || k == p - 1) {
+      const int q = k / 4;
+      o << "    sts128_f(zrow_s + " << q * 16 << "u";
+      for (int j = 4 * q; j < 4 * q + 4; ++j) o << ", " << (j <= k ? "e" + std::to_string(j) : std::string("0.0f"));
+      o << ");\n";
+    }
+    return o.str();
+  };
+  std::string ts_stmt = times_given ? std::string() : "    Ts = " + field(0) + " * c_scale.cs;\n";
+  if (xmode == 2) ts_stmt += "    const float nbts = -1.2676506e30f * Ts;\n";
+
+  // ---- schedule ---------------------------------------------------------------------------------------------------
+  // 0: G blocks in lock-step, then the nodes they complete (phases alternate between the multiplier pipe and the rest)
+  // 1: software pipeline -- the rounds of block b + 1 are interleaved with the nodes completed by block b, so that every
+  //    warp always offers the schedulers IMAD.WIDE work and ALU / FP32 / SFU work at the same time
+  int sched = 0;  // measured on B200: 0 = 22.8 ms, 1 (with ptxas -O1, which keeps the order) = 24.7 ms per cfg-3 E-step
+  if (const char* e = std::getenv("MCCBN_JIT_SCHED")) sched = std::atoi(e);
+  int G = 2;
+  if (const char* e = std::getenv("MCCBN_JIT_PHILOX_ILP")) G = std::max(1, std::min(8, std::atoi(e)));
+  if (sched == 0) {
+    int generated = 0;  // blocks generated so far
+    for (int k = 0; k < p; ++k) {
+      while (generated <= fwd_field_block(k + 1)) {
+        const int b0 = generated, g = std::min(G, nblocks - b0);
+        for (int b = b0; b < b0 + g; ++b) s << philox_init(b);
+        for (int r = 0; r < rounds; ++r)
+          for (int b = b0; b < b0 + g; ++b) s << philox_round(b, r);
+        if (b0 == 0) s << ts_stmt;
+        generated += g;
+      }
+      s << node_stmt(k);
+    }
+  } else {
+    s << philox_init(0);
+    for (int r = 0; r < rounds; ++r) s << philox_round(0, r);
+    for (int b = 0; b < nblocks; ++b) {
+      // statements that become ready with block b
+      std::vector<std::string> ready;
+      if (b == 0 && !ts_stmt.empty()) ready.push_back(ts_stmt);
+      for (int k = 0; k < p; ++k)
+        if (fwd_field_block(k + 1) == b) ready.push_back(node_stmt(k));
+      // sched 2: an opaque never-taken branch closes the basic block, ptxas schedules each phase on its own
+      if (sched == 2 && b > 0) s << "    if (l == 0xfffffff7u) asm volatile(\"trap;\");\n";
+      if (b + 1 < nblocks) {
+        s << philox_init(b + 1);
+        size_t done = 0;
+        for (int r = 0; r < rounds; ++r) {
+          s << philox_round(b + 1, r);
+          const size_t upto = ready.size() * (size_t)(r + 1) / (size_t)rounds;
+          for (; done < upto; ++done) s << ready[done];
+        }
+        for (; done < ready.size(); ++done) s << ready[done];
+      } else {
+        for (const std::string& st : ready) s << st;
+      }
+    }
+  }
+  if (xmode == 1) s << "    x = __float2uint_rz(xlo) | (__float2uint_rz(xhi) << 16);\n";
+  if (xmode == 2) {  // Horner collected not-X, most significant bit first: reverse and complement
+    const int nlo = std::min(p, 16), nhi = p - nlo;
+    s << "    x = ~((__brev(__float2uint_rz(xlo)) >> " << (32 - nlo) << ")";
+    if (nhi > 0) s << " | ((__brev(__float2uint_rz(xhi)) >> " << (32 - nhi) << ") << 16)";
+    s << ") & 0x" << std::hex << (p >= 32 ? 0xffffffffu : ((1u << p) - 1u)) << std::dec << "u;\n";
   }
   s << "    X = x;\n"
        "    Ts_out = Ts;\n"
@@ -164,8 +257,12 @@ static bool jit_compile(NvrtcApi& rtc, const std::string& src, JitCompiled& out)
     out.log = std::string("nvrtcCreateProgram: ") + rtc.GetErrorString(rc);
     return false;
   }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--ptxas-options=-v"};
-  rc = rtc.CompileProgram(prog, 4, opts);
+  // ptxas -O1 keeps the generated statement order (needed by the software-pipelined schedule experiment); the default
+  // level hoists every Philox round to the front of the sample and leaves the node code at the end -- which is faster
+  std::string popt = "--ptxas-options=-O3";
+  if (const char* e = std::getenv("MCCBN_JIT_PTXAS_O")) popt = std::string("--ptxas-options=-O") + e;
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--ptxas-options=-v", popt.c_str()};
+  rc = rtc.CompileProgram(prog, 5, opts);
   size_t ls = 0;
   rtc.GetProgramLogSize(prog, &ls);
   if (ls > 1) {
@@ -215,18 +312,21 @@ static std::string jit_cache_path(const std::string& src) {
   if (dir.empty() || dir == "off") return "";
   (void)!system(("mkdir -p '" + dir + "' 2>/dev/null").c_str());
   char name[64];
-  std::snprintf(name, sizeof name, "/fwd_%016llx.cubin", (unsigned long long)fnv1a64(src + kSrc_kernels_forward_cuh));
+  std::snprintf(name, sizeof name, "/fwd_%016llx.cubin", (unsigned long long)fnv1a64(src + kSrc_kernels_forward_cuh + kSrc_philox_cuh + kSrc_device_types_cuh +
+                                                    (std::getenv("MCCBN_JIT_PTXAS_O") ? std::getenv("MCCBN_JIT_PTXAS_O") : "")));
   return dir + name;
+}
+
+// resident blocks per SM the specialised kernel is compiled for (register cap = 65536 / (128 * minb))
+static int jit_default_minb() {
+  if (const char* e = std::getenv("MCCBN_JIT_MINB")) return std::max(1, std::min(8, std::atoi(e)));
+  return 3;  // best of {3,4,5,6} on B200 (profiles/README.md): fewer, fatter warps win on this pipe-bound kernel
 }
 
 struct JitCache {
   NvrtcApi rtc;
   std::map<std::string, JitKernel> kernels;
-  int minb = 4;  // 116 registers: best of {4,5,6} resident blocks on B200 (profiles/README.md)
-
-  JitCache() {
-    if (const char* e = std::getenv("MCCBN_JIT_MINB")) minb = std::max(1, std::min(8, std::atoi(e)));
-  }
+  int minb = jit_default_minb();
 
   // `only_if_cached`: do not compile, return the kernel only if it is already in memory or on disk
   JitKernel* get(const FlatPoset& f, bool times_given, bool only_if_cached = false) {
@@ -277,7 +377,7 @@ struct JitCache {
       if (e == cudaSuccess && bytes == sizeof(FwdScale)) {
         jk.ok = true;
         jk.pmax = jit_pmax(f.p);
-        jk.smem = sizeof(float) * (size_t)jk.pmax * kFwdBlock;
+        jk.smem = (size_t)(((jk.pmax / 4) | 1) * 16) * kFwdBlock;  // ZStage<float, pmax>::kRowBytes per thread
         jk.compile_ms = cc.compile_ms;
       } else {
         std::fprintf(stderr, "mccbn_b200: loading the specialised kernel failed (%s); using the generic kernel\n",

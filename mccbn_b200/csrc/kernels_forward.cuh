@@ -16,6 +16,11 @@
 // Weights are tracked relative to the best (smallest-distance) sample seen so far, r^(d - dref) in fp32 with
 // r = eps/(1-eps) <= 1 -- a running log-sum-exp -- and the per-lane fp32 partial sums over <= L/32 samples are
 // reduced across the warp in fp64.
+// Random bits (fp32 path): the p + 1 uniforms of a sample are 24-bit fields packed back to back in the Philox
+// output stream (field 0 = sampling time, field k + 1 = node k; 23 bits of each are used as the mantissa), so a
+// sample of p = 30 events costs 6 Philox4x32-10 blocks instead of 8.  What is staged and accumulated per node is
+// e_k = log2(u_k) <= 0; the scale c_k = -ln2/lambda_k enters the event time through one FFMA
+// (T_k = e_k c_k + max parents) and the sufficient statistic once per record (sum_l w_l Z_lk = c_k sum_l w_l e_lk).
 #pragma once
 #include "device_types.cuh"
 #include "philox.cuh"
@@ -44,19 +49,46 @@ template <typename real>
 struct RealTraits;
 template <>
 struct RealTraits<float> {
-  static constexpr int kUniPerBlock = 4;
-  static __device__ __forceinline__ float expo(const uint4& r, int w, float c) {
-    const uint32_t bits = w == 0 ? r.x : (w == 1 ? r.y : (w == 2 ? r.z : r.w));
-    return fast_lg2(u01_open0(bits)) * c;  // c = -ln2/lambda  =>  -ln(u)/lambda
-  }
+  static constexpr int kUniPerBlock = 4;  // conditional kernels: one 32-bit word per uniform
 };
 template <>
 struct RealTraits<double> {
   static constexpr int kUniPerBlock = 2;
-  static __device__ __forceinline__ double expo(const uint4& r, int w, double c) {
-    const double u = w == 0 ? u01_open0_d(r.x, r.y) : u01_open0_d(r.z, r.w);
-    return log(u) * c;  // c = -1/lambda
+  // e = ln(u) <= 0;  Z = e * c with c = -1/lambda
+  static __device__ __forceinline__ double log_u(const uint4& r, int w) {
+    return log(w == 0 ? u01_open0_d(r.x, r.y) : u01_open0_d(r.z, r.w));
   }
+};
+
+// ---- fp32 path: 24-bit uniform fields packed in the Philox output stream ----------------------------------------
+// Field f occupies stream bits [24 f, 24 f + 24); word w of block b is stream word 4 b + w.  23 of the 24 bits become
+// the mantissa of a float in [1, 2); u = 2 - that lies in (0, 1].  `f` is a compile-time constant wherever this is
+// called (unrolled loops / generated code), so every case below folds to one or two instructions.
+__host__ __device__ constexpr int fwd_field_last_word(int f) { return (24 * f + 23) / 32; }
+__host__ __device__ constexpr int fwd_field_block(int f) { return fwd_field_last_word(f) / 4; }
+// Philox blocks needed for fields 0 .. nf-1
+__host__ __device__ constexpr int fwd_blocks_for_fields(int nf) { return nf <= 0 ? 0 : fwd_field_block(nf - 1) + 1; }
+
+// `one` = 0x3f800000 held in a register (PosetProg::one_bits): with an immediate the compiler needs two LOP3 for
+// (x & mask) | one, with a register operand it is a single three-input LOP3.
+template <int NW>
+__device__ __forceinline__ float field_u01(const uint32_t (&W)[NW], const int f, const uint32_t one) {
+  const int s = 24 * f, wi = s >> 5, o = s & 31;
+  uint32_t m;
+  if (o == 0) m = (W[wi] & 0x7fffffu) | one;                                          // stream bits [s, s+23)
+  else if (o == 8) m = (W[wi] >> 9) | 0x3f800000u;                                    // [s+1, s+24): one LEA.HI
+  else m = (__funnelshift_r(W[wi], W[wi + 1 < NW ? wi + 1 : wi], o) & 0x7fffffu) | one;  // o = 16, 24: [s, s+23)
+  return 2.0f - __uint_as_float(m);
+}
+
+// Z staging: each thread owns a row of PMAX values (e_k) stored as 16-byte vectors; an odd number of vectors per
+// row makes the 128-bit accesses of a warp bank-conflict free.
+template <typename real, int PMAX>
+struct ZStage {
+  static constexpr int kVec = 16 / (int)sizeof(real);
+  static constexpr int kStrideVec = ((PMAX + kVec - 1) / kVec) | 1;
+  static constexpr int kStride = kStrideVec * kVec;  // elements per thread
+  static constexpr uint32_t kRowBytes = (uint32_t)(kStride * sizeof(real));
 };
 
 // per-node exponential scale: fp32 -> constant-bank operand, fp64 -> shared memory (validation mode)
@@ -96,6 +128,14 @@ __device__ __forceinline__ void sts_at(uint32_t saddr, real v) {
   if (sizeof(real) == 4) sts_at_f(saddr, (float)v);
   else sts_at_d(saddr, (double)v);
 }
+__device__ __forceinline__ void sts128_f(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+__device__ __forceinline__ float4 lds128_f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
 
 // max over the parents of node k (0 without parents): two unconditional loads (absent parents read the dummy
 // row, which holds 0); nodes with in-degree > 2 (warp-uniform test) read four more rows unconditionally, and only
@@ -119,42 +159,63 @@ __device__ __forceinline__ real parents_max(const PosetProg& pg, const unsigned 
   return m;
 }
 
-// One forward draw for sample l of (global) observation gi.  The waiting time Z_k and the event time T_k of the
-// node at topological position k are staged in this thread's shared-memory columns (element k at
-// col[k * kFwdBlock]; `tcol_s` / `zcol_s` are 32-bit shared-space addresses); X = hidden genotype in
-// topological-position space.  All PMAX slots run unconditionally (no per-node branch): slots k >= p have scale 0
-// and no parents, so their T is 0 and the caller's valid_mask removes them from X.
-// Random stream of a sample: node k consumes word k%4 of Philox block k/4 (23 high bits); the sampling time
-// consumes the otherwise unused 9 low bits of the first three words of block 0 (independent of the high bits).
+// One forward draw for sample l of (global) observation gi.  The event time T_k of the node at topological
+// position k is staged in this thread's shared-memory column (element k at tcol_s + k * kFwdBlock * sizeof(real));
+// e_k = log(u_k) (log2 in fp32, ln in fp64) is staged in this thread's row at zrow_s (ZStage layout); X = hidden
+// genotype in topological-position space.  All PMAX slots run unconditionally (no per-node branch): slots k >= p
+// have scale 0 and no parents, so their T is 0 and the caller's valid_mask removes them from X.
+// Random stream of a sample (fp32): field 0 = sampling time, field k + 1 = node k (field_u01); Philox block b is
+// generated right before the first field that touches it, and only if that field belongs to a real node.
 template <typename real, int PMAX, bool TIMES_GIVEN>
-__device__ __forceinline__ void sample_forward(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zcol_s,
+__device__ __forceinline__ void sample_forward(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zrow_s,
                                                const uint32_t l, const uint32_t gi, const uint32_t k0,
                                                const uint32_t k1, const uint32_t cw, const real ts_given,
                                                const ScaleSrc<real, PMAX> scale, uint32_t& X, real& Ts_out) {
-  constexpr int UPB = RealTraits<real>::kUniPerBlock;
   constexpr uint32_t kRow = kFwdBlock * sizeof(real);
   const unsigned multi_mask = pg.multi_mask;
-  uint4 r = make_uint4(0, 0, 0, 0);
   real Ts = ts_given;
-  if (!TIMES_GIVEN && sizeof(real) == 8) {
-    r = philox4x32_10(l, gi, 255u, cw, k0, k1);
-    Ts = RealTraits<real>::expo(r, 0, scale(-1));
-  }
   X = 0u;
+  if constexpr (sizeof(real) == 4) {
+    constexpr int NB = fwd_blocks_for_fields(PMAX + 1);
+    uint32_t W[4 * NB];
+    float zq[4];
+    const uint32_t one = pg.one_bits;
 #pragma unroll
-  for (int k = 0; k < PMAX; ++k) {
-    if (k % UPB == 0) {
-      r = philox4x32_10(l, gi, (uint32_t)(k / UPB), cw, k0, k1);
-      if (k == 0 && !TIMES_GIVEN && sizeof(real) == 4) {
-        const uint32_t low = (r.x & 0x1ffu) | ((r.y & 0x1ffu) << 9) | ((r.z & 0x1fu) << 18);
-        Ts = (real)(fast_lg2(2.0f - __uint_as_float(low | 0x3f800000u)) * (float)scale(-1));
+    for (int k = 0; k < PMAX; ++k) {
+      const int b = fwd_field_block(k + 1);
+      if (k == 0 || b != fwd_field_block(k)) {  // compile-time after unrolling
+        // block b is first touched by node k; for k == 0 this is block 0, which also holds field 0
+        if (k == 0 || k < pg.p) {               // warp-uniform
+          const uint4 r = philox4x32_10(l, gi, (uint32_t)b, cw, k0, k1);
+          W[4 * b + 0] = r.x, W[4 * b + 1] = r.y, W[4 * b + 2] = r.z, W[4 * b + 3] = r.w;
+        } else {
+          W[4 * b + 0] = W[4 * b + 1] = W[4 * b + 2] = W[4 * b + 3] = 0u;
+        }
+        if (k == 0 && !TIMES_GIVEN) Ts = fast_lg2(field_u01(W, 0, one)) * scale(-1);
       }
+      const float e = fast_lg2(field_u01(W, k + 1, one));  // log2(u) <= 0;  Z = e * c,  c = -ln2/lambda
+      const float t = fmaf(e, scale(k), parents_max<real>(pg, multi_mask, k, tcol_s));
+      sts_at_f(tcol_s + k * kRow, t);
+      zq[k & 3] = e;
+      if ((k & 3) == 3) sts128_f(zrow_s + (uint32_t)(k - 3) * 4u, zq[0], zq[1], zq[2], zq[3]);
+      if (t <= Ts) X |= (1u << k);
     }
-    const real z = RealTraits<real>::expo(r, k % UPB, scale(k));
-    const real t = z + parents_max<real>(pg, multi_mask, k, tcol_s);
-    sts_at<real>(tcol_s + k * kRow, t);
-    sts_at<real>(zcol_s + k * kRow, z);
-    if (t <= Ts) X |= (1u << k);
+  } else {
+    constexpr int UPB = RealTraits<double>::kUniPerBlock;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (!TIMES_GIVEN) {
+      r = philox4x32_10(l, gi, 255u, cw, k0, k1);
+      Ts = RealTraits<double>::log_u(r, 0) * scale(-1);
+    }
+#pragma unroll
+    for (int k = 0; k < PMAX; ++k) {
+      if (k % UPB == 0) r = philox4x32_10(l, gi, (uint32_t)(k / UPB), cw, k0, k1);
+      const double e = RealTraits<double>::log_u(r, k % UPB);
+      const double t = fma(e, scale(k), parents_max<real>(pg, multi_mask, k, tcol_s));
+      sts_at_d(tcol_s + k * kRow, t);
+      sts_at_d(zrow_s + (uint32_t)k * 8u, e);
+      if (t <= Ts) X |= (1u << k);
+    }
   }
   X &= pg.valid_mask;
   Ts_out = Ts;
@@ -186,7 +247,8 @@ __device__ __forceinline__ void load_scales_fp64(const PosetProg& pg, const DevM
 #endif
 template <typename real, int PMAX>
 __host__ __device__ constexpr size_t fwd_smem_bytes(bool stages_t = true) {
-  return sizeof(real) * (size_t)(stages_t ? 2 * PMAX + 1 : PMAX) * kFwdBlock;
+  return (stages_t ? sizeof(real) * (size_t)(PMAX + 1) * kFwdBlock : 0) +
+         (size_t)ZStage<real, PMAX>::kRowBytes * kFwdBlock;
 }
 
 // The generic sampler interprets the poset program at run time (event times staged in shared memory).  A
@@ -195,19 +257,20 @@ __host__ __device__ constexpr size_t fwd_smem_bytes(bool stages_t = true) {
 template <typename real, int PMAX, bool TIMES_GIVEN>
 struct GenericSampler {
   static constexpr bool kStagesT = true;
-  __device__ __forceinline__ void operator()(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zcol_s,
+  __device__ __forceinline__ void operator()(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zrow_s,
                                              const uint32_t l, const uint32_t gi, const uint32_t k0,
                                              const uint32_t k1, const uint32_t cw, const real ts_given,
                                              const ScaleSrc<real, PMAX> scale, uint32_t& X, real& Ts_out) const {
-    sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zcol_s, l, gi, k0, k1, cw, ts_given, scale, X, Ts_out);
+    sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zrow_s, l, gi, k0, k1, cw, ts_given, scale, X, Ts_out);
   }
 };
 
 template <typename real, int PMAX, bool TIMES_GIVEN, typename Sampler>
 __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const PosetProg& pg, const Sampler sampler) {
-  // dynamic shared memory (fwd_smem_bytes): [rows 0..PMAX-1 staged T_k, row PMAX the dummy row (0),] then PMAX rows
-  // of staged waiting times Z_k (frees PMAX registers per thread)
+  // dynamic shared memory (fwd_smem_bytes): [rows 0..PMAX-1 staged T_k, row PMAX the dummy row (0),] then one row
+  // per thread of staged e_k = log(u_k) (ZStage; frees PMAX registers per thread)
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  using ZS = ZStage<real, PMAX>;
   real* s_T = reinterpret_cast<real*>(smem_raw);
   real* s_Z = s_T + (Sampler::kStagesT ? (PMAX + 1) * kFwdBlock : 0);
   __shared__ real s_rtab[kRtabN];
@@ -218,10 +281,9 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Poset
   const int lane = threadIdx.x & 31;
   constexpr int kWarps = kFwdBlock / 32;
   if (Sampler::kStagesT) s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;
-  for (int k = pg.p; k < PMAX; ++k) s_Z[k * kFwdBlock + threadIdx.x] = (real)0;  // unused node slots
+  for (int k = 0; k < ZS::kStride; ++k) s_Z[threadIdx.x * ZS::kStride + k] = (real)0;  // unused node slots stay 0
   const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
-  const uint32_t zcol_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x);
-  constexpr uint32_t kRow = kFwdBlock * sizeof(real);
+  const uint32_t zrow_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x * ZS::kStride);
 
   for (int t = threadIdx.x; t < kRtabN; t += kFwdBlock)
     s_rtab[t] = sizeof(real) == 4 ? (real)mdl->rtab[t] : (real)mdl->rtab_d[t];
@@ -255,7 +317,7 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Poset
       const bool valid = l < l_end;
       uint32_t X;
       real Ts;
-      sampler(pg, tcol_s, zcol_s, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given, scale, X, Ts);
+      sampler(pg, tcol_s, zrow_s, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given, scale, X, Ts);
       const int d = __popc(X ^ yt);
       const int de = flip ? p - d : d;  // weights decrease in `de`
       const int dmin = __reduce_min_sync(0xffffffffu, valid ? de : (1 << 19));
@@ -272,8 +334,19 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Poset
       aw += wr;
       aw2 = fma(wr, wr, aw2);
       awd = fma(wr, (real)d, awd);
+      if constexpr (sizeof(real) == 4) {
 #pragma unroll
-      for (int k = 0; k < PMAX; ++k) acc[k] = fma(wr, lds_at<real>(zcol_s + k * kRow), acc[k]);
+        for (int q = 0; q < PMAX / 4; ++q) {
+          const float4 e = lds128_f(zrow_s + (uint32_t)q * 16u);
+          acc[4 * q + 0] = fmaf(wr, e.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(wr, e.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(wr, e.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(wr, e.w, acc[4 * q + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PMAX; ++k) acc[k] = fma(wr, lds_at<real>(zrow_s + (uint32_t)k * 8u), acc[k]);
+      }
     }
 
     // warp reduction in fp64 (all lanes share dref), lane k writes slot kStatHdr + k
@@ -303,7 +376,8 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Poset
         if (lane == (k & 31)) mine = v;
       }
     }
-    if (lane < p) out[kStatHdr + lane] = mine;
+    // acc holds sum w' e_k: the waiting time is Z_k = e_k c_k (c_k = -ln2/lambda_k in fp32, -1/lambda_k in fp64)
+    if (lane < p) out[kStatHdr + lane] = mine * (double)scale(lane);
   }
 }
 
@@ -333,12 +407,13 @@ __global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpAr
                                                                  const __grid_constant__ PosetProg pg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* s_T = reinterpret_cast<real*>(smem_raw);
+  using ZS = ZStage<real, PMAX>;
   real* s_Z = s_T + (PMAX + 1) * kFwdBlock;
   __shared__ real s_scale[PMAX + 1];
   const int p = pg.p;
   s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;
   const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
-  const uint32_t zcol_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x);
+  const uint32_t zrow_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x * ZS::kStride);
   load_scales_fp64<real, PMAX>(pg, a.model, s_scale);
   __syncthreads();
   ScaleSrc<real, PMAX> scale;
@@ -347,14 +422,14 @@ __global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpAr
   for (int l = blockIdx.x * kFwdBlock + threadIdx.x; l < a.L; l += gridDim.x * kFwdBlock) {
     uint32_t X;
     real Ts;
-    sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zcol_s, (uint32_t)l, a.gi, a.key0, a.key1, a.cw, (real)a.time,
+    sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zrow_s, (uint32_t)l, a.gi, a.key0, a.key1, a.cw, (real)a.time,
                                             scale, X, Ts);
     a.dist_out[l] = __popc(X ^ yt);
     uint32_t xe = 0u;
 #pragma unroll
     for (int k = 0; k < PMAX; ++k)
       if (k < p) {
-        a.Z_out[(size_t)pg.ev[k] * a.L + l] = (double)s_Z[k * kFwdBlock + threadIdx.x];
+        a.Z_out[(size_t)pg.ev[k] * a.L + l] = (double)s_Z[threadIdx.x * ZS::kStride + k] * (double)scale(k);
         xe |= ((X >> k) & 1u) << pg.ev[k];
       }
     a.X_out[l] = xe;

@@ -29,21 +29,22 @@ __global__ void __launch_bounds__(kFwdBlock) pool_generate_kernel(float* __restr
                                                                   const __grid_constant__ PosetProg pg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_T = reinterpret_cast<float*>(smem_raw);
+  using ZS = ZStage<float, PMAX>;
   float* s_Z = s_T + (PMAX + 1) * kFwdBlock;
   s_T[PMAX * kFwdBlock + threadIdx.x] = 0.f;
   const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
-  const uint32_t zcol_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x);
+  const uint32_t zrow_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x * ZS::kStride);
   ScaleSrc<float, PMAX> scale;
   scale = ScaleSrc<float, PMAX>{nullptr};
   for (int k = blockIdx.x * kFwdBlock + threadIdx.x; k < K; k += gridDim.x * kFwdBlock) {
     uint32_t X;
     float Ts;
     // TIMES_GIVEN = true: no sampling time is drawn here (it is drawn per (observation, entry) later)
-    sample_forward<float, PMAX, true>(pg, tcol_s, zcol_s, (uint32_t)k, 0xffffffffu, key0, key1, cw, 0.f, scale, X, Ts);
+    sample_forward<float, PMAX, true>(pg, tcol_s, zrow_s, (uint32_t)k, 0xffffffffu, key0, key1, cw, 0.f, scale, X, Ts);
 #pragma unroll
     for (int j = 0; j < PMAX; ++j) {
       Tp[(size_t)k * PMAX + j] = j < pg.p ? s_T[j * kFwdBlock + threadIdx.x] : __int_as_float(0x7f800000);
-      Zp[(size_t)k * PMAX + j] = j < pg.p ? s_Z[j * kFwdBlock + threadIdx.x] : 0.f;
+      Zp[(size_t)k * PMAX + j] = j < pg.p ? s_Z[threadIdx.x * ZS::kStride + j] * scale(j) : 0.f;  // Z = e c
     }
   }
 }

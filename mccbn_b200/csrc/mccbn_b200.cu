@@ -84,6 +84,7 @@ static PosetProg build_prog(const FlatPoset& f, int pmax, int elem_bytes) {
   g.p = f.p;
   g.store_mask = (unsigned)f.has_children_pos;
   g.valid_mask = f.p >= 32 ? 0xffffffffu : ((1u << f.p) - 1u);
+  g.one_bits = 0x3f800000u;
   const unsigned dummy = (unsigned)pmax * kFwdBlock * elem_bytes;
   int x = 0;
   for (int k = 0; k < kFastMaxP; ++k) {

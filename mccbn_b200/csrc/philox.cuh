@@ -9,6 +9,12 @@
 #pragma once
 #include "device_types.cuh"
 
+// Philox4x32-10 is the production generator (10 rounds, the Random123 / cuRAND default).  The round count is a macro only
+// so that profiling experiments can measure how much of a kernel's time the generator accounts for.
+#ifndef MCCBN_PHILOX_ROUNDS
+#define MCCBN_PHILOX_ROUNDS 10
+#endif
+
 namespace mccbn {
 
 struct PhiloxKey {
@@ -26,7 +32,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
                                                uint32_t k1) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < MCCBN_PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = (uint64_t)M0 * c0;  // IMAD.WIDE.U32
     const uint64_t p1 = (uint64_t)M1 * c2;
     const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;  // LOP3
@@ -57,7 +63,7 @@ __device__ __forceinline__ void philox4x32_10_multi(const uint32_t c0, const uin
     a3[i] = c3;
   }
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < MCCBN_PHILOX_ROUNDS; ++r) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const uint64_t p0 = (uint64_t)M0 * a0[i];

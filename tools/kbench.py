@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Dev helper: time one EM iteration (E-step + reduction + M-step) of a config with inputs resident on the GPU.
-usage: python tools_kbench.py cfg3 [cfg2 ...]   (MCCBN_B200_LIB selects a kernel-variant build)"""
+usage: python tools/kbench.py cfg3 [cfg2 ...]   (MCCBN_B200_LIB selects a kernel-variant build)"""
 import sys, os, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import mccbn_b200 as mc
 from bench import CONFIGS, make_problem
