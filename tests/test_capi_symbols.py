@@ -102,6 +102,7 @@ def test_jit_source_generation_and_nvrtc_compile():
     assert r["cubin_bytes"] > 10000
     assert "mccbn_fwd_spec" in r["source"] and "estep_forward_body<float, 12, false>" in r["source"]
     topo, _ = mc.flatten_poset(c["poset"])
-    assert r["source"].count("fast_lg2(u01_open0(") == 9  # one exponential per event
+    assert r["source"].count("fast_lg2(") == 9 + 1  # one exponential per event + the sampling time
+    assert r["source"].count("(uint64_t)0xD2511F53u") == 10 * 2  # 10 uniforms of 24 bits = 2 Philox blocks x 10 rounds
     assert r["source"].count("fmaxf(") == sum(max(0, int(d) - 1) for d in c["poset"].sum(axis=0))  # |E| - #non-roots
     assert "registers" in r["log"]
