@@ -252,7 +252,9 @@ def run_ours(args):
     if rank == 0:
         # roofline of the dominant kernel (estep_forward / estep_conditional): see module docstring
         pmax = ((p + 3) // 4) * 4
-        words_per_sample = pmax if sampling == "forward" else pmax + 4
+        # forward: p + 1 uniforms of 24 bits packed back to back in the Philox stream (kernels_forward.cuh)
+        fwd_blocks = ((24 * p + 23) // 32) // 4 + 1
+        words_per_sample = 4 * fwd_blocks if sampling == "forward" else pmax + 4
         peak = None
         try:
             with torch.cuda.stream(stream):
@@ -269,8 +271,11 @@ def run_ours(args):
         line["roofline"] = {
             "bound": "instruction issue (Philox INT32 + FP32/SFU); not hbm/tensor",
             "achieved": ach / 1e9, "peak": (peak / 1e9) if peak else None, "unit": "Gword/s (32-bit Philox output)",
-            "frac": (ach / peak) if peak else None, "traffic": None,
-            "peak_source": "pure Philox4x32-10 generator micro-kernel measured live on this GPU",
+            "frac": (ach / peak) if peak else None, "traffic": ncu_traffic_bytes(args.config),
+            "words_per_sample": words_per_sample,
+            "peak_source": "pure Philox4x32-10 generator micro-kernel (IMAD.WIDE-bound) measured live on this GPU; "
+                           "frac = share of the step the multiplier pipe alone would need (see profiles/README.md "
+                           "for the measured issue-cost model that accounts for the rest)",
             "hbm": {"achieved_GBs": hbm_bytes / (ms * 1e-3) / 1e9, "peak_GBs": peaks.get("hbm_gbs"),
                     "note": "algorithmic HBM bytes per E-step / step time: memory is not the limiter"},
         }
@@ -280,6 +285,15 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic_bytes(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json); None if there is no capture for it."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(config, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def cpu_baseline(cfg, p, N, L, sampling, args):

@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -69,21 +71,97 @@ struct NcclApi {
   }
 };
 
+// Device-memory cache.  The reference-facing entry points (mccbn_obs_log_likelihood, mccbn_importance_weight, ...)
+// are called once per E-step by the R wrappers and build a fresh problem each time; cudaMalloc / cudaFree of its
+// ~10 buffers (tens of MB) would cost more than the upload.  Freed blocks are therefore kept per device and handed
+// out again (best fit within 2x).  Every entry point synchronises its stream before its buffers are destroyed, so a
+// cached block is never in use by in-flight work.  MCCBN_DEVICE_CACHE_MB caps the cache (default 4096, 0 = off).
+struct DeviceCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;  // (device, bytes) -> block
+  std::map<void*, std::pair<int, size_t>> live;               // block -> (device, bytes)
+  size_t cached_bytes = 0, cap_bytes = (size_t)4096 << 20;
+  DeviceCache() {
+    if (const char* e = std::getenv("MCCBN_DEVICE_CACHE_MB")) cap_bytes = (size_t)std::max(0L, std::atol(e)) << 20;
+  }
+  static size_t round_up(size_t n) {
+    const size_t g = n <= (1u << 20) ? 512 : (size_t)1 << 20;  // 512 B below 1 MiB, 1 MiB above
+    return (n + g - 1) / g * g;
+  }
+  void* alloc(size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t want = round_up(std::max<size_t>(bytes, 1));
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = free_blocks.lower_bound({dev, want});
+      if (it != free_blocks.end() && it->first.first == dev && it->first.second <= 2 * want) {
+        void* p = it->second;
+        cached_bytes -= it->first.second;
+        live[p] = it->first;
+        free_blocks.erase(it);
+        return p;
+      }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+      cudaGetLastError();
+      trim();
+      e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) throw Error(MCCBN_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lk(mu);
+    live[p] = {dev, want};
+    return p;
+  }
+  void free(void* p) {
+    if (!p) return;
+    std::unique_lock<std::mutex> lk(mu);
+    auto it = live.find(p);
+    if (it == live.end()) {
+      lk.unlock();
+      cudaFree(p);
+      return;
+    }
+    const std::pair<int, size_t> key = it->second;
+    live.erase(it);
+    if (cached_bytes + key.second <= cap_bytes) {
+      free_blocks.emplace(key, p);
+      cached_bytes += key.second;
+      return;
+    }
+    lk.unlock();
+    cudaFree(p);
+  }
+  void trim() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+inline DeviceCache& device_cache() {
+  static DeviceCache* c = new DeviceCache();  // intentionally leaked: outlives every static destructor
+  return *c;
+}
+
 template <typename T>
 struct DevBuf {  // grow-only device buffer
   T* ptr = nullptr;
   size_t cap = 0;
   T* ensure(size_t n) {
     if (n > cap) {
-      if (ptr) cudaFree(ptr);
+      if (ptr) device_cache().free(ptr);
       ptr = nullptr;
-      MCCBN_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+      cap = 0;
+      ptr = static_cast<T*>(device_cache().alloc(n * sizeof(T)));
       cap = n;
     }
     return ptr;
   }
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) device_cache().free(ptr);
     ptr = nullptr;
     cap = 0;
   }

@@ -50,7 +50,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
   int L_eff = L;
 
   if (scheme == kForward) {
-    choose_chunks(L, chunks, chunk_len, grid_x);
+    JitKernel* jk = precision == 1 ? nullptr : resolve_jit(flat[c], times_given, L);
+    choose_chunks(L, chunks, chunk_len, grid_x, jk ? jk->blocks_per_sm : 0);
     n_items = (long long)N * chunks;
     FwdArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -71,6 +72,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.PS = PS();
     if (precision == 1)
       launch_forward<double>(a, flat[c], times_given, grid_x, c);
+    else if (jk)
+      launch_forward_jit(jk, a, flat[c], c, grid_x);
     else
       launch_forward<float>(a, flat[c], times_given, grid_x, c);
   } else if (scheme == kBackward || scheme == kBernoulli || scheme == kOtcbn) {

@@ -291,6 +291,7 @@ struct JitKernel {
   void* scale_sym = nullptr;
   size_t smem = 0;
   int pmax = 0;
+  int blocks_per_sm = 0;  // resident 128-thread blocks per SM (occupancy query at load time)
   bool ok = false;
   double compile_ms = 0;
 };
@@ -379,6 +380,14 @@ struct JitCache {
         jk.pmax = jit_pmax(f.p);
         jk.smem = (size_t)(((jk.pmax / 4) | 1) * 16) * kFwdBlock;  // ZStage<float, pmax>::kRowBytes per thread
         jk.compile_ms = cc.compile_ms;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)jk.kern, kFwdBlock, jk.smem) != cudaSuccess ||
+            nb <= 0) {
+          cudaGetLastError();
+          nb = minb;  // the launch bound the kernel was compiled for
+        }
+        if (const char* e = std::getenv("MCCBN_JIT_RESIDENT")) nb = std::max(1, std::min(nb, std::atoi(e)));
+        jk.blocks_per_sm = nb;
       } else {
         std::fprintf(stderr, "mccbn_b200: loading the specialised kernel failed (%s); using the generic kernel\n",
                      cudaGetErrorString(e));

@@ -213,21 +213,23 @@ struct mccbn_problem {
     }
   }
 
-  // poset-specialised kernel (jit.cuh) when the sampling work amortises a compilation
-  bool launch_forward_jit(const FwdArgs& a, const FlatPoset& f, int c, bool times_given, int grid) {
+  // poset-specialised kernel (jit.cuh) when the sampling work amortises a compilation; nullptr = generic kernel
+  JitKernel* resolve_jit(const FlatPoset& f, bool times_given, int L) {
     int mode = ctx->jit_mode;
     if (mode < 0) {
       const char* e = std::getenv("MCCBN_JIT");
       if (e && std::strcmp(e, "0") == 0) mode = 0;
       else if (e && std::strcmp(e, "1") == 0) mode = 1;
     }
-    if (mode == 0) return false;
+    if (mode == 0) return nullptr;
     if (!ctx->jit) ctx->jit = new JitCache();
     // auto: compile only when the announced sampling work (samples per E-step x expected E-steps) amortises the
-    // ~0.3 s compilation (generic 2.1e10, specialised 3.6e10 samples/s on B200); cached kernels are always used
-    const bool worth = (double)N * (double)a.L * (double)std::max(1, expected_esteps) >= 5e9;
-    JitKernel* jk = ctx->jit->get(f, times_given, /*only_if_cached=*/mode < 0 && !worth);
-    if (!jk) return false;
+    // ~0.3 s compilation (generic 2.2e10, specialised 4.5e10 samples/s on B200); cached kernels are always used
+    const bool worth = (double)N * (double)L * (double)std::max(1, expected_esteps) >= 5e9;
+    return ctx->jit->get(f, times_given, /*only_if_cached=*/mode < 0 && !worth);
+  }
+
+  void launch_forward_jit(JitKernel* jk, const FwdArgs& a, const FlatPoset& f, int c, int grid) {
     cudaStream_t s = ctx->stream;
     MCCBN_CUDA(cudaMemcpyAsync(jk->scale_sym, scales.ptr + c, sizeof(FwdScale), cudaMemcpyDeviceToDevice, s));
     PosetProg pg = build_prog(f, jk->pmax, 4);
@@ -235,13 +237,11 @@ struct mccbn_problem {
     void* params[] = {(void*)&args, (void*)&pg};
     MCCBN_CUDA(cudaLaunchKernel((const void*)jk->kern, dim3(grid), dim3(kFwdBlock), params, jk->smem, s));
     ctx->launches++;
-    return true;
   }
 
   template <typename real>
   void launch_forward(const FwdArgs& a, const FlatPoset& f, bool times_given, int grid, int c = 0) {
     cudaStream_t s = ctx->stream;
-    if (sizeof(real) == 4 && launch_forward_jit(a, f, c, times_given, grid)) return;
 #define MCCBN_FWD(PM)                                                                                   \
   do {                                                                                                  \
     const PosetProg pg = build_prog(f, PM, (int)sizeof(real));                                          \
@@ -274,9 +274,12 @@ struct mccbn_problem {
   }
 
   // chunking of the L samples of one observation over warps (see DESIGN.md "work decomposition")
-  void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x) const {
+  // `blocks_per_sm` = resident blocks of the kernel that will run (0: the generic forward kernel's launch bounds); the
+  // grid is exactly one resident wave, every warp strides over ~24 items
+  void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x, int blocks_per_sm = 0) const {
     const int warps_per_block = kFwdBlock / 32;
-    const int resident_blocks = ctx->sm_count * (p > MCCBN_FWD_BIGP - 4 ? MCCBN_FWD_MINB_BIG : 6);  // blocks of 4 warps per SM
+    if (blocks_per_sm <= 0) blocks_per_sm = p > MCCBN_FWD_BIGP - 4 ? MCCBN_FWD_MINB_BIG : 6;
+    const int resident_blocks = ctx->sm_count * blocks_per_sm;  // blocks of 4 warps
     const long long total_warps = (long long)resident_blocks * warps_per_block;
     long long want_items = total_warps * 24;
     long long c = (want_items + N - 1) / std::max(1, N);
