@@ -165,11 +165,11 @@ def run_ours(args):
     # forward scheme: NVRTC poset-specialised kernel (csrc/jit.cuh); compiled once during warm-up
     mc.set_jit(0 if args.no_jit else 1, ctx=ctx)
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(mc.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        ctx.init_comm(rank, world, bytes(idt.cpu().tolist()))
+        from mccbn_b200 import dist as mdist
+        if args.exchange == "peer":  # statistic exchange fused into the reduction / M-step kernels over NVLink peer memory
+            ctx.init_peers(rank, world, mdist.gather_peer_handles(ctx, dist, torch.device("cuda", local)))
+        else:                        # one ncclAllReduce per EM iteration
+            ctx.init_comm(rank, world, mdist.broadcast_unique_id(dist, torch.device("cuda", local)))
 
     pb = mc.Problem(obs, ctx=ctx, obs_offset=lo, N_global=N)
     pb.set_model(cfg["poset"], cfg["lambda0"], 0.1 if cfg["eps"] != 0.01 else 0.01)
@@ -241,7 +241,9 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32 sampling / f64 reduction", "data": "synthetic",
         "config": {"workload": f"{args.config}: {desc}", "sampling": sampling, "p": p, "N": N, "L": L,
                    "sec_per_mcem_iteration": ms * 1e-3, "l2": "256 MiB buffer written between timed iterations",
-                   "parallelism": f"observations sharded over {world} rank(s), 1 allreduce of p+5 doubles / iteration",
+                   "parallelism": (f"observations sharded over {world} rank(s); per iteration one exchange of p+5 doubles, " +
+                                   ("fused into the reduction/M-step kernels over NVLink peer memory"
+                                    if args.exchange == "peer" else "ncclAllReduce")),
                    "kernel": ("generic estep_forward_kernel" if args.no_jit or sampling != "forward" else
                               "NVRTC poset-specialised estep_forward_body (compiled during warm-up)")},
         "e2e": {"value": N * L_eff / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
@@ -326,6 +328,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU statistic exchange: fused peer-memory kernels (default) or ncclAllReduce")
     ap.add_argument("--no-jit", action="store_true", help="time the generic (poset-interpreting) forward kernel")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -42,6 +42,7 @@ extern "C" {
 #define MCCBN_MAX_P 64
 #define MCCBN_FAST_MAX_P 32
 #define MCCBN_NCCL_ID_BYTES 128
+#define MCCBN_IPC_HANDLE_BYTES 64
 
 typedef struct mccbn_ctx mccbn_ctx; /* owns the device buffers, stream, NCCL communicator */
 
@@ -62,6 +63,15 @@ int mccbn_ctx_set_stream(mccbn_ctx* ctx, void* cuda_stream);
 int mccbn_nccl_unique_id(unsigned char id[MCCBN_NCCL_ID_BYTES], char* err, size_t errlen);
 int mccbn_ctx_init_comm(mccbn_ctx* ctx, int rank, int world, const unsigned char id[MCCBN_NCCL_ID_BYTES], char* err,
                         size_t errlen);
+/* Preferred on one NVLink / NVSwitch domain (<= 16 GPUs of one box): the statistic exchange fused into the reduction
+ * and M-step kernels over peer memory.  Every rank owns a mailbox in its HBM; the reduction kernel stores the rank's
+ * p+5 doubles into every rank's mailbox with NVLink peer stores and publishes a sequence number, the M-step kernel
+ * waits for all ranks and sums in rank order (bit-identical parameters on all ranks, no collective call, no host
+ * involvement).  Bootstrap: every rank calls mccbn_ctx_peer_handle, the 64-byte CUDA IPC handles are all-gathered
+ * by any means (torch.distributed in the Python binding), then every rank calls mccbn_ctx_init_peers with the
+ * world x 64 bytes in rank order.  When both this and the NCCL communicator are initialised, this one is used. */
+int mccbn_ctx_peer_handle(mccbn_ctx* ctx, unsigned char handle[MCCBN_IPC_HANDLE_BYTES], char* err, size_t errlen);
+int mccbn_ctx_init_peers(mccbn_ctx* ctx, int rank, int world, const unsigned char* handles, char* err, size_t errlen);
 /* Counters for the bench contract: kernels launched by this library since the last reset. */
 uint64_t mccbn_kernel_launches(mccbn_ctx* ctx, int reset);
 

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("MCCBN_B200_LIB") or os.path.join(_HERE, "libmccbn_b20
 
 OK, ERR_NOT_ACYCLIC, ERR_ZERO_WEIGHT, ERR_CUDA, ERR_ARG, ERR_IO = 0, 1, 2, 3, 4, 5
 NCCL_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 class MccbnError(RuntimeError):
@@ -33,7 +34,8 @@ _lib = None
 # every symbol include/mccbn_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "mccbn_version", "mccbn_device_count", "mccbn_ctx_create", "mccbn_ctx_destroy", "mccbn_ctx_set_stream",
-    "mccbn_nccl_unique_id", "mccbn_ctx_init_comm", "mccbn_kernel_launches", "mccbn_MCEM_hcbn",
+    "mccbn_nccl_unique_id", "mccbn_ctx_init_comm", "mccbn_ctx_peer_handle", "mccbn_ctx_init_peers",
+    "mccbn_kernel_launches", "mccbn_MCEM_hcbn",
     "mccbn_obs_log_likelihood", "mccbn_importance_weight", "mccbn_importance_weight_genotype",
     "mccbn_adaptive_simulated_annealing", "mccbn_MCEM", "mccbn_flatten_poset", "mccbn_compatible_observations",
     "mccbn_neighbors", "mccbn_initialize_lambda", "mccbn_forward_from_times", "mccbn_estep_forward_from_times",

@@ -42,6 +42,23 @@ class Context:
         e.check(capi.lib().mccbn_ctx_init_comm(self._h, int(rank), int(world), buf, *e.args))
         self.rank, self.world = rank, world
 
+    def peer_handle(self):
+        """CUDA IPC handle of this rank's statistic mailbox (allocated on first use)."""
+        e = ErrBuf()
+        buf = (C.c_ubyte * capi.IPC_HANDLE_BYTES)()
+        e.check(capi.lib().mccbn_ctx_peer_handle(self._h, buf, *e.args))
+        return bytes(buf)
+
+    def init_peers(self, rank, world, handles):
+        """`handles`: the world IPC handles in rank order (bytes of length world * 64)."""
+        handles = bytes(handles)
+        if len(handles) != world * capi.IPC_HANDLE_BYTES:
+            raise ValueError("expected world * 64 bytes of IPC handles")
+        e = ErrBuf()
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        e.check(capi.lib().mccbn_ctx_init_peers(self._h, int(rank), int(world), buf, *e.args))
+        self.rank, self.world = rank, world
+
     def kernel_launches(self, reset=False):
         return int(capi.lib().mccbn_kernel_launches(self._h, int(reset)))
 

@@ -29,6 +29,8 @@ constexpr int kMaxCand = 16;       // concurrently scored candidate posets (ASA 
 constexpr int kMaxEdgesFast = 512; // >= 32*31/2
 constexpr int kFwdBlock = 128;     // threads per block of the forward E-step kernel
 constexpr int kStatHdr = 5;        // partial record: [sum w', sum w'^2, sum w' d, #{w>0}, log scale]; stats: [LL, N_eff, D, zero_count, -]
+constexpr int kMaxWorld = 16;      // ranks of one NVLink domain in the peer-memory statistic exchange
+constexpr int kMaxPSlots = 72;     // >= kStatHdr + 64
 constexpr int kRtabN = 72;         // relative-weight table r^delta, delta = 0..64, tail = 0
 
 // static structure of one poset, topological-position space (uploaded by the host)
@@ -59,7 +61,21 @@ struct DevModel {
   int flip;
   int iter;           // EM iterations done since set_model
   int zero_weight;    // sticky: some observation had sum w == 0
-  int pad;
+  int comm_error;     // sticky: the peer-memory statistic exchange timed out waiting for a rank
+};
+
+// Peer-memory statistic exchange (kernels_reduce.cuh): every rank owns one mailbox in its HBM; the reduction kernel of
+// rank r stores its statistic vector into slot[parity][r] of EVERY rank's mailbox over NVLink and then publishes the
+// exchange number in flag[r]; the M-step kernel waits for all flags and sums the slots in rank order, so all ranks
+// compute bit-identical parameters without a collective call.
+struct Mailbox {
+  unsigned long long flag[kMaxWorld];
+  double slot[2][kMaxWorld][kMaxPSlots];
+};
+struct PeerView {
+  Mailbox* box[kMaxWorld];  // box[q] = rank q's mailbox mapped into this process (box[rank] is local memory)
+  int rank, world;
+  unsigned long long seq;   // number of this exchange (1, 2, ...), identical on all ranks
 };
 
 // Static "program" of one poset for the sampling kernels.  It is known to the host, so it travels as a

@@ -34,6 +34,7 @@ struct Error : std::runtime_error {
 
 static const char* kMsgNotAcyclic = "Poset does not correspond to an acyclic graph";
 static const char* kMsgZeroWeight = "ERROR: all samples have weight 0. Consider increasing L";
+static const char* kMsgCommTimeout = "peer-memory statistic exchange timed out: a rank did not publish its statistics";
 
 // ---- NCCL through dlopen (no link-time dependency; reuses the libnccl.so.2 torch already loaded, if any) -----
 struct NcclApi {
@@ -183,6 +184,11 @@ struct mccbn_ctx {
   mccbn::NcclApi::comm_t comm = nullptr;
   int rank = 0, world = 1;
   uint64_t launches = 0;
+  // peer-memory statistic exchange (device_types.cuh: Mailbox); preferred over NCCL when initialised
+  mccbn::Mailbox* mailbox = nullptr;
+  mccbn::Mailbox* peer_box[mccbn::kMaxWorld] = {};
+  bool peer_ready = false;
+  unsigned long long xchg_seq = 0;
   mccbn::JitCache* jit = nullptr;  // poset-specialised kernels (jit.cuh)
   int jit_mode = -1;               // -1 auto (large problems only), 0 off, 1 always
 };

@@ -294,6 +294,7 @@ static std::vector<EmResult> run_mcem_multi(mccbn_problem& pb, const std::vector
     for (size_t r = 0; r < runs.size(); ++r) {
       EmRun& R = runs[r];
       if (R.done || n_run[r] == 0) continue;
+      if (dms[r].comm_error) throw Error(MCCBN_ERR_CUDA, kMsgCommTimeout);
       if (dms[r].zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
       for (unsigned t = 0; t < n_run[r]; ++t) {
         const double* row = rows[r].data() + (size_t)t * stride;
@@ -462,6 +463,9 @@ void mccbn_ctx_destroy(mccbn_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   delete c->jit;
+  for (int q = 0; q < kMaxWorld; ++q)
+    if (c->peer_box[q] && c->peer_box[q] != c->mailbox) cudaIpcCloseMemHandle(c->peer_box[q]);
+  if (c->mailbox) cudaFree(c->mailbox);
   if (c->comm) c->nccl.CommDestroy(c->comm);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -499,6 +503,47 @@ int mccbn_ctx_init_comm(mccbn_ctx* c, int rank, int world, const unsigned char i
     std::memcpy(u.internal, id, MCCBN_NCCL_ID_BYTES);
     c->nccl.check(c->nccl.CommInitRank(&c->comm, world, u, rank), "ncclCommInitRank");
   }
+  MCCBN_CATCH
+}
+
+// ---- peer-memory statistic exchange: bootstrap -------------------------------------------------------------------
+int mccbn_ctx_peer_handle(mccbn_ctx* c, unsigned char handle[MCCBN_IPC_HANDLE_BYTES], char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  static_assert(sizeof(cudaIpcMemHandle_t) == MCCBN_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!c->mailbox) {
+    MCCBN_CUDA(cudaMalloc((void**)&c->mailbox, sizeof(Mailbox)));
+    MCCBN_CUDA(cudaMemset(c->mailbox, 0, sizeof(Mailbox)));
+    MCCBN_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t h;
+  MCCBN_CUDA(cudaIpcGetMemHandle(&h, c->mailbox));
+  std::memcpy(handle, &h, MCCBN_IPC_HANDLE_BYTES);
+  MCCBN_CATCH
+}
+
+int mccbn_ctx_init_peers(mccbn_ctx* c, int rank, int world, const unsigned char* handles, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+    throw Error(MCCBN_ERR_ARG, "invalid rank/world for the peer exchange (at most 16 ranks)");
+  if (!c->mailbox) throw Error(MCCBN_ERR_ARG, "call mccbn_ctx_peer_handle first");
+  if (c->comm && (c->rank != rank || c->world != world)) throw Error(MCCBN_ERR_ARG, "rank/world differ from the NCCL communicator");
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) {
+      c->peer_box[q] = c->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)q * MCCBN_IPC_HANDLE_BYTES, MCCBN_IPC_HANDLE_BYTES);
+    void* ptr = nullptr;
+    MCCBN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_box[q] = static_cast<Mailbox*>(ptr);
+  }
+  c->rank = rank;
+  c->world = world;
+  c->xchg_seq = 0;
+  c->peer_ready = world > 1;
   MCCBN_CATCH
 }
 
@@ -574,6 +619,7 @@ int mccbn_problem_read(mccbn_problem* pb, double* lambda, double* eps, double* l
   if (lambda) std::memcpy(lambda, dm.lambda, sizeof(double) * pb->p);
   if (eps) *eps = dm.eps;
   if (llhood) *llhood = dm.llhood;
+  if (dm.comm_error) throw Error(MCCBN_ERR_CUDA, kMsgCommTimeout);
   if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
   MCCBN_CATCH
 }
@@ -655,6 +701,7 @@ int mccbn_obs_log_likelihood(mccbn_ctx* c, const int* obs, const int* poset, con
                sampling_times_available, seed, N, p, opt, false);
   DevModel dm;
   pb.read_model(0, dm);
+  if (dm.comm_error) throw Error(MCCBN_ERR_CUDA, kMsgCommTimeout);
   if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
   *llhood_out = dm.llhood;
   MCCBN_CATCH
@@ -937,6 +984,7 @@ int mccbn_estep_forward_from_times(mccbn_ctx* c, const int* obs, int N, const in
   pb.run_mstep(0, 1);
   DevModel dm;
   pb.read_model(0, dm);
+  if (dm.comm_error) throw Error(MCCBN_ERR_CUDA, kMsgCommTimeout);
   if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
   if (w_sum) MCCBN_CUDA(cudaMemcpyAsync(w_sum, pb.out_w.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
   if (w_sum_sq) MCCBN_CUDA(cudaMemcpyAsync(w_sum_sq, pb.out_w2.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));

@@ -110,6 +110,60 @@ __global__ void reduce_stats_kernel(const double* __restrict__ blk_part, double*
   }
 }
 
+// ---- peer-memory statistic exchange (replaces ncclAllReduce on one NVLink domain) ---------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// second stage + push: fixed-order sum of the block partials, stored into slot[seq & 1][rank] of every rank's mailbox
+// (NVLink peer stores), then flag[rank] = seq with release semantics at system scope.  One block.
+__global__ void reduce_push_kernel(const double* __restrict__ blk_part, double* __restrict__ stats, int n_blocks, int PS,
+                                   const PeerView pv) {
+  const int par = (int)(pv.seq & 1ull);
+  for (int s = threadIdx.x; s < PS; s += blockDim.x) {
+    double t = 0.0;
+    for (int b = 0; b < n_blocks; ++b) t += blk_part[(size_t)b * PS + s];
+    stats[s] = t;  // the local (unreduced) vector stays visible for debugging; mstep overwrites it with the sum
+    for (int q = 0; q < pv.world; ++q) pv.box[q]->slot[par][pv.rank][s] = t;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < pv.world) st_release_sys(&pv.box[threadIdx.x]->flag[pv.rank], pv.seq);
+}
+
+// pull: wait until every rank has published exchange `seq`, then sum the slots in rank order into st_out[PS]
+// (shared or global).  Returns false (for all threads) after ~10 s without progress: a rank died.
+__device__ inline bool peer_pull(const PeerView& pv, int PS, double* st_out) {
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  Mailbox* mine = pv.box[pv.rank];
+  if (threadIdx.x < pv.world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine->flag[threadIdx.x]) < pv.seq) {
+      if (clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
+        s_ok = 0;
+        break;
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  const int par = (int)(pv.seq & 1ull);
+  for (int s = threadIdx.x; s < PS; s += blockDim.x) {
+    double t = 0.0;
+    for (int r = 0; r < pv.world; ++r) t += *(volatile double*)&mine->slot[par][r][s];
+    st_out[s] = t;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
 // Derived tables for the next E-step (device function, run by one block).
 __device__ inline void prepare_tables(const DevPoset* __restrict__ pos, DevModel* __restrict__ mdl,
                                       FwdScale* __restrict__ sc) {
@@ -146,9 +200,15 @@ __global__ void prepare_kernel(const DevPoset* poset, DevModel* model, FwdScale*
 
 // Stage 6: M-step + trace row + tables for the next iteration.  One block.
 // stats may have been all-reduced across GPUs in between (identical on every rank => replicated M-step).
-__global__ void mstep_kernel(const double* __restrict__ st, const DevPoset* pos, DevModel* mdl, FwdScale* scale,
-                             double* trace, int trace_stride, int max_trace_rows, int PS, int update_params) {
+// With a PeerView (world > 1) the kernel first pulls the statistic vectors of all ranks out of its mailbox.
+__global__ void mstep_kernel(double* __restrict__ st, const DevPoset* pos, DevModel* mdl, FwdScale* scale,
+                             double* trace, int trace_stride, int max_trace_rows, int PS, int update_params,
+                             const PeerView pv) {
   const int p = pos->p;
+  if (pv.world > 1) {
+    if (!peer_pull(pv, PS, st) && threadIdx.x == 0) mdl->comm_error = 1;
+    __threadfence_block();
+  }
   const double LL = st[0], Neff = st[1], D = st[2], zero = st[3];
   if (update_params) {
     for (int k = threadIdx.x; k < p; k += blockDim.x) {

@@ -146,6 +146,16 @@ struct mccbn_problem {
   FlatPoset flat[kMaxCand];
   int iter_host[kMaxCand];
   uint32_t eval_id[kMaxCand];
+  unsigned long long xchg_seq[kMaxCand] = {};  // exchange number of the candidate's pending reduce_push
+  PeerView peer_view(unsigned long long seq) const {
+    PeerView pv;
+    std::memset(&pv, 0, sizeof(pv));
+    for (int q = 0; q < ctx->world && q < kMaxWorld; ++q) pv.box[q] = ctx->peer_box[q];
+    pv.rank = ctx->rank;
+    pv.world = ctx->world;
+    pv.seq = seq;
+    return pv;
+  }
   int fin_blocks = 0;
   int expected_esteps = 1;  // hint for the JIT policy (set by the EM driver)
 
@@ -320,18 +330,31 @@ struct mccbn_problem {
     fa.L_eff = L_eff;
     fa.uniform_fallback = uniform_fallback;
     finalize_kernel<<<fin_blocks, kFinBlock, 0, s>>>(fa);
-    reduce_stats_kernel<<<1, 64, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS());
+    if (ctx->world > 1 && ctx->peer_ready) {
+      xchg_seq[c] = ++ctx->xchg_seq;
+      reduce_push_kernel<<<1, 64, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS(), peer_view(xchg_seq[c]));
+    } else {
+      reduce_stats_kernel<<<1, 64, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS());
+    }
     ctx->launches += 2;
     MCCBN_CUDA(cudaGetLastError());
   }
   void run_mstep(int c, int update_params) {
     cudaStream_t s = ctx->stream;
-    if (ctx->world > 1)
-      ctx->nccl.check(ctx->nccl.AllReduce(stats_of(c), stats_of(c), (size_t)PS(), NcclApi::kDouble, NcclApi::kSum,
-                                          ctx->comm, s),
-                      "ncclAllReduce");
+    PeerView pv = peer_view(0);
+    if (ctx->world > 1 && ctx->peer_ready) {
+      pv = peer_view(xchg_seq[c]);  // the M-step kernel pulls the vectors pushed by reduce_push_kernel
+    } else {
+      pv.world = 1;
+      if (ctx->world > 1) {
+        if (!ctx->comm) throw Error(MCCBN_ERR_ARG, "world > 1 but neither the peer exchange nor NCCL is initialised");
+        ctx->nccl.check(ctx->nccl.AllReduce(stats_of(c), stats_of(c), (size_t)PS(), NcclApi::kDouble, NcclApi::kSum,
+                                            ctx->comm, s),
+                        "ncclAllReduce");
+      }
+    }
     mstep_kernel<<<1, 64, 0, s>>>(stats_of(c), posets.ptr + c, models.ptr + c, scales.ptr + c,
-                                  trace.ptr ? trace_of(c) : nullptr, p + 2, trace_rows, PS(), update_params);
+                                  trace.ptr ? trace_of(c) : nullptr, p + 2, trace_rows, PS(), update_params, pv);
     ctx->launches++;
     MCCBN_CUDA(cudaGetLastError());
     iter_host[c]++;

@@ -3,8 +3,9 @@ bootstrap of the library's own NCCL communicator.
 
 The path shards by observation (the reference's OpenMP loop over i, src/mcem_hcbn.cpp:665-700, has only `+`
 reductions): rank r holds rows [lo, hi) of obs / times / weights, runs the E-step on them with GLOBAL row indices in
-the Philox counters, and one sum-allreduce of the p+5 statistic vector [LL, N_eff, D, zero_count, 0, S_0..S_{p-1}]
-per EM iteration (issued by the C library on its own stream) precedes the replicated on-device M-step.
+the Philox counters, and one exchange of the p+5 statistic vector [LL, N_eff, D, zero_count, 0, S_0..S_{p-1}] per EM
+iteration precedes the replicated on-device M-step: either fused into the library's reduction and M-step kernels over
+NVLink peer memory (default on one box) or one ncclAllReduce issued by the C library on its own stream.
 """
 import numpy as np
 
@@ -47,12 +48,27 @@ def broadcast_unique_id(dist, device=None):
     return bytes(buf.cpu().tolist())
 
 
-def init_context(local_rank, dist=None):
-    """Context on cuda:local_rank whose NCCL communicator spans the torch.distributed world."""
+def gather_peer_handles(ctx, dist, device=None):
+    """All-gather of the 64-byte CUDA IPC handles of the ranks' statistic mailboxes, in rank order."""
+    import torch
+    mine = torch.tensor(list(ctx.peer_handle()), dtype=torch.uint8, device=device)
+    parts = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, mine)
+    return b"".join(bytes(t.cpu().tolist()) for t in parts)
+
+
+def init_context(local_rank, dist=None, exchange="peer"):
+    """Context on cuda:local_rank for one rank of the torch.distributed world.
+
+    exchange="peer": the statistic exchange runs inside the reduction / M-step kernels over NVLink peer memory (one box);
+    exchange="nccl": one ncclAllReduce per EM iteration on the library's own communicator (also across boxes)."""
     from . import api
     ctx = api.Context(local_rank)
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         import torch
         dev = torch.device("cuda", local_rank) if dist.get_backend() == "nccl" else None
-        ctx.init_comm(dist.get_rank(), dist.get_world_size(), broadcast_unique_id(dist, dev))
+        if exchange == "peer":
+            ctx.init_peers(dist.get_rank(), dist.get_world_size(), gather_peer_handles(ctx, dist, dev))
+        else:
+            ctx.init_comm(dist.get_rank(), dist.get_world_size(), broadcast_unique_id(dist, dev))
     return ctx
