@@ -32,6 +32,8 @@ struct CondLauncher {
       if (times_given) MCCBN_COND(true, kCondBackward); else MCCBN_COND(false, kCondBackward);
     } else if (mode == kCondBernoulli) {
       if (times_given) MCCBN_COND(true, kCondBernoulli); else MCCBN_COND(false, kCondBernoulli);
+    } else if (mode == kCondAddRemove) {
+      if (times_given) MCCBN_COND(true, kCondAddRemove); else MCCBN_COND(false, kCondAddRemove);
     } else {
       if (times_given) MCCBN_COND(true, kCondOtcbn); else MCCBN_COND(false, kCondOtcbn);
     }
@@ -76,10 +78,11 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
       launch_forward_jit(jk, a, flat[c], c, grid_x);
     else
       launch_forward<float>(a, flat[c], times_given, grid_x, c);
-  } else if (scheme == kBackward || scheme == kBernoulli || scheme == kOtcbn) {
+  } else if (scheme == kBackward || scheme == kBernoulli || scheme == kOtcbn || scheme == kAddRemove) {
     CondArgs a;
     std::memset(&a, 0, sizeof(a));
-    int mode = scheme == kBackward ? kCondBackward : (scheme == kBernoulli ? kCondBernoulli : kCondOtcbn);
+    int mode = scheme == kBackward ? kCondBackward
+                                   : (scheme == kBernoulli ? kCondBernoulli : (scheme == kAddRemove ? kCondAddRemove : kCondOtcbn));
     if (scheme == kBackward) {
       BackwardPlan bp = plan_backward(p, neighborhood_dist, (unsigned)L);
       if (bp.reps == 0) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);  // L < nrows_sum: no samples at all
@@ -121,7 +124,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.chunk_len = chunk_len;
     a.n_items = n_items;
     a.obs_offset = obs_offset;
-    const PhiloxKey key = make_key(seed, (uint32_t)iter, scheme == kBackward ? 1u : (scheme == kBernoulli ? 2u : 5u));
+    const PhiloxKey key = make_key(seed, (uint32_t)iter, scheme == kBackward ? 1u : (scheme == kBernoulli ? 2u : (scheme == kAddRemove ? 6u : 5u)));
     a.key0 = key.k0;
     a.key1 = key.k1;
     a.cw = eval_id[c];
@@ -192,7 +195,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     MCCBN_CUDA(cudaGetLastError());
     L_eff = K;  // obs_llhood_i = log(sum_k q_k / K)  (w_l = sum q / K for all L resampled rows, :491)
   } else {
-    throw Error(MCCBN_ERR_ARG, "sampling scheme 'add-remove' is not implemented in this build");
+    throw Error(MCCBN_ERR_ARG, "unknown sampling scheme");
   }
   run_finalize(c, chunks, n_items, L_eff, 0, per_obs_out);
   run_mstep(c, update_params);

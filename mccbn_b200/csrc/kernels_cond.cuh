@@ -1,9 +1,10 @@
 // kernels_cond.cuh -- conditional ("truncated-exponential") proposal E-step for sm_100a: the backward
-// (Hamming-ball) and bernoulli schemes of the reference, and the OT-CBN proposal (X == Y).
+// (Hamming-ball), bernoulli and add-remove schemes of the reference, and the OT-CBN proposal (X == Y).
 //
 // Replaces, per (observation i, sample l):
 //   neighbors / replicate          src/backward_sampling.cpp:37-54, src/mcem_hcbn.cpp:497-513  X = Y ^ flip[l mod n]
 //   coin_tossing                   src/backward_sampling.cpp:64-77                              X = Y ^ Bernoulli(eps) mask
+//   add-remove proposal            src/mcem_hcbn.cpp:389-459, src/add_remove.cpp:17-141          X = closure(Y +/- one event)
 //   generate_mutation_times        src/add_remove.cpp:156-203   T_s ~ Exp(lambda_s); per node in topological order
 //                                     m = max_pa T; X_j ? z ~ TExp(lambda_j, 0, T_s - m), T_j = m + z
 //                                                       : z ~ Exp(lambda_j),            T_j = max(m, T_s) + z;  Z_j = T_j - m
@@ -23,7 +24,7 @@
 
 namespace mccbn {
 
-enum CondMode { kCondBackward = 0, kCondBernoulli = 1, kCondOtcbn = 2 };
+enum CondMode { kCondBackward = 0, kCondBernoulli = 1, kCondOtcbn = 2, kCondAddRemove = 3 };
 
 struct CondArgs {
   const uint64_t* obs_bits;
@@ -131,6 +132,15 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
   __shared__ real s_lam2[PMAX + 1];
   __shared__ real s_inv[PMAX + 1];
   __shared__ real s_lpyx2[68];  // log2 P(Y|X) by Hamming distance
+  // add-remove scheme: transitive closures and "expected time to reach" scales (scale_path_to_mutation,
+  // src/add_remove.cpp:17-37) by topological position; per warp the categorical over the <= p + 1 proposals of the
+  // current observation (cumulative probabilities, hidden genotype and constant log2-weight part of every proposal)
+  constexpr int kAR = MODE == kCondAddRemove ? PMAX : 1;
+  __shared__ uint32_t s_anc[kAR], s_desc[kAR];
+  __shared__ real s_sc[kAR];
+  __shared__ real s_cdf[kFwdBlock / 32][kAR + 1];
+  __shared__ real s_lc[kFwdBlock / 32][kAR + 1];
+  __shared__ uint32_t s_Xc[kFwdBlock / 32][kAR + 1];
 
   const DevModel* __restrict__ mdl = a.model;
   const int p = pg.p;
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
   }
   for (int d = threadIdx.x; d < 68; d += kFwdBlock) {
     double lp = 0.0;
-    if (MODE == kCondBackward && d <= p) {
+    if ((MODE == kCondBackward || MODE == kCondAddRemove) && d <= p) {
       // log_bernoulli_process (src/mcem_hcbn.cpp:84-100), incl. the eps == 0 special case
       const double eps = mdl->eps;
       if (eps == 0.0)
@@ -157,6 +167,24 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
         lp = log(eps) * d + log1p(-eps) * (p - d);
     }
     s_lpyx2[d] = (real)(lp * kLog2e);
+  }
+  if (MODE == kCondAddRemove && threadIdx.x == 0) {
+    double sc[PMAX];
+    for (int k = 0; k < p; ++k) {  // topological order: parents before children
+      uint32_t an = 1u << k;
+      double mx = -1.0;
+      for (uint32_t m = pg.parent_mask[k]; m; m &= m - 1) {
+        const int j = __ffs((int)m) - 1;
+        an |= s_anc[j];
+        mx = fmax(mx, sc[j]);
+      }
+      s_anc[k] = an;
+      sc[k] = 1.0 / mdl->lambda[pg.ev[k]] + (mx > -1.0 ? mx : 0.0);
+      s_sc[k] = (real)sc[k];
+      s_desc[k] = 1u << k;
+    }
+    for (int k = p - 1; k >= 0; --k)
+      for (uint32_t m = pg.parent_mask[k]; m; m &= m - 1) s_desc[__ffs((int)m) - 1] |= s_desc[k];
   }
   __syncthreads();
 
@@ -179,12 +207,12 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
     real aw = (real)0, aw2 = (real)0, awd = (real)0, npos = (real)0;
     real mref = (real)-1e30;  // this lane's log2 reference
 
-    auto consume = [&](const uint32_t l, const uint32_t Xt, const int d, const bool valid) {
+    auto consume = [&](const uint32_t l, const uint32_t Xt, const int d, const bool valid, const real lw2_extra) {
       real Z[PMAX];
       real Ts;
       const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(pg, tcol_s, s_lam2, s_inv, l, gi, a.key0, a.key1, cw,
                                                                     ts_given, Xt, Z, Ts);
-      const real lw2 = lw2s + s_lpyx2[d];
+      const real lw2 = lw2s + lw2_extra;
       const bool ok = valid && (lw2 > (real)-1e30);  // F <= 0 (incompatible) gives NaN / -inf -> not ok
       if (ok && lw2 > mref) {  // rare after the first few samples: move the reference up (with head-room)
         const real nref = lw2 + (real)4;
@@ -222,9 +250,72 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
         for (int r0 = 0; r0 < a.reps; r0 += 32) {
           const int rep = r0 + lane;
           // sample index as in the reference's replicate(reps, 1) layout: row l = g + n_ball * rep
-          consume((uint32_t)(g + a.n_ball * rep), Xt, d, rep < a.reps);
+          consume((uint32_t)(g + a.n_ball * rep), Xt, d, rep < a.reps, s_lpyx2[d]);
         }
       }
+    } else if constexpr (MODE == kCondAddRemove) {
+      // The reference draws (move, idx_add, idx_remove) independently and uses one of the two indices
+      // (src/mcem_hcbn.cpp:401-437); the pair (move, used index) is ONE categorical variable over <= p + 1 proposals:
+      //   add event k (y_k = 0):     prob P(add) a_k / sum a,  a_k = 1 / scale_k;   X = closure_up(Y + k)
+      //   remove event k (y_k = 1):  prob P(rem) r_k / sum r,  r_k = scale_k;       X = closure_down(Y - k)
+      //   stand still (Y compatible): X = Y
+      // with closure_up / closure_down of the whole genotype when Y is incompatible (add_all / remove_all,
+      // src/add_remove.cpp:39-56, :74-91) and of the touched event only when it is compatible (:58-72, :93-107).
+      const int w = threadIdx.x >> 5;
+      const bool live = lane < p;
+      const bool yk = live && ((yt >> lane) & 1u);
+      const bool compat = compatible_topo<PMAX>(pg, yt);
+      const int mutations = __popc(yt);
+      const uint32_t anc = live ? s_anc[lane] : 0u, desc = live ? s_desc[lane] : 0u;
+      const uint32_t up = __reduce_or_sync(0xffffffffu, yk ? anc : 0u);                 // Y plus all its ancestors
+      const uint32_t down = __ballot_sync(0xffffffffu, yk && (anc & ~yt) == 0u);        // largest compatible subset
+      const real sck = live ? s_sc[lane] : (real)1;
+      real wa = (live && !yk) ? (real)1 / sck : (real)0, wr = yk ? sck : (real)0;
+      real sa = wa, sr = wr;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      }
+      real p_add, p_rem, p_stand;
+      if (!compat) p_add = (real)0.5, p_rem = (real)0.5, p_stand = (real)0;
+      else if (mutations == 0) p_add = (real)0.5, p_rem = (real)0, p_stand = (real)0.5;
+      else if (mutations == p) p_add = (real)0, p_rem = (real)0.5, p_stand = (real)0.5;
+      else p_add = p_rem = p_stand = (real)(1.0 / 3.0);
+      const real pmf = !live ? (real)0 : (yk ? p_rem * wr / sr : p_add * wa / sa);
+      real cdf = pmf;  // inclusive scan over lanes = proposals in topological-position order
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const real t = __shfl_up_sync(0xffffffffu, cdf, o);
+        if (lane >= o) cdf += t;
+      }
+      const uint32_t Xk = yk ? ((compat ? yt : down) & ~desc) : ((compat ? yt : up) | anc);
+      const uint32_t has = __ballot_sync(0xffffffffu, pmf > (real)0);
+      const int cmax = p_stand > (real)0 ? p : 31 - __clz((int)has);  // last proposal that can be drawn
+      __syncwarp();
+      if (live) {
+        s_cdf[w][lane] = cdf;
+        s_Xc[w][lane] = Xk;
+        s_lc[w][lane] = s_lpyx2[__popc(Xk ^ yt)] - CondMath<real>::lg2(fmax(pmf, (real)1e-37));
+      }
+      if (lane == 0) {
+        s_cdf[w][p] = (real)2;
+        s_Xc[w][p] = yt;
+        s_lc[w][p] = s_lpyx2[0] - CondMath<real>::lg2(fmax(p_stand, (real)1e-37));
+      }
+      __syncwarp();
+      const int l_begin = ch * a.chunk_len, l_end = min(a.L, l_begin + a.chunk_len);
+      for (int l0 = l_begin; l0 < l_end; l0 += 32) {
+        const int l = l0 + lane;
+        const uint4 rc = philox4x32_10((uint32_t)l, gi, 64u, cw, a.key0, a.key1);
+        const real u = cond_uniform<real>(rc, 0);
+        int cidx = 0;
+        for (int k = 0; k < p; ++k) cidx += (s_cdf[w][k] <= u) ? 1 : 0;  // broadcast reads
+        cidx = min(cidx, cmax);
+        const uint32_t Xt = s_Xc[w][cidx];
+        consume((uint32_t)l, Xt, __popc(Xt ^ yt), l < l_end, s_lc[w][cidx]);
+      }
+      __syncwarp();
     } else {
       const int l_begin = ch * a.chunk_len, l_end = min(a.L, l_begin + a.chunk_len);
       for (int l0 = l_begin; l0 < l_end; l0 += 32) {
@@ -243,7 +334,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
           }
         }
         const bool comp = compatible_topo<PMAX>(pg, Xt);
-        consume((uint32_t)l, Xt, __popc(Xt ^ yt), (l < l_end) && comp);
+        consume((uint32_t)l, Xt, __popc(Xt ^ yt), (l < l_end) && comp, s_lpyx2[__popc(Xt ^ yt)]);
       }
     }
 
