@@ -1610,6 +1610,14 @@ int ref_initialize_lambda(const int* obs, int N, const int* poset, int p, float 
 }
 
 // draw `n` exponentials exactly as rexp<StdRng> would from a fresh Context(seed) (RNG pinning test)
+// Known-answer test of the third-party generator the reference is built on: the C++ standard ([rand.predef]) fixes the
+// 10000th output of a default-constructed std::mt19937 to 4123659995.
+unsigned ref_mt19937_kat() {
+  std::mt19937 g;
+  g.discard(9999);
+  return (unsigned)g();
+}
+
 int ref_rexp(int n, double rate, int seed, double* out) {
   REF_TRY
   Context ctx(seed);

@@ -322,6 +322,13 @@ def initialize_lambda(obs, poset, lambda_s=1.0, max_lambda=1e6):
     return lam, e.value
 
 
+def mt19937_kat():
+    """10000th output of a default-seeded std::mt19937 (the C++ standard says 4123659995)."""
+    f = lib().ref_mt19937_kat
+    f.restype = C.c_uint
+    return int(f())
+
+
 def rexp(n, rate, seed):
     out = np.zeros(n)
     _chk(lib().ref_rexp(n, C.c_double(rate), seed, _p(out)))
