@@ -19,6 +19,7 @@
 
 #include <chrono>
 #include <map>
+#include <set>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -311,7 +312,11 @@ static std::string jit_cache_path(const std::string& src) {
   if (const char* e = std::getenv("MCCBN_CACHE_DIR")) dir = e;
   else if (const char* h = std::getenv("HOME")) dir = std::string(h) + "/.cache/mccbn_b200";
   if (dir.empty() || dir == "off") return "";
-  (void)!system(("mkdir -p '" + dir + "' 2>/dev/null").c_str());
+  static std::string made;  // create the directory once per process, not once per lookup
+  if (made != dir) {
+    (void)!system(("mkdir -p '" + dir + "' 2>/dev/null").c_str());
+    made = dir;
+  }
   char name[64];
   std::snprintf(name, sizeof name, "/fwd_%016llx.cubin", (unsigned long long)fnv1a64(src + kSrc_kernels_forward_cuh + kSrc_philox_cuh + kSrc_device_types_cuh +
                                                     (std::getenv("MCCBN_JIT_PTXAS_O") ? std::getenv("MCCBN_JIT_PTXAS_O") : "")));
@@ -327,6 +332,7 @@ static int jit_default_minb() {
 struct JitCache {
   NvrtcApi rtc;
   std::map<std::string, JitKernel> kernels;
+  std::set<std::string> disk_misses;  // posets looked up with only_if_cached and not found on disk
   int minb = jit_default_minb();
 
   // `only_if_cached`: do not compile, return the kernel only if it is already in memory or on disk
@@ -335,10 +341,16 @@ struct JitCache {
     auto it = kernels.find(key);
     if (it != kernels.end()) return it->second.ok ? &it->second : nullptr;
     if (only_if_cached) {
+      // this lookup sits on the per-iteration path of small problems: remember that the disk cache has no kernel for
+      // this poset instead of regenerating and hashing the source every time
+      if (disk_misses.count(key)) return nullptr;
       const std::string p0 = jit_cache_path(generate_forward_source(f, times_given, minb));
-      if (p0.empty()) return nullptr;
-      FILE* fp = std::fopen(p0.c_str(), "rb");
-      if (!fp) return nullptr;
+      FILE* fp = p0.empty() ? nullptr : std::fopen(p0.c_str(), "rb");
+      if (!fp) {
+        if (disk_misses.size() > 4096) disk_misses.clear();
+        disk_misses.insert(key);
+        return nullptr;
+      }
       std::fclose(fp);
     }
     JitKernel jk;
