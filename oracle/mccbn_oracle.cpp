@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <functional>
 #include <limits>
 #include <memory>
@@ -219,6 +220,143 @@ struct Model {
   void update_node_idx() {  // model_impl.cpp:318-322
     for (int i = 0; i < p; ++i) node_idx[event_id[i]] = i;
     update_node_idx_flag = false;
+  }
+
+  // ---- edit operations of the annealer (src/model_impl.cpp:89-316) -------------------------------------------
+  bool raw_add_edge(int u, int v) {  // boost::add_edge on a setS out-edge list: false if the edge exists
+    if (!out[u].insert(v).second) return false;
+    in[v].insert(u);
+    return true;
+  }
+  void raw_remove_edge(int u, int v) {
+    out[u].erase(v);
+    in[v].erase(u);
+  }
+  // set_children (:90-107): all successors per vertex, visiting vertices in reverse topological order
+  void set_children() {
+    for (int u : topo_path) {
+      children[u].clear();
+      for (int v : out[u]) {
+        children[u].insert(v);
+        children[u].insert(children[v].begin(), children[v].end());
+      }
+    }
+    update_children_flag = false;
+  }
+  // update_children (:110-122)
+  void update_children(int u) {
+    children[u].clear();
+    for (int v : out[u]) {
+      children[u].insert(v);
+      children[u].insert(children[v].begin(), children[v].end());
+    }
+  }
+  // transitive_reduction_dag (:148-190): drop every edge u -> v whose target is already reachable through an
+  // earlier (in topological order) direct successor of u; reduction_flag = "nothing had to be dropped"
+  void transitive_reduction_dag() {
+    reduction_flag = true;
+    std::vector<int> rank(p, 0);
+    int n = 0;
+    for (auto it = topo_path.rbegin(); it != topo_path.rend(); ++it, ++n) rank[*it] = n;
+    std::vector<std::vector<int>> succ(p);
+    for (int v = 0; v < p; ++v) {
+      succ[v].assign(out[v].begin(), out[v].end());
+      std::stable_sort(succ[v].begin(), succ[v].end(), [&](int a, int b) { return rank[a] < rank[b]; });
+    }
+    std::vector<std::unordered_set<int>> all_succ(p);
+    for (int u : topo_path) {
+      for (int v : succ[u]) {
+        if (all_succ[u].count(v)) {
+          remove_edge(u, v);
+          reduction_flag = false;
+        } else {
+          all_succ[u].insert(v);
+          all_succ[u].insert(all_succ[v].begin(), all_succ[v].end());
+        }
+      }
+    }
+  }
+  // add_edge (:193-212)
+  bool add_edge(int u, int v) {
+    const bool added = raw_add_edge(u, v);
+    if (added) {
+      has_cycles();
+      if (!cycle) {
+        topological_sort();
+        transitive_reduction_dag();
+        update_children_flag = true;
+      }
+    }
+    return added;
+  }
+  // remove_edge (:214-217)
+  void remove_edge(int u, int v) {
+    raw_remove_edge(u, v);
+    update_children_flag = true;
+  }
+  // remove_redundant_edges (:219-238)
+  void remove_redundant_edges(int u, int v) {
+    std::vector<int> outs(out[u].begin(), out[u].end());
+    for (int w : outs)
+      if (w == v || children[v].count(w)) raw_remove_edge(u, w);
+    children[u].insert(v);
+    children[u].insert(children[v].begin(), children[v].end());
+    std::vector<int> ins(in[u].begin(), in[u].end());
+    for (int q : ins) remove_redundant_edges(q, v);
+  }
+  // add_relation (:240-285)
+  bool add_relation(int u, int v) {
+    const bool added = raw_add_edge(u, v);
+    if (added) {
+      if (children[u].count(v)) {  // v already reachable from u
+        reduction_flag = false;
+        return added;
+      }
+      if (children[v].count(u)) {
+        cycle = true;
+        return added;
+      }
+      if (!cycle) {
+        std::vector<int> outs(out[u].begin(), out[u].end());
+        for (int w : outs)
+          if (children[v].count(w)) raw_remove_edge(u, w);
+        children[u].insert(v);
+        children[u].insert(children[v].begin(), children[v].end());
+        std::vector<int> ins(in[u].begin(), in[u].end());
+        for (int q : ins) remove_redundant_edges(q, v);
+        topological_sort();
+        transitive_reduction_dag();
+      }
+    }
+    return added;
+  }
+  // remove_relation (:287-316)
+  void remove_relation(int u, int v) {
+    raw_remove_edge(u, v);
+    update_children(u);
+    std::vector<int> vouts(out[v].begin(), out[v].end());
+    for (int w : vouts) {
+      if (!children[u].count(w)) {
+        raw_add_edge(u, w);
+        children[u].insert(w);
+        children[u].insert(children[w].begin(), children[w].end());
+      }
+    }
+    std::vector<int> uins(in[u].begin(), in[u].end());
+    for (int pa : uins) {
+      update_children(pa);
+      if (!children[pa].count(v)) {
+        raw_add_edge(pa, v);
+        children[pa].insert(v);
+        children[pa].insert(children[v].begin(), children[v].end());
+      }
+    }
+  }
+  // swap_node (:312-316)
+  void swap_node(int u, int v) {
+    std::swap(event_id[u], event_id[v]);
+    update_children_flag = true;
+    update_node_idx_flag = true;
   }
 };
 
@@ -1024,6 +1162,240 @@ static void initialize_lambda(Model& model, const MatB& obs, float max_lambda) {
 
 
 // ----------------------------------------------------------------------------------------------
+// adaptive simulated annealing (src/asa.cpp:131-594).  ONE generator (ctx.rng) drives the move proposals, the
+// compatibility heuristic, the Metropolis rule and -- through get_auxiliary_rngs -- every MCEM score, exactly as in the
+// reference.  `score_mode` 1 replaces the MCEM score by a deterministic function of the proposed poset (test seam for
+// the move generator / bookkeeping; not part of the reference).
+// ----------------------------------------------------------------------------------------------
+struct ControlSA {  // src/mcem.hpp:228-260
+  std::string outdir;
+  float acceptance_rate = 1.0f / 3, T = 50.0f, adap_rate = 0.3f;
+  int step_size = 1;
+  unsigned max_iter = 10000;
+  bool adaptive = true;
+  float compatible_fraction_factor = 0.05f;
+};
+
+static void write_poset(const Model& M, const std::string& outdir) {  // :59-70 (boost::edges order: by source vertex)
+  std::ofstream f(outdir + "poset.txt", std::ofstream::trunc);
+  for (int u = 0; u < M.p; ++u)
+    for (int v : M.out[u]) f << M.event_id[u] << "\t" << M.event_id[v] << std::endl;
+}
+
+static bool heuristic_compatibility(Model& M, const MatB& obs, double fraction_compatible, double& fraction_new,
+                                    float factor, Context& ctx) {  // :133-162
+  std::uniform_real_distribution<> rand01(0.0, 1.0);
+  const int N = obs.rows;
+  fraction_new = (double)num_compatible_observations(obs, M, N) / N;
+  if (fraction_new < fraction_compatible) {
+    double prob = std::exp((fraction_new - fraction_compatible) / factor);
+    if (prob > rand01(ctx.rng)) return true;
+  } else {
+    return true;
+  }
+  return false;
+}
+
+struct AsaStats {  // what the tests compare
+  int num_accept_total = 0, moves[4] = {0, 0, 0, 0}, n_scored = 0;
+};
+
+static double asa_score(Model& M_new, const MatB& obs, const std::vector<double>& times,
+                        const std::vector<double>& weights, unsigned L, const std::string& sampling,
+                        const ControlEM& ctl, bool times_available, unsigned thrds, Context& ctx, int score_mode,
+                        AsaStats& st) {
+  const int N = obs.rows, p = M_new.p;
+  initialize_lambda(M_new, obs, ctl.max_lambda);
+  M_new.update_epsilon((double)num_incompatible_events(obs, M_new) / ((double)N * p),
+                       std::numeric_limits<double>::epsilon());
+  st.n_scored++;
+  if (score_mode == 1)  // deterministic pseudo score (negative, never exactly 0.0 = "not computed")
+    return -1000.0 - (double)num_incompatible_events(obs, M_new) + 3.0 * (double)M_new.num_edges();
+  return MCEM_hcbn(M_new, obs, times, weights, L, sampling, ctl, times_available, thrds, ctx);
+}
+
+// propose_edge (:167-470)
+static double propose_edge(Model& M, const MatB& obs, double llhood_current, double& fraction_compatible,
+                           const std::vector<double>& times, const std::vector<double>& weights, float T,
+                           int& num_accept, float factor, unsigned L, const std::string& sampling,
+                           const ControlEM& ctl, bool times_available, MatD& ll_addRemove, MatD& ll_swap,
+                           MatD& ll_preserve, unsigned thrds, Context& ctx, int score_mode, AsaStats& st) {
+  const unsigned p = (unsigned)M.p;
+  Model M_new(M);
+  double llhood_new = 0.0, fraction_new = 0.0;
+  const unsigned num_edges = (unsigned)M.num_edges();
+  std::vector<int> idxs_pool(num_edges), cover_pool(p * p);
+  std::iota(idxs_pool.begin(), idxs_pool.end(), 0);
+  std::shuffle(idxs_pool.begin(), idxs_pool.end(), ctx.rng);
+  std::iota(cover_pool.begin(), cover_pool.end(), 0);
+  std::shuffle(cover_pool.begin(), cover_pool.end(), ctx.rng);
+  std::uniform_real_distribution<> rand01(0.0, 1.0);
+  std::discrete_distribution<int> distribution({0.5, 0.0, 0.4, 0.1});
+  const int move = distribution(ctx.rng);
+  st.moves[move]++;
+  unsigned i = 0, v1 = 0, v2 = 0;
+  auto score = [&]() {
+    return asa_score(M_new, obs, times, weights, L, sampling, ctl, times_available, thrds, ctx, score_mode, st);
+  };
+  switch (move) {
+    case 0:
+      for (i = 0; i < p * p; ++i) {
+        M_new = M;
+        v1 = (unsigned)cover_pool[i] / p;
+        v2 = (unsigned)cover_pool[i] % p;
+        if (v1 == v2) continue;
+        bool add = M_new.add_edge((int)v1, (int)v2);
+        if (add) {
+          if (M_new.cycle) continue;
+          if (!M_new.reduction_flag) continue;
+        } else {
+          M_new.remove_edge((int)v1, (int)v2);
+        }
+        if (heuristic_compatibility(M_new, obs, fraction_compatible, fraction_new, factor, ctx)) break;
+      }
+      if (ll_addRemove((int)v1, (int)v2) == 0.0) {
+        llhood_new = score();
+        ll_addRemove((int)v1, (int)v2) = llhood_new;
+      } else {
+        llhood_new = ll_addRemove((int)v1, (int)v2);
+      }
+      break;
+    case 1:
+      for (i = 0; i < num_edges; ++i) {
+        M_new = M;
+        int cnt = 0, a = -1, b = -1;
+        for (int u = 0; u < (int)p && a < 0; ++u)
+          for (int w : M_new.out[u]) {
+            if (cnt == idxs_pool[i]) {
+              a = u;
+              b = w;
+              break;
+            }
+            ++cnt;
+          }
+        M_new.remove_edge(a, b);
+        M_new.add_edge(b, a);
+        if (M_new.cycle) continue;
+        if (heuristic_compatibility(M_new, obs, fraction_compatible, fraction_new, factor, ctx)) break;
+      }
+      llhood_new = score();
+      break;
+    case 2:
+      for (i = 0; i < p * p; ++i) {
+        v1 = (unsigned)cover_pool[i] / p;
+        v2 = (unsigned)cover_pool[i] % p;
+        if (v1 == v2) continue;
+        if (M.update_children_flag) M.set_children();
+        M_new = M;
+        bool add = M_new.add_relation((int)v1, (int)v2);
+        if (add) {
+          if (M_new.cycle) continue;
+          if (!M_new.reduction_flag) continue;
+        } else {
+          M_new.remove_relation((int)v1, (int)v2);
+        }
+        if (heuristic_compatibility(M_new, obs, fraction_compatible, fraction_new, factor, ctx)) break;
+      }
+      if (ll_preserve((int)v1, (int)v2) == 0.0) {
+        llhood_new = score();
+        ll_preserve((int)v1, (int)v2) = llhood_new;
+      } else {
+        llhood_new = ll_preserve((int)v1, (int)v2);
+      }
+      break;
+    case 3:
+      for (i = 0; i < p * p; ++i) {
+        M_new = M;
+        v1 = (unsigned)cover_pool[i] / p;
+        v2 = (unsigned)cover_pool[i] % p;
+        if (v1 == v2) continue;
+        M_new.swap_node((int)v1, (int)v2);
+        if (heuristic_compatibility(M_new, obs, fraction_compatible, fraction_new, factor, ctx)) break;
+      }
+      if (ll_swap((int)v1, (int)v2) == 0.0) {
+        llhood_new = score();
+        ll_swap((int)v1, (int)v2) = ll_swap((int)v2, (int)v1) = llhood_new;
+      } else {
+        llhood_new = ll_swap((int)v1, (int)v2);
+      }
+      break;
+  }
+  auto accept = [&]() {
+    num_accept += 1;
+    st.num_accept_total += 1;
+    M = M_new;
+    fraction_compatible = fraction_new;
+    std::fill(ll_addRemove.a.begin(), ll_addRemove.a.end(), 0.0);
+    std::fill(ll_swap.a.begin(), ll_swap.a.end(), 0.0);
+    std::fill(ll_preserve.a.begin(), ll_preserve.a.end(), 0.0);
+    return llhood_new;
+  };
+  if (llhood_new > llhood_current) return accept();
+  if (T == 0.0) return llhood_current;
+  const double acceptance_prob = std::exp(-(llhood_current - llhood_new) / T);
+  if (acceptance_prob > rand01(ctx.rng)) return accept();
+  return llhood_current;
+}
+
+// simulated_annealing (:475-594)
+static double simulated_annealing(Model& poset, const MatB& obs, const std::vector<double>& times,
+                                  const std::vector<double>& weights, ControlSA& ctl_asa, unsigned L,
+                                  const std::string& sampling, const ControlEM& ctl_em, bool times_available,
+                                  unsigned thrds, Context& ctx, int score_mode, AsaStats& st) {
+  const int N = obs.rows, p = poset.p;
+  const float scaling_const = -std::log(2.0) / std::log(ctl_asa.acceptance_rate);
+  int num_accept = 0;
+  MatD ll_addRemove(p, p, 0.0), ll_swap(p, p, 0.0), ll_preserve(p, p, 0.0);
+  auto full_score = [&](Model& m, const ControlEM& c) {
+    if (score_mode == 1) return -1000.0 - (double)num_incompatible_events(obs, m) + 3.0 * (double)m.num_edges();
+    return MCEM_hcbn(m, obs, times, weights, L, sampling, c, times_available, thrds, ctx);
+  };
+  double llhood = full_score(poset, ctl_em);
+  Model poset_ML(poset);
+  double llhood_ML = llhood;
+  double fraction_compatible = (double)num_compatible_observations(obs, poset, N) / N;
+  std::ofstream f_temp(ctl_asa.outdir + "asa.txt"), f_par(ctl_asa.outdir + "params.txt");
+  f_temp << "step\t llhood\t temperature\t acceptance rate" << std::endl;
+  f_par << "step\t llhood\t epsilon\t lambdas" << std::endl;
+  auto put_lambda = [&](std::ostream& os, const Model& m) {
+    for (int j = 0; j < p; ++j) os << (j ? " " : "") << m.lambda[j];  // Eigen's default row-vector format
+  };
+  f_par << 0 << "\t" << llhood << "\t" << poset.epsilon << "\t";
+  put_lambda(f_par, poset);
+  f_par << std::endl;
+  for (unsigned iter = 1; iter < ctl_asa.max_iter; ++iter) {
+    llhood = propose_edge(poset, obs, llhood, fraction_compatible, times, weights, ctl_asa.T, num_accept,
+                          ctl_asa.compatible_fraction_factor, L, sampling, ctl_em, times_available, ll_addRemove,
+                          ll_swap, ll_preserve, thrds, ctx, score_mode, st);
+    if (llhood > llhood_ML) {
+      llhood_ML = llhood;
+      poset_ML = poset;
+      write_poset(poset, ctl_asa.outdir);
+    }
+    f_par << iter << "\t" << llhood << "\t" << poset.epsilon << "\t";
+    put_lambda(f_par, poset);
+    f_par << std::endl;
+    if (!ctl_asa.adaptive) {
+      const float rate = (float)num_accept / (iter + 1);
+      ctl_asa.T *= 1 - 1.0 / p;
+      f_temp << iter << "\t" << llhood << "\t" << ctl_asa.T << "\t" << rate << std::endl;
+    } else if (!(iter % ctl_asa.step_size)) {
+      const float rate = (float)num_accept / ctl_asa.step_size;
+      ctl_asa.T *= std::exp((0.5 - std::pow(rate, scaling_const)) * ctl_asa.adap_rate);
+      num_accept = 0;
+      f_temp << iter << "\t" << llhood << "\t" << ctl_asa.T << "\t" << rate << std::endl;
+    }
+  }
+  ControlEM last = ctl_em;
+  last.max_iter = ctl_em.max_iter * 2;
+  last.update_step_size = ctl_em.update_step_size * 2;
+  last.neighborhood_dist = 1;  // ControlEM's default: the 4-argument constructor is used at :583-585
+  poset = poset_ML;
+  llhood = full_score(poset, last);
+  return llhood;
+}
+
+// ----------------------------------------------------------------------------------------------
 // legacy OT-CBN MCEM (src/mcem.cpp:30-210).  The reference draws from R's global RNG (runif / rexp sugar);
 // here the same formulas are driven by StdRng -- the stream differs, the distribution does not.
 // ----------------------------------------------------------------------------------------------
@@ -1610,6 +1982,52 @@ int ref_initialize_lambda(const int* obs, int N, const int* poset, int p, float 
 }
 
 // draw `n` exponentials exactly as rexp<StdRng> would from a fresh Context(seed) (RNG pinning test)
+// _adaptive_simulated_annealing (src/asa.cpp:596-665); stats_out[6] = {accepted, move0..move3 counts, scored}
+int ref_adaptive_simulated_annealing(const int* poset, const int* obs, const double* times, float lambda_s,
+                                     const double* weights, unsigned L, const char* sampling, unsigned max_iter_EM,
+                                     unsigned update_step_size, double tol, float max_lambda, float T0, float adap_rate,
+                                     float acceptance_rate, int step_size, unsigned max_iter_ASA,
+                                     unsigned neighborhood_dist, int adaptive, const char* outdir, int times_available,
+                                     int thrds, int verbose, int seed, int N, int p, int score_mode, double* lambda_out,
+                                     double* eps_out, int* poset_out, double* llhood_out, int* stats_out) {
+  REF_TRY
+  Model M = build_model(poset, p, lambda_s);
+  MatB O = obs_from_int(obs, N, p);
+  initialize_lambda(M, O, max_lambda);
+  M.update_epsilon((double)num_incompatible_events(O, M) / ((double)N * p), std::numeric_limits<double>::epsilon());
+  ControlEM cem;
+  cem.max_iter = max_iter_EM;
+  cem.update_step_size = update_step_size;
+  cem.tol = tol;
+  cem.max_lambda = max_lambda;
+  cem.neighborhood_dist = neighborhood_dist;
+  ControlSA csa;
+  csa.outdir = outdir;
+  csa.acceptance_rate = acceptance_rate;
+  csa.T = T0;
+  csa.adap_rate = adap_rate;
+  csa.step_size = step_size;
+  csa.max_iter = max_iter_ASA;
+  csa.adaptive = adaptive != 0;
+  Context ctx(seed, verbose != 0);
+  AsaStats st;
+  double ll = simulated_annealing(M, O, std::vector<double>(times, times + N), std::vector<double>(weights, weights + N),
+                                  csa, L, sampling, cem, times_available != 0, (unsigned)thrds, ctx, score_mode, st);
+  std::copy(M.lambda.begin(), M.lambda.end(), lambda_out);
+  *eps_out = M.epsilon;
+  *llhood_out = ll;
+  // adjacency_list2mat (src/model_impl.cpp:355-363): entry (event(u), event(v)) = 1, column-major p x p
+  for (int i = 0; i < p * p; ++i) poset_out[i] = 0;
+  for (int u = 0; u < p; ++u)
+    for (int v : M.out[u]) poset_out[(size_t)M.event_id[v] * p + M.event_id[u]] = 1;
+  if (stats_out) {
+    stats_out[0] = st.num_accept_total;
+    for (int k = 0; k < 4; ++k) stats_out[1 + k] = st.moves[k];
+    stats_out[5] = st.n_scored;
+  }
+  REF_CATCH
+}
+
 // Known-answer test of the third-party generator the reference is built on: the C++ standard ([rand.predef]) fixes the
 // 10000th output of a default-constructed std::mt19937 to 4123659995.
 unsigned ref_mt19937_kat() {

@@ -358,3 +358,30 @@ def MCEM_otcbn(ilambda, poset, obs, times=None, max_iter=100, alpha=0.2, weights
                               int(nrOfSamples), C.c_float(max_lambda), C.c_float(lambda_s), int(times is not None),
                               int(seed), N, p, _p(out_l), C.byref(out_ll)))
     return dict(lambda_=out_l, llhood=out_ll.value)
+
+
+def adaptive_simulated_annealing(poset, obs, L, times=None, lambda_s=1.0, weights=None, sampling="forward", max_iter=100,
+                                 update_step_size=20, tol=0.001, max_lambda=1e6, T0=50.0, adap_rate=0.3,
+                                 acceptance_rate=None, step_size=None, max_iter_asa=10000, neighborhood_dist=1,
+                                 adaptive=True, outdir="", thrds=1, verbose=False, seed=1, score_mode=0):
+    """`_adaptive_simulated_annealing` (src/asa.cpp:596-665) with the defaults of the R wrapper
+    (R/adaptive_simulated_annealing.R:62-113).  score_mode=1: deterministic pseudo score (test seam)."""
+    obs, poset = _i32(obs), _i32(poset)
+    N, p = obs.shape
+    t = np.zeros(N) if times is None else _f64(times)
+    w = np.ones(N) if weights is None else _f64(weights)
+    if acceptance_rate is None:
+        acceptance_rate = 1.0 / p
+    if step_size is None:
+        step_size = max(1, max_iter_asa // 10)
+    lam, eps, ll = np.zeros(p), C.c_double(0), C.c_double(0)
+    out = np.zeros((p, p), np.int32, order="F")
+    stats = np.zeros(6, np.int32)
+    _chk(lib().ref_adaptive_simulated_annealing(
+        _p(poset), _p(obs), _p(t), C.c_float(lambda_s), _p(w), C.c_uint(L), sampling.encode(), C.c_uint(max_iter),
+        C.c_uint(update_step_size), C.c_double(tol), C.c_float(max_lambda), C.c_float(T0), C.c_float(adap_rate),
+        C.c_float(acceptance_rate), int(step_size), C.c_uint(max_iter_asa), C.c_uint(neighborhood_dist), int(adaptive),
+        outdir.encode(), int(times is not None), int(thrds), int(verbose), int(seed), N, p, int(score_mode), _p(lam),
+        C.byref(eps), _p(out), C.byref(ll), _p(stats)))
+    return dict(lambda_=lam, eps=eps.value, poset=out, llhood=ll.value, n_accept=int(stats[0]),
+                moves=stats[1:5].tolist(), n_scored=int(stats[5]))
