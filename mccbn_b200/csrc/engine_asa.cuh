@@ -285,10 +285,14 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
   f_par << std::endl;
 
   // 3. annealing loop: iter = 1 .. max_iter - 1 (:530)
+  // batch > 0: fixed speculative batch size; batch < 0: automatic with upper bound -batch -- start at 2, double after a
+  // batch without an accepted move, fall back to (position of the accepted move + 1) after an acceptance
+  const unsigned batch_cap = (unsigned)std::max(1, batch < 0 ? -batch : batch);
+  unsigned batch_now = batch < 0 ? std::min(2u, batch_cap) : batch_cap;
   unsigned iter = 1;
   while (iter < ctl_asa.max_iter) {
     // 3.0 speculative batch: proposals for steps iter, iter+1, ... assuming every earlier one is rejected
-    const unsigned B = std::min<unsigned>((unsigned)std::max(1, batch), ctl_asa.max_iter - iter);
+    const unsigned B = std::min<unsigned>(batch_now, ctl_asa.max_iter - iter);
     std::vector<Proposal> props;
     props.reserve(B);
     std::vector<Candidate*> to_score;
@@ -356,6 +360,7 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
         std::fill(memo_pres.begin(), memo_pres.end(), 0.0);
         rng_prop = pr.rng_after;  // discard the speculation beyond this step
         accepted_any = true;
+        if (batch < 0) batch_now = std::min(batch_cap, b + 1u);
       }
       if (llhood > llhood_ML) {  // :541-545
         llhood_ML = llhood;
@@ -377,6 +382,7 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
         f_temp << iter << "\t" << llhood << "\t" << ctl_asa.T << "\t" << rate << std::endl;
       }
     }
+    if (batch < 0 && !accepted_any) batch_now = std::min(batch_cap, batch_now * 2u);
   }
   // 4. final fit of the ML poset with doubled EM budget; neighborhood_dist falls back to its default 1 (:583-585)
   EmControl last = ctl_em;

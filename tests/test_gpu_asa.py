@@ -13,7 +13,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _run(tmp, batch, seed=7, **kw):
-    os.environ["MCCBN_ASA_BATCH"] = str(batch)
+    if batch is None:  # automatic batch size (work-based cap, adapted to the acceptance pattern)
+        os.environ.pop("MCCBN_ASA_BATCH", None)
+    else:
+        os.environ["MCCBN_ASA_BATCH"] = str(batch)
     out = os.path.join(tmp, f"b{batch}_")
     c = synth.make_config(8, 400, eps=0.05, seed=5, density=0.3)
     start = np.zeros((8, 8), np.int32)  # empty poset as the initial guess
@@ -24,11 +27,12 @@ def _run(tmp, batch, seed=7, **kw):
 
 def test_asa_batched_equals_sequential(tmp_path):
     c, r1, o1 = _run(str(tmp_path), 1)
-    _, r8, o8 = _run(str(tmp_path), 8)
-    assert np.array_equal(r1["poset"], r8["poset"])
-    assert np.array_equal(r1["lambda_"], r8["lambda_"]) and r1["eps"] == r8["eps"] and r1["llhood"] == r8["llhood"]
-    for name in ("asa.txt", "params.txt", "poset.txt"):
-        assert open(o1 + name).read() == open(o8 + name).read(), name
+    for batch in (8, None):
+        _, r8, o8 = _run(str(tmp_path), batch)
+        assert np.array_equal(r1["poset"], r8["poset"])
+        assert np.array_equal(r1["lambda_"], r8["lambda_"]) and r1["eps"] == r8["eps"] and r1["llhood"] == r8["llhood"]
+        for name in ("asa.txt", "params.txt", "poset.txt"):
+            assert open(o1 + name).read() == open(o8 + name).read(), name
 
 
 def test_asa_outputs_and_search(tmp_path):
