@@ -149,6 +149,20 @@ int mccbn_MCEM(mccbn_ctx* ctx, const double* ilambda, const int* poset, const in
 
 /* ---- indexing seams (bit-exact tier) --------------------------------------------------------------------- */
 
+/* ---- forward simulators of the generative model (test / benchmark-data seams of the reference) -------------------
+ * `_sample_genotypes` (src/mcem_hcbn.cpp:1012-1049): N draws of (X, Z, T_s); samples / Tdiff are N x p column-major,
+ * T_sampling is read when sampling_times_available and written otherwise.
+ * `_sample_times` (:1052-1083): mutation_times = accumulated event times T, Tdiff = waiting times Z.
+ * `_generate_genotypes` (:1086-1120): X = [T_events_sum <= T_s] for given event times. */
+int mccbn_sample_genotypes(mccbn_ctx* ctx, unsigned N, const int* poset, const double* lambda, double* T_sampling,
+                           float lambda_s, int sampling_times_available, int seed, int p, int* samples, double* Tdiff,
+                           char* err, size_t errlen);
+int mccbn_sample_times(mccbn_ctx* ctx, unsigned N, const int* poset, const double* lambda, int seed, int p,
+                       double* mutation_times, double* Tdiff, char* err, size_t errlen);
+int mccbn_generate_genotypes(mccbn_ctx* ctx, const double* T_events_sum, const int* poset, double* T_sampling,
+                             float lambda_s, int sampling_times_available, int seed, int N, int p, int* samples,
+                             char* err, size_t errlen);
+
 /* Stage 1, poset flattening (adjacency_mat2list + has_cycles + topological_sort + get_direct_predecessors,
  * src/model_impl.cpp:343-352,40-87): topo[p] = event ids in a valid topological order, parent_mask[p] = bitmask of
  * direct parents by event id.  Returns MCCBN_ERR_NOT_ACYCLIC for a cyclic poset.  Host-only (no device needed). */

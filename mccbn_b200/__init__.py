@@ -9,6 +9,7 @@ from .api import (Context, Problem, MCEM_hcbn, adaptive_simulated_annealing, com
                   conditional_from_uniforms, device_count, estep_forward_from_times, estimate_mutation_rates,
                   flatten_poset,
                   forward_from_times, importance_weight, initialize_lambda, neighbors, nccl_unique_id,
-                  obs_loglikelihood, poset_edit, set_jit, jit_compile_forward)
+                  obs_loglikelihood, poset_edit, set_jit, jit_compile_forward, sample_genotypes, sample_times,
+                  generate_genotypes)
 
 __version__ = "0.1.0"

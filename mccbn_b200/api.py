@@ -356,6 +356,46 @@ def jit_compile_forward(poset, times_given=False):
     return dict(cubin_bytes=n.value, ms=ms.value, log=log.value.decode(), source=src.value.decode())
 
 
+def sample_genotypes(N, poset, lambda_, lambda_s=1.0, times=None, seed=1, ctx=None):
+    """`_sample_genotypes` (src/mcem_hcbn.cpp:1012-1049): N draws from the generative model on the device.
+    Returns dict(samples N x p int32, Tdiff N x p, sampling_time N)."""
+    poset, lam = i32(poset), f64(lambda_)
+    p = poset.shape[0]
+    ts = np.zeros(N) if times is None else f64(times).copy()
+    X = np.zeros((N, p), np.int32, order="F")
+    Z = np.zeros((N, p), order="F")
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_sample_genotypes(_ctx(ctx), C.c_uint(int(N)), ptr(poset), ptr(lam), ptr(ts),
+                                              C.c_float(lambda_s), int(times is not None), int(seed), p, ptr(X), ptr(Z),
+                                              *e.args))
+    return dict(samples=X, Tdiff=Z, sampling_time=ts)
+
+
+def sample_times(N, poset, lambda_, seed=1, ctx=None):
+    """`_sample_times` (src/mcem_hcbn.cpp:1052-1083): returns dict(mutation_times N x p, Tdiff N x p)."""
+    poset, lam = i32(poset), f64(lambda_)
+    p = poset.shape[0]
+    T = np.zeros((N, p), order="F")
+    Z = np.zeros((N, p), order="F")
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_sample_times(_ctx(ctx), C.c_uint(int(N)), ptr(poset), ptr(lam), int(seed), p, ptr(T), ptr(Z),
+                                          *e.args))
+    return dict(mutation_times=T, Tdiff=Z)
+
+
+def generate_genotypes(T_events_sum, poset, times=None, lambda_s=1.0, seed=1, ctx=None):
+    """`_generate_genotypes` (src/mcem_hcbn.cpp:1086-1120): returns dict(samples N x p int32, sampling_time N)."""
+    T = f64(T_events_sum)
+    poset = i32(poset)
+    N, p = T.shape
+    ts = np.zeros(N) if times is None else f64(times).copy()
+    X = np.zeros((N, p), np.int32, order="F")
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_generate_genotypes(_ctx(ctx), ptr(T), ptr(poset), ptr(ts), C.c_float(lambda_s),
+                                                int(times is not None), int(seed), N, p, ptr(X), *e.args))
+    return dict(samples=X, sampling_time=ts)
+
+
 POSET_OPS = dict(add_edge=0, remove_edge=1, add_relation=2, remove_relation=3, transitive_reduction=4, swap_node=5)
 
 

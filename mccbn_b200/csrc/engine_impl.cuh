@@ -812,6 +812,118 @@ int mccbn_importance_weight_genotype(mccbn_ctx* c, const int* genotype, unsigned
   MCCBN_CATCH
 }
 
+// ---- forward simulators (src/mcem_hcbn.cpp:1012-1120): the generative model on the device -----------------------
+// One sample per thread through the fp64 forward sampler (53-bit uniforms): Z ~ Exp(lambda), T_s ~ Exp(lambda_s) unless
+// given, T_j = Z_j + max parents, X_j = [T_j <= T_s].  All outputs optional.
+static void simulate_forward(mccbn_ctx* c, unsigned N, const int* poset, const double* lambda, int p, float lambda_s,
+                             int seed, double* T_sampling /* out */, int* samples, double* Tdiff, double* T_sum) {
+  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox samplers support p <= 32");
+  if (N == 0) return;
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  int zero_obs[64] = {0};
+  double zero_t = 0.0;
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = 1;
+  pb.p = p;
+  pb.upload(zero_obs, &zero_t, nullptr);
+  pb.set_model(0, f, lambda, 0.5, lambda_s, 3.0e38f);
+  cudaStream_t s = c->stream;
+  DevBuf<double> dZ, dT, dTs;
+  DevBuf<int> dD;
+  DevBuf<uint32_t> dX;
+  FwdDumpArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.model = pb.models.ptr;
+  a.Z_out = dZ.ensure((size_t)N * p);
+  a.T_out = T_sum ? dT.ensure((size_t)N * p) : nullptr;
+  a.dist_out = dD.ensure(N);
+  a.X_out = dX.ensure(N);
+  a.Ts_out = dTs.ensure(N);
+  a.L = (int)N;
+  const PhiloxKey key = make_key((uint32_t)seed, 0u, 7u);
+  a.key0 = key.k0;
+  a.key1 = key.k1;
+  const int grid = (int)std::min<unsigned>((N + kFwdBlock - 1) / kFwdBlock, 4096u);
+  const PosetProg pg = build_prog(f, 32, 8);
+  constexpr size_t sm = fwd_smem_bytes<double, 32>();
+  optin_smem(forward_dump_kernel<double, 32, false>, sm);
+  forward_dump_kernel<double, 32, false><<<grid, kFwdBlock, sm, s>>>(a, pg);
+  c->launches++;
+  MCCBN_CUDA(cudaGetLastError());
+  std::vector<uint32_t> hx(N);
+  std::vector<double> hts(N), hT;
+  MCCBN_CUDA(cudaMemcpyAsync(hx.data(), dX.ptr, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaMemcpyAsync(hts.data(), dTs.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, dZ.ptr, sizeof(double) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+  if (T_sum) MCCBN_CUDA(cudaMemcpyAsync(T_sum, dT.ptr, sizeof(double) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  if (T_sampling) std::copy(hts.begin(), hts.end(), T_sampling);
+  if (samples) {
+    for (unsigned i = 0; i < N; ++i)
+      for (int j = 0; j < p; ++j) samples[(size_t)j * N + i] = (hx[i] >> j) & 1u;
+  }
+}
+
+int mccbn_sample_genotypes(mccbn_ctx* c, unsigned N, const int* poset, const double* lambda, double* T_sampling,
+                           float lambda_s, int sampling_times_available, int seed, int p, int* samples, double* Tdiff,
+                           char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (sampling_times_available) {
+    // X_j = [T_j <= t_i] with the caller's per-sample times: simulate the event times, compare on the host
+    if (!T_sampling) throw Error(MCCBN_ERR_ARG, "sampling times expected");
+    std::vector<double> T((size_t)N * p);
+    simulate_forward(c, N, poset, lambda, p, lambda_s, seed, nullptr, nullptr, Tdiff, T.data());
+    if (samples)
+      for (unsigned i = 0; i < N; ++i)
+        for (int j = 0; j < p; ++j) samples[(size_t)j * N + i] = T[(size_t)j * N + i] <= T_sampling[i] ? 1 : 0;
+  } else {
+    simulate_forward(c, N, poset, lambda, p, lambda_s, seed, T_sampling, samples, Tdiff, nullptr);
+  }
+  MCCBN_CATCH
+}
+
+int mccbn_sample_times(mccbn_ctx* c, unsigned N, const int* poset, const double* lambda, int seed, int p,
+                       double* mutation_times, double* Tdiff, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  simulate_forward(c, N, poset, lambda, p, 1.0f, seed, nullptr, nullptr, Tdiff, mutation_times);
+  MCCBN_CATCH
+}
+
+int mccbn_generate_genotypes(mccbn_ctx* c, const double* T_events_sum, const int* poset, double* T_sampling,
+                             float lambda_s, int sampling_times_available, int seed, int N, int p, int* samples,
+                             char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);  // the reference validates the poset although the comparison does not use it
+  if (N <= 0) return MCCBN_OK;
+  cudaStream_t s = c->stream;
+  DevBuf<double> dT, dTs;
+  DevBuf<int> dS;
+  dT.ensure((size_t)N * p);
+  dTs.ensure(N);
+  dS.ensure((size_t)N * p);
+  MCCBN_CUDA(cudaMemcpyAsync(dT.ptr, T_events_sum, sizeof(double) * (size_t)N * p, cudaMemcpyHostToDevice, s));
+  if (sampling_times_available)
+    MCCBN_CUDA(cudaMemcpyAsync(dTs.ptr, T_sampling, sizeof(double) * N, cudaMemcpyHostToDevice, s));
+  const PhiloxKey key = make_key((uint32_t)seed, 0u, 8u);
+  generate_genotypes_kernel<<<std::min(1024, (N + 255) / 256), 256, 0, s>>>(dT.ptr, dTs.ptr, dS.ptr, N, p, (double)lambda_s,
+                                                                          sampling_times_available, key.k0, key.k1);
+  c->launches++;
+  MCCBN_CUDA(cudaGetLastError());
+  if (samples) MCCBN_CUDA(cudaMemcpyAsync(samples, dS.ptr, sizeof(int) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+  if (T_sampling && !sampling_times_available)
+    MCCBN_CUDA(cudaMemcpyAsync(T_sampling, dTs.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  MCCBN_CATCH
+}
+
 // ---- indexing seams ---------------------------------------------------------------------------------------------
 int mccbn_flatten_poset(const int* poset, int p, int* topo, uint64_t* parent_mask, char* err, size_t errlen) {
   MCCBN_TRY

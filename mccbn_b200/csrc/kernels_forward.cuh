@@ -394,6 +394,7 @@ struct FwdDumpArgs {
   double time;
   const DevModel* model;
   double* Z_out;    // L x p column-major by EVENT id
+  double* T_out;    // L x p event times (sample_times, src/mcem_hcbn.cpp:184-213), or nullptr
   int* dist_out;    // L
   uint32_t* X_out;  // L, event-id bit order (p <= 32)
   double* Ts_out;   // L
@@ -430,10 +431,29 @@ __global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpAr
     for (int k = 0; k < PMAX; ++k)
       if (k < p) {
         a.Z_out[(size_t)pg.ev[k] * a.L + l] = (double)s_Z[threadIdx.x * ZS::kStride + k] * (double)scale(k);
+        if (a.T_out) a.T_out[(size_t)pg.ev[k] * a.L + l] = (double)s_T[k * kFwdBlock + threadIdx.x];
         xe |= ((X >> k) & 1u) << pg.ev[k];
       }
     a.X_out[l] = xe;
     a.Ts_out[l] = (double)Ts;
+  }
+}
+
+// generate_genotypes (src/mcem_hcbn.cpp:215-236): X_kj = [T_sum(k, j) <= T_s(k)]; T_s ~ Exp(lambda_s) unless given.
+// One thread per row; T_sum is N x p column-major by event id, the output an N x p int matrix.
+__global__ void generate_genotypes_kernel(const double* __restrict__ T_sum, double* __restrict__ T_sampling,
+                                          int* __restrict__ samples, int N, int p, double lambda_s, int times_given,
+                                          uint32_t key0, uint32_t key1) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    double ts;
+    if (times_given) {
+      ts = T_sampling[i];
+    } else {
+      const uint4 r = philox4x32_10((uint32_t)i, 0u, 0u, 0u, key0, key1);
+      ts = -log(u01_open0_d(r.x, r.y)) / lambda_s;
+      T_sampling[i] = ts;
+    }
+    for (int j = 0; j < p; ++j) samples[(size_t)j * N + i] = T_sum[(size_t)j * N + i] <= ts ? 1 : 0;
   }
 }
 
