@@ -163,6 +163,24 @@ int mccbn_generate_genotypes(mccbn_ctx* ctx, const double* T_events_sum, const i
                              float lambda_s, int sampling_times_available, int seed, int N, int p, int* samples,
                              char* err, size_t errlen);
 
+/* ---- the reference's remaining small export seams ------------------------------------------------------------
+ * `_scale_path_to_mutation` src/add_remove.cpp:218-242, `_cbn_density_log` :323-335, `_complete_log_likelihood`
+ * src/mcem_hcbn.cpp:738-760 (host arithmetic), `_draw_sample` src/add_remove.cpp:244-284 (reference generator: bit-exact
+ * for a seed), `_coin_tossing` src/backward_sampling.cpp:105-123 (device, Philox coins), `_generate_mutation_times`
+ * src/add_remove.cpp:286-321 (reference generator and draw order, fp64 arithmetic on the device). */
+int mccbn_scale_path_to_mutation(const int* poset, int p, const double* lambda, double* out, char* err, size_t errlen);
+int mccbn_cbn_density_log(const double* time, int N, int p, const double* lambda, double* out, char* err,
+                          size_t errlen);
+int mccbn_complete_log_likelihood(const double* lambda, int p, double eps, const double* Tdiff, int N,
+                                  const double* dist, const double* weights, double* out, char* err, size_t errlen);
+int mccbn_draw_sample(const int* genotype, const int* poset, int p, unsigned move, const double* q_prob, int seed,
+                      int* sample, double* q_choice, char* err, size_t errlen);
+int mccbn_coin_tossing(mccbn_ctx* ctx, double eps, unsigned L, const int* genotype, int p, int seed, int* out, char* err,
+                       size_t errlen);
+int mccbn_generate_mutation_times(mccbn_ctx* ctx, const int* obs, const int* poset, const double* lambda, double* time,
+                                  float lambda_s, int sampling_times_available, int seed, int N, int p, double* Tdiff,
+                                  double* proposal_density, char* err, size_t errlen);
+
 /* Stage 1, poset flattening (adjacency_mat2list + has_cycles + topological_sort + get_direct_predecessors,
  * src/model_impl.cpp:343-352,40-87): topo[p] = event ids in a valid topological order, parent_mask[p] = bitmask of
  * direct parents by event id.  Returns MCCBN_ERR_NOT_ACYCLIC for a cyclic poset.  Host-only (no device needed). */

@@ -396,6 +396,72 @@ def generate_genotypes(T_events_sum, poset, times=None, lambda_s=1.0, seed=1, ct
     return dict(samples=X, sampling_time=ts)
 
 
+def scale_path_to_mutation(poset, lambda_):
+    """`_scale_path_to_mutation` (src/add_remove.cpp:218-242)."""
+    poset, lam = i32(poset), f64(lambda_)
+    out = np.zeros(poset.shape[0])
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_scale_path_to_mutation(ptr(poset), poset.shape[0], ptr(lam), ptr(out), *e.args))
+    return out
+
+
+def cbn_density_log(time, lambda_):
+    """`_cbn_density_log` (src/add_remove.cpp:323-335)."""
+    t, lam = f64(time), f64(lambda_)
+    N, p = t.shape
+    out = np.zeros(N)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_cbn_density_log(ptr(t), N, p, ptr(lam), ptr(out), *e.args))
+    return out
+
+
+def complete_log_likelihood(lambda_, eps, Tdiff, dist, weights):
+    """`_complete_log_likelihood` (src/mcem_hcbn.cpp:738-760)."""
+    lam, T, d, w = f64(lambda_), f64(Tdiff), f64(dist), f64(weights)
+    N, p = T.shape
+    out = C.c_double(0)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_complete_log_likelihood(ptr(lam), p, C.c_double(eps), ptr(T), N, ptr(d), ptr(w),
+                                                     C.byref(out), *e.args))
+    return out.value
+
+
+def draw_sample(genotype, poset, move, q_prob, seed=1):
+    """`_draw_sample` (src/add_remove.cpp:244-284): returns (sample, q_choice)."""
+    g, poset, q = i32(genotype), i32(poset), f64(q_prob)
+    p = poset.shape[0]
+    out = np.zeros(p, np.int32)
+    qc = C.c_double(0)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_draw_sample(ptr(g), ptr(poset), p, C.c_uint(int(move)), ptr(q), int(seed), ptr(out),
+                                         C.byref(qc), *e.args))
+    return out, qc.value
+
+
+def coin_tossing(eps, L, genotype, seed=1, ctx=None):
+    """`_coin_tossing` (src/backward_sampling.cpp:105-123): L x p noisy copies of `genotype`."""
+    g = i32(genotype).ravel()
+    out = np.zeros((int(L), g.size), np.int32, order="F")
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_coin_tossing(_ctx(ctx), C.c_double(eps), C.c_uint(int(L)), ptr(g), g.size, int(seed),
+                                          ptr(out), *e.args))
+    return out
+
+
+def generate_mutation_times(obs, poset, lambda_, times=None, lambda_s=1.0, seed=1, ctx=None):
+    """`_generate_mutation_times` (src/add_remove.cpp:286-321): returns dict(Tdiff, proposal_density, sampling_time)."""
+    obs, poset, lam = i32(obs), i32(poset), f64(lambda_)
+    N, p = obs.shape
+    ts = np.zeros(N) if times is None else f64(times).copy()
+    T = np.zeros((N, p), order="F")
+    dens = np.zeros(N)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_generate_mutation_times(_ctx(ctx), ptr(obs), ptr(poset), ptr(lam), ptr(ts),
+                                                     C.c_float(lambda_s), int(times is not None), int(seed), N, p,
+                                                     ptr(T), ptr(dens), *e.args))
+    return dict(Tdiff=T, proposal_density=dens, sampling_time=ts)
+
+
 POSET_OPS = dict(add_edge=0, remove_edge=1, add_relation=2, remove_relation=3, transitive_reduction=4, swap_node=5)
 
 

@@ -434,6 +434,7 @@ static void lambda_from_counts(const FlatPoset& f, const unsigned long long* cnt
 }
 }  // namespace mccbn
 
+#include <functional>
 #include "engine_asa.cuh"
 
 // ================================================================================================================
@@ -1146,6 +1147,221 @@ int mccbn_conditional_from_uniforms(mccbn_ctx* c, const int* X, int L, const int
   if (log_pz) MCCBN_CUDA(cudaMemcpyAsync(log_pz, dpz.ptr, sizeof(double) * L, cudaMemcpyDeviceToHost, s));
   if (incompatible) MCCBN_CUDA(cudaMemcpyAsync(incompatible, dInc.ptr, sizeof(int) * L, cudaMemcpyDeviceToHost, s));
   MCCBN_CUDA(cudaStreamSynchronize(s));
+  MCCBN_CATCH
+}
+
+// ---- the reference's remaining small export seams ----------------------------------------------------
+// Boost's topological_sort (DFS from vertex 0.., out-edges by ascending target, post-order) as the reference uses it
+// (src/model_impl.cpp:51-69): returns the vertices in TOPOLOGICAL order (= topo_path.rbegin() .. rend()).
+static std::vector<int> boost_like_topological_order(const int* poset, int p) {
+  std::vector<std::vector<int>> out(p);
+  for (int i = 0; i < p; ++i)
+    for (int j = 0; j < p; ++j)
+      if (poset[(size_t)j * p + i] == 1) out[i].push_back(j);
+  std::vector<int> post;
+  std::vector<char> seen(p, 0);
+  std::function<void(int)> dfs = [&](int v) {
+    seen[v] = 1;
+    for (int w : out[v])
+      if (!seen[w]) dfs(w);
+    post.push_back(v);
+  };
+  for (int v = 0; v < p; ++v)
+    if (!seen[v]) dfs(v);
+  std::reverse(post.begin(), post.end());
+  return post;
+}
+
+// `_scale_path_to_mutation` (src/add_remove.cpp:17-37, :218-242): host arithmetic, O(p + |E|)
+int mccbn_scale_path_to_mutation(const int* poset, int p, const double* lambda, double* out, char* err,
+                                 size_t errlen) {
+  MCCBN_TRY
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  std::vector<double> sc(p, 0.0);  // by topological position
+  for (int k = 0; k < p; ++k) {
+    double mx = -1.0;
+    for (uint64_t m = f.parent_pos[k]; m; m &= m - 1) mx = std::max(mx, sc[ctz64(m)]);
+    sc[k] = 1.0 / lambda[f.topo[k]] + (mx > -1.0 ? mx : 0.0);
+    out[f.topo[k]] = sc[k];
+  }
+  MCCBN_CATCH
+}
+
+// `_cbn_density_log` (src/add_remove.cpp:206-216, :323-335): log-density of the waiting times, per row
+int mccbn_cbn_density_log(const double* time, int N, int p, const double* lambda, double* out, char* err,
+                          size_t errlen) {
+  MCCBN_TRY
+  double sumlog = 0.0;
+  for (int j = 0; j < p; ++j) sumlog += std::log(lambda[j]);
+  for (int i = 0; i < N; ++i) {
+    double dot = 0.0;
+    for (int j = 0; j < p; ++j) dot += time[(size_t)j * N + i] * lambda[j];
+    out[i] = sumlog - dot;
+  }
+  MCCBN_CATCH
+}
+
+// `_complete_log_likelihood` (src/mcem_hcbn.cpp:102-136, :738-760): weighted complete-data log-likelihood
+int mccbn_complete_log_likelihood(const double* lambda, int p, double eps, const double* Tdiff, int N,
+                                  const double* dist, const double* weights, double* out, char* err, size_t errlen) {
+  MCCBN_TRY
+  double wsum = 0.0, sumlog = 0.0;
+  for (int i = 0; i < N; ++i) wsum += weights[i];
+  for (int j = 0; j < p; ++j) sumlog += std::log(lambda[j]);
+  double llhood = wsum * sumlog;
+  for (int j = 0; j < p; ++j) {
+    double s = 0.0;
+    for (int i = 0; i < N; ++i) s += weights[i] * Tdiff[(size_t)j * N + i];
+    llhood -= lambda[j] * s;
+  }
+  double wd = 0.0, wpd = 0.0;
+  for (int i = 0; i < N; ++i) {
+    wd += weights[i] * dist[i];
+    wpd += weights[i] * ((double)p - dist[i]);
+  }
+  if (eps == 0.0) {  // only observations at a non-zero distance contribute (:120-126)
+    for (int i = 0; i < N; ++i)
+      if (dist[i] != 0.0)
+        llhood += std::log(eps + DBL_EPSILON) * weights[i] * dist[i] +
+                  std::log(1 - eps - DBL_EPSILON) * weights[i] * ((double)p - dist[i]);
+  } else {
+    llhood += std::log(eps) * wd + std::log1p(-eps) * wpd;
+  }
+  *out = llhood;
+  MCCBN_CATCH
+}
+
+// `_draw_sample` (src/add_remove.cpp:109-141, :244-284): one add / remove / stand-still proposal.  The reference's
+// own generator (mt19937 through the ranlux24 -> seed_seq chain, std::discrete_distribution) is used, so the seam is
+// bit-identical to the reference for a given seed.
+int mccbn_draw_sample(const int* genotype, const int* poset, int p, unsigned move, const double* q_prob, int seed,
+                      int* sample, double* q_choice, char* err, size_t errlen) {
+  MCCBN_TRY
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  uint64_t g = 0;
+  for (int j = 0; j < p; ++j)
+    if (genotype[j]) g |= 1ull << j;
+  // closures by event id
+  std::vector<uint64_t> anc(p, 0), desc(p, 0), par(p, 0);
+  for (int i = 0; i < p; ++i)
+    for (int j = 0; j < p; ++j)
+      if (poset[(size_t)j * p + i] == 1) par[j] |= 1ull << i;
+  for (int k = 0; k < p; ++k) {
+    const int v = f.topo[k];
+    anc[v] = 1ull << v;
+    for (uint64_t m = par[v]; m; m &= m - 1) anc[v] |= anc[ctz64(m)];
+  }
+  for (int k = p - 1; k >= 0; --k) {
+    const int v = f.topo[k];
+    desc[v] |= 1ull << v;
+    for (uint64_t m = par[v]; m; m &= m - 1) desc[ctz64(m)] |= desc[v];
+  }
+  bool compatible = true;
+  uint64_t up = 0, down = 0;
+  for (int v = 0; v < p; ++v)
+    if ((g >> v) & 1ull) {
+      up |= anc[v];
+      if (par[v] & ~g) compatible = false;
+      if ((anc[v] & ~g) == 0) down |= 1ull << v;
+    }
+  std::vector<double> rw(p), aw(p);
+  double rs = 0.0, as = 0.0;
+  for (int j = 0; j < p; ++j) {
+    rw[j] = ((g >> j) & 1ull) ? q_prob[j] : 0.0;
+    aw[j] = ((g >> j) & 1ull) ? 0.0 : 1.0 / q_prob[j];
+    rs += rw[j];
+    as += aw[j];
+  }
+  std::mt19937 rng = make_std_rng((unsigned)seed);
+  std::discrete_distribution<int> Dr(rw.begin(), rw.end()), Da(aw.begin(), aw.end());
+  const int idx_remove = Dr(rng);
+  const int idx_add = Da(rng);
+  uint64_t x = g;
+  double q = 1.0;
+  if (move == 0) {
+    q = aw[idx_add] / as;
+    x = (compatible ? g : up) | anc[idx_add];
+  } else if (move == 1) {
+    q = rw[idx_remove] / rs;
+    x = (compatible ? g : down) & ~desc[idx_remove];
+  }
+  for (int j = 0; j < p; ++j) sample[j] = (int)((x >> j) & 1ull);
+  *q_choice = q;
+  MCCBN_CATCH
+}
+}  // extern "C"
+
+namespace mccbn {
+// coin_tossing (src/backward_sampling.cpp:64-77) with the E-step's own Philox coins: row l flips bit j with probability eps
+__global__ void coin_tossing_kernel(const int* __restrict__ genotype, int* __restrict__ out, int L, int p, uint32_t thr,
+                                    uint32_t key0, uint32_t key1) {
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
+    uint4 rc = make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < p; ++j) {
+      if ((j & 3) == 0) rc = philox4x32_10((uint32_t)l, 0u, 64u + (uint32_t)(j >> 2), 0u, key0, key1);
+      const uint32_t bits = (j & 3) == 0 ? rc.x : ((j & 3) == 1 ? rc.y : ((j & 3) == 2 ? rc.z : rc.w));
+      out[(size_t)j * L + l] = (bits < thr) ? !genotype[j] : genotype[j];
+    }
+  }
+}
+}  // namespace mccbn
+
+extern "C" {
+// `_coin_tossing` (src/backward_sampling.cpp:105-123): L noisy copies of a genotype, L x p column-major
+int mccbn_coin_tossing(mccbn_ctx* c, double eps, unsigned L, const int* genotype, int p, int seed, int* out, char* err,
+                       size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (p < 1 || p > MCCBN_MAX_P) throw Error(MCCBN_ERR_ARG, "1 <= p <= 64 expected");
+  if (L == 0) return MCCBN_OK;
+  cudaStream_t s = c->stream;
+  DevBuf<int> dg, dout;
+  MCCBN_CUDA(cudaMemcpyAsync(dg.ensure(p), genotype, sizeof(int) * p, cudaMemcpyHostToDevice, s));
+  dout.ensure((size_t)L * p);
+  const uint32_t thr = (uint32_t)std::min(std::max(eps, 0.0) * 4294967296.0, 4294967295.0);
+  const PhiloxKey key = make_key((uint32_t)seed, 0u, 2u);
+  coin_tossing_kernel<<<std::min(1024u, (L + 255u) / 256u), 256, 0, s>>>(dg.ptr, dout.ptr, (int)L, p, thr, key.k0, key.k1);
+  c->launches++;
+  MCCBN_CUDA(cudaGetLastError());
+  MCCBN_CUDA(cudaMemcpyAsync(out, dout.ptr, sizeof(int) * (size_t)L * p, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  MCCBN_CATCH
+}
+
+// `_generate_mutation_times` (src/add_remove.cpp:286-321): conditional proposal for N given genotypes.  The uniforms
+// come from the reference's generator in the reference's order (T_s first unless given, then N draws per node in
+// topological order); the arithmetic runs in fp64 on the device (conditional_from_uniforms_kernel).
+int mccbn_generate_mutation_times(mccbn_ctx* c, const int* obs, const int* poset, const double* lambda, double* time,
+                                  float lambda_s, int sampling_times_available, int seed, int N, int p, double* Tdiff,
+                                  double* proposal_density, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  if (N <= 0) return MCCBN_OK;
+  std::mt19937 rng = make_std_rng((unsigned)seed);
+  std::uniform_real_distribution<double> U(0.0, 1.0);
+  std::vector<double> ts(N), u((size_t)N * p);
+  for (int n = 0; n < N; ++n) {
+    if (sampling_times_available) {
+      ts[n] = time[n];
+    } else {
+      ts[n] = -std::log1p(U(rng) * std::expm1(-INFINITY * (double)lambda_s)) / (double)lambda_s;  // rexp, rng_utils.cpp:44-56
+      time[n] = ts[n];
+    }
+  }
+  for (int v : boost_like_topological_order(poset, p))
+    for (int n = 0; n < N; ++n) u[(size_t)v * N + n] = U(rng);
+  std::vector<double> lq(N);
+  const int rc = mccbn_conditional_from_uniforms(c, obs, N, poset, p, lambda, u.data(), ts.data(), Tdiff, lq.data(),
+                                                 nullptr, nullptr, err, errlen);
+  if (rc != MCCBN_OK) return rc;
+  if (proposal_density) std::copy(lq.begin(), lq.end(), proposal_density);
   MCCBN_CATCH
 }
 

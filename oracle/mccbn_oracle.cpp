@@ -2028,6 +2028,29 @@ int ref_adaptive_simulated_annealing(const int* poset, const int* obs, const dou
   REF_CATCH
 }
 
+// _draw_sample (src/add_remove.cpp:244-284)
+int ref_draw_sample(const int* genotype, const int* poset, int p, unsigned move, const double* q_prob, int seed,
+                    int* sample, double* q_choice) {
+  REF_TRY
+  Model M = build_model(poset, p, 1.0f);
+  std::vector<unsigned char> g(p);
+  for (int j = 0; j < p; ++j) g[j] = genotype[j] != 0;
+  const bool compatible = is_compatible(g.data(), M);
+  std::vector<double> rw(p), aw(p);
+  for (int j = 0; j < p; ++j) {
+    rw[j] = g[j] ? q_prob[j] : 0.0;
+    aw[j] = g[j] ? 0.0 : 1.0 / q_prob[j];
+  }
+  Context ctx(seed);
+  const int idx_remove = rdiscrete_std(1, rw, ctx.rng)[0];
+  const int idx_add = rdiscrete_std(1, aw, ctx.rng)[0];
+  double q = 0;
+  std::vector<unsigned char> s = draw_sample(g, M, move, rw, aw, q, idx_remove, idx_add, compatible);
+  for (int j = 0; j < p; ++j) sample[j] = s[j];
+  *q_choice = q;
+  REF_CATCH
+}
+
 // Known-answer test of the third-party generator the reference is built on: the C++ standard ([rand.predef]) fixes the
 // 10000th output of a default-constructed std::mt19937 to 4123659995.
 unsigned ref_mt19937_kat() {

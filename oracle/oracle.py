@@ -385,3 +385,13 @@ def adaptive_simulated_annealing(poset, obs, L, times=None, lambda_s=1.0, weight
         C.byref(eps), _p(out), C.byref(ll), _p(stats)))
     return dict(lambda_=lam, eps=eps.value, poset=out, llhood=ll.value, n_accept=int(stats[0]),
                 moves=stats[1:5].tolist(), n_scored=int(stats[5]))
+
+
+def draw_sample(genotype, poset, move, q_prob, seed=1):
+    """`_draw_sample` (src/add_remove.cpp:244-284)."""
+    g, poset, q = _i32(genotype), _i32(poset), _f64(q_prob)
+    p = poset.shape[0]
+    out = np.zeros(p, np.int32)
+    qc = C.c_double(0)
+    _chk(lib().ref_draw_sample(_p(g), _p(poset), p, C.c_uint(move), _p(q), int(seed), _p(out), C.byref(qc)))
+    return out, qc.value
