@@ -153,6 +153,9 @@ struct DevBuf {  // grow-only device buffer
   size_t cap = 0;
   T* ensure(size_t n) {
     if (n > cap) {
+      // growing a buffer that in-flight kernels may still use: wait before its block goes back to the cache (rare:
+      // buffers reach their final size in the first iteration)
+      if (ptr) cudaDeviceSynchronize();
       if (ptr) device_cache().free(ptr);
       ptr = nullptr;
       cap = 0;
