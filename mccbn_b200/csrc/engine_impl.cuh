@@ -146,9 +146,10 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
   } else if (scheme == kPool) {
     // pool of K = p * L prior draws shared by all observations, regenerated every EM iteration (:606, :650-654)
     const int K = p * L;
-    const int PM = p <= 8 ? 8 : (p <= 16 ? 16 : (p <= 24 ? 24 : 32));
+    const int PM = p <= 8 ? 8 : (p <= 16 ? 16 : 32);  // powers of two: the kernel binary-searches the sorted rows
     float* Tp = pool_T.ensure((size_t)K * PM);
     float* Zp = pool_Z.ensure((size_t)K * PM);
+    uint32_t* Mp = pool_M.ensure((size_t)K * (PM + 1));
     const PhiloxKey kgen = make_key(seed, (uint32_t)iter, 3u);
     const PhiloxKey kts = make_key(seed, (uint32_t)iter, 4u);
     const int ggen = std::max(1, std::min((K + kFwdBlock - 1) / kFwdBlock, ctx->sm_count * 6));
@@ -164,6 +165,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.times = times.ptr;
     a.model = models.ptr + c;
     a.Tp = Tp;
+    a.Mp = Mp;
     a.Zp = Zp;
     a.part = part.ensure((size_t)n_items * PS());
     a.N = N;
@@ -179,8 +181,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
 #define MCCBN_POOL(PMX)                                                                                         \
   do {                                                                                                          \
     const PosetProg pg = build_prog(flat[c], PMX, 4);                                                           \
-    pool_generate_kernel<PMX><<<ggen, kFwdBlock, fwd_smem_bytes<float, PMX>(), s>>>(Tp, Zp, K, kgen.k0, kgen.k1, \
-                                                                                    eval_id[c], pg);            \
+    pool_generate_kernel<PMX><<<ggen, kFwdBlock, fwd_smem_bytes<float, PMX>(), s>>>(Tp, Mp, Zp, K, kgen.k0,     \
+                                                                                    kgen.k1, eval_id[c], pg);   \
     if (times_given)                                                                                            \
       estep_pool_kernel<PMX, true><<<grid, kPoolBlock, 0, s>>>(a, pg);                                          \
     else                                                                                                        \
@@ -188,7 +190,6 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
   } while (0)
     if (PM == 8) MCCBN_POOL(8);
     else if (PM == 16) MCCBN_POOL(16);
-    else if (PM == 24) MCCBN_POOL(24);
     else MCCBN_POOL(32);
 #undef MCCBN_POOL
     ctx->launches += 2;

@@ -9,8 +9,11 @@
 // directly (Rao-Blackwellisation of the resampling step: same estimand, less Monte-Carlo noise; documented in
 // DESIGN.md) -- the O(N K p) comparison work is the reference's.
 //
-// Mapping: pool entries are staged tile by tile in shared memory ([j][k] so that a whole warp reads one float4 of
-// an entry as a broadcast); one THREAD per observation sweeps the tile with its p+2 running sums in registers.
+// Mapping: pool entries are staged tile by tile in shared memory; one THREAD per observation sweeps the tile with its
+// p+2 running sums in registers.  The genotype of entry k at sampling time t is a PREFIX of its events sorted by event
+// time, so the pool stores per entry the sorted times and the p + 1 prefix genotypes: X_k(t) costs a 5-step binary
+// search in the entry's sorted row (per-lane shared-memory addresses inside one 128-byte row: conflict-free) and one
+// mask load instead of p compares.
 #pragma once
 #include "device_types.cuh"
 #include "kernels_forward.cuh"
@@ -18,14 +21,24 @@
 
 namespace mccbn {
 
+#ifndef MCCBN_POOL_UNROLL
+#define MCCBN_POOL_UNROLL 4  // 1 / 2 / 4 / 8 -> 35.0 / 32.4 / 26.3 / 26.5 ms on cfg 5 (independent rank searches in flight)
+#endif
+#define MCCBN_PRAGMA_(x) _Pragma(#x)
+#define MCCBN_PRAGMA(x) MCCBN_PRAGMA_(x)
+#define MCCBN_POOL_UNROLL_PRAGMA MCCBN_PRAGMA(unroll MCCBN_POOL_UNROLL)
+
 constexpr int kPoolBlock = 128;  // observations per block
 constexpr int kPoolTile = 64;    // pool entries per shared-memory tile
 
-// Pool generation: entry k draws Z_j ~ Exp(lambda_j) and propagates T_j.  Output layout [k][PMAX] (row per entry,
-// topological-position order, padded with +inf for T so that padded events are never mutated, 0 for Z).
+// Pool generation: entry k draws Z_j ~ Exp(lambda_j) and propagates T_j (sample_times, src/mcem_hcbn.cpp:184-213).
+// Output per entry: Tp[k][PMAX] the event times in ASCENDING order (padded with +inf), Mp[k][PMAX + 1] the prefix
+// genotypes in topological-position bit order (Mp[k][r] = events with the r smallest times; Mp[k][0] = 0),
+// Zp[k][PMAX] the waiting times by topological position (padded with 0).
 template <int PMAX>
-__global__ void __launch_bounds__(kFwdBlock) pool_generate_kernel(float* __restrict__ Tp, float* __restrict__ Zp, int K,
-                                                                  uint32_t key0, uint32_t key1, uint32_t cw,
+__global__ void __launch_bounds__(kFwdBlock) pool_generate_kernel(float* __restrict__ Tp, uint32_t* __restrict__ Mp,
+                                                                  float* __restrict__ Zp, int K, uint32_t key0,
+                                                                  uint32_t key1, uint32_t cw,
                                                                   const __grid_constant__ PosetProg pg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_T = reinterpret_cast<float*>(smem_raw);
@@ -36,15 +49,32 @@ __global__ void __launch_bounds__(kFwdBlock) pool_generate_kernel(float* __restr
   const uint32_t zrow_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x * ZS::kStride);
   ScaleSrc<float, PMAX> scale;
   scale = ScaleSrc<float, PMAX>{nullptr};
+  const int p = pg.p;
   for (int k = blockIdx.x * kFwdBlock + threadIdx.x; k < K; k += gridDim.x * kFwdBlock) {
     uint32_t X;
     float Ts;
     // TIMES_GIVEN = true: no sampling time is drawn here (it is drawn per (observation, entry) later)
     sample_forward<float, PMAX, true>(pg, tcol_s, zrow_s, (uint32_t)k, 0xffffffffu, key0, key1, cw, 0.f, scale, X, Ts);
-#pragma unroll
+    // insertion sort of (time, position) in this thread's T column (in place; the column is rewritten by the next draw)
+    unsigned char ord[PMAX];
+    for (int j = 0; j < p; ++j) {
+      const float t = s_T[j * kFwdBlock + threadIdx.x];
+      int r = j;
+      while (r > 0 && s_T[(r - 1) * kFwdBlock + threadIdx.x] > t) {
+        s_T[r * kFwdBlock + threadIdx.x] = s_T[(r - 1) * kFwdBlock + threadIdx.x];
+        ord[r] = ord[r - 1];
+        --r;
+      }
+      s_T[r * kFwdBlock + threadIdx.x] = t;
+      ord[r] = (unsigned char)j;
+    }
+    uint32_t m = 0u;
+    Mp[(size_t)k * (PMAX + 1)] = 0u;
     for (int j = 0; j < PMAX; ++j) {
-      Tp[(size_t)k * PMAX + j] = j < pg.p ? s_T[j * kFwdBlock + threadIdx.x] : __int_as_float(0x7f800000);
-      Zp[(size_t)k * PMAX + j] = j < pg.p ? s_Z[threadIdx.x * ZS::kStride + j] * scale(j) : 0.f;  // Z = e c
+      if (j < p) m |= 1u << ord[j];
+      Tp[(size_t)k * PMAX + j] = j < p ? s_T[j * kFwdBlock + threadIdx.x] : __int_as_float(0x7f800000);
+      Mp[(size_t)k * (PMAX + 1) + j + 1] = m;
+      Zp[(size_t)k * PMAX + j] = j < p ? s_Z[threadIdx.x * ZS::kStride + j] * scale(j) : 0.f;  // Z = e c
     }
   }
 }
@@ -53,8 +83,9 @@ struct PoolArgs {
   const uint64_t* obs_bits;
   const double* times;
   const DevModel* model;
-  const float* Tp;  // K x PMAX
-  const float* Zp;  // K x PMAX
+  const float* Tp;     // K x PMAX sorted event times
+  const uint32_t* Mp;  // K x (PMAX + 1) prefix genotypes
+  const float* Zp;     // K x PMAX
   double* part;     // N x chunks x PS
   int N, K, chunks, chunk_len;  // chunk over pool entries (multiple of kPoolTile)
   long long obs_offset;
@@ -66,6 +97,8 @@ template <int PMAX, bool TIMES_GIVEN>
 __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a, const __grid_constant__ PosetProg pg) {
   __shared__ __align__(16) float s_Tt[kPoolTile * PMAX];
   __shared__ __align__(16) float s_Zt[kPoolTile * PMAX];
+  __shared__ uint32_t s_Mt[kPoolTile * (PMAX + 1)];
+  static_assert((PMAX & (PMAX - 1)) == 0, "the rank search needs a power-of-two row length");
   __shared__ float s_rtab[kRtabN];
   const DevModel* __restrict__ mdl = a.model;
   const int p = pg.p;
@@ -93,8 +126,10 @@ __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a
       reinterpret_cast<float4*>(s_Tt)[t] = reinterpret_cast<const float4*>(a.Tp + (size_t)k0 * PMAX)[t];
       reinterpret_cast<float4*>(s_Zt)[t] = reinterpret_cast<const float4*>(a.Zp + (size_t)k0 * PMAX)[t];
     }
+    for (int t = threadIdx.x; t < nk * (PMAX + 1); t += kPoolBlock) s_Mt[t] = a.Mp[(size_t)k0 * (PMAX + 1) + t];
     __syncthreads();
     uint4 r = make_uint4(0, 0, 0, 0);
+    MCCBN_POOL_UNROLL_PRAGMA
     for (int kk = 0; kk < nk; ++kk) {
       float Ts = ts_given;
       if (!TIMES_GIVEN) {
@@ -103,14 +138,14 @@ __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a
         const uint32_t bits = (kk & 3) == 0 ? r.x : ((kk & 3) == 1 ? r.y : ((kk & 3) == 2 ? r.z : r.w));
         Ts = fast_lg2(u01_open0(bits)) * cs;
       }
-      uint32_t X = 0u;
-      const float4* Tk = reinterpret_cast<const float4*>(s_Tt + kk * PMAX);
+      // rank = #{j : T_kj <= Ts} by binary search in the entry's sorted row, X = prefix genotype of that rank
+      const float* Tk = s_Tt + kk * PMAX;
+      int rank = 0;
 #pragma unroll
-      for (int q = 0; q < PMAX / 4; ++q) {
-        const float4 t4 = Tk[q];  // warp-wide broadcast
-        X |= (t4.x <= Ts ? 1u : 0u) << (4 * q) | (t4.y <= Ts ? 1u : 0u) << (4 * q + 1) |
-             (t4.z <= Ts ? 1u : 0u) << (4 * q + 2) | (t4.w <= Ts ? 1u : 0u) << (4 * q + 3);
-      }
+      for (int step = PMAX / 2; step >= 1; step >>= 1)
+        if (Tk[rank + step - 1] <= Ts) rank += step;
+      if (Tk[rank] <= Ts) rank += 1;  // rank in [0, PMAX]: the loop alone reaches PMAX - 1
+      const uint32_t X = s_Mt[kk * (PMAX + 1) + rank];
       const int d = __popc(X ^ yt);
       const int de = flip ? p - d : d;
       if (de < dref) {  // per-thread running reference (lanes are different observations); rare

@@ -139,7 +139,8 @@ struct mccbn_problem {
   DevBuf<double> out_w, out_w2, out_dist, out_T;
   DevBuf<int> out_leff;
   DevBuf<uint64_t> ball;  // backward scheme: flip masks of the Hamming ball
-  DevBuf<float> pool_T, pool_Z;  // pool scheme: K x PMAX event / waiting times
+  DevBuf<float> pool_T, pool_Z;  // pool scheme: K x PMAX sorted event times / waiting times
+  DevBuf<uint32_t> pool_M;       // pool scheme: K x (PMAX + 1) prefix genotypes
   DevBuf<unsigned long long> counts;  // compatibility / initialize_lambda counters
   int ball_p = -1, ball_k = -1;
   int trace_rows = 0;
