@@ -131,7 +131,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.PS = PS();
     const int warps_per_block = kFwdBlock / 32;
     long long blocks = (n_items + warps_per_block - 1) / warps_per_block;
-    grid_x = (int)std::max(1LL, std::min<long long>(blocks, (long long)ctx->sm_count * 2));
+    // one resident wave: MCCBN_COND_MINB blocks per SM for the fp32 kernels, 1 for the fp64 validation mode
+    grid_x = (int)std::max(1LL, std::min<long long>(blocks, (long long)ctx->sm_count * (precision == 1 ? 1 : MCCBN_COND_MINB)));
     if (precision == 1) {
       CondLauncher::go<double, 32>(a, flat[c], times_given, mode, grid_x, s);
     } else if (p <= 16) {

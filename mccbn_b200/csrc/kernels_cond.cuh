@@ -126,7 +126,10 @@ __device__ __forceinline__ bool compatible_topo(const PosetProg& pg, const uint3
 }
 
 template <typename real, int PMAX, bool TIMES_GIVEN, int MODE>
-__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? 2 : 1)
+#ifndef MCCBN_COND_MINB
+#define MCCBN_COND_MINB 4  // resident blocks per SM (ncu r1e: 2 blocks left the schedulers at IPC 0.9 of 2.5)
+#endif
+__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB : 1)
     estep_conditional_kernel(const CondArgs a, const __grid_constant__ PosetProg pg) {
   __shared__ real s_T[(PMAX + 1) * kFwdBlock];
   __shared__ real s_lam2[PMAX + 1];
