@@ -40,7 +40,7 @@ extern "C" {
 #define MCCBN_ERR_IO 5          /* ASA output files */
 
 #define MCCBN_MAX_P 64
-#define MCCBN_FAST_MAX_P 32
+#define MCCBN_FAST_MAX_P 32 /* all schemes; the forward scheme accepts p <= MCCBN_MAX_P (64-bit genotype words) */
 #define MCCBN_NCCL_ID_BYTES 128
 #define MCCBN_IPC_HANDLE_BYTES 64
 

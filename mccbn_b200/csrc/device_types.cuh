@@ -25,6 +25,7 @@ typedef long long int64_t;
 namespace mccbn {
 
 constexpr int kFastMaxP = 32;      // one 32-bit genotype word on the Philox fast path
+constexpr int kWideMaxP = 64;      // forward scheme only: 64-bit genotype word, generic kernel (PosetProgWide)
 constexpr int kMaxCand = 16;       // concurrently scored candidate posets (ASA batching)
 constexpr int kMaxEdgesFast = 512; // >= 32*31/2
 constexpr int kFwdBlock = 128;     // threads per block of the forward E-step kernel
@@ -84,6 +85,7 @@ struct PeerView {
 // have children is staged in a per-thread shared-memory column, row PMAX of that column holds 0 so that
 // absent parents can be loaded unconditionally (max with 0 is the reference's T_max initialisation).
 struct PosetProg {
+  typedef uint32_t word_t;  // genotype word of the kernels driven by this program
   int p;
   unsigned store_mask;   // bit k: T_k has children -> stage it
   unsigned multi_mask;   // bit k: node k has more than two parents -> `xo[k]` holds parents 3..6
@@ -99,10 +101,23 @@ struct PosetProg {
   unsigned short xoff[kMaxEdgesFast];
 };
 
+// The same program for 32 < p <= 64 (forward scheme, generic kernel): 64-bit masks, no compatibility masks.
+struct PosetProgWide {
+  typedef uint64_t word_t;
+  int p;
+  unsigned one_bits;
+  uint64_t store_mask, multi_mask, valid_mask, huge_mask;
+  uint2 off[kWideMaxP];
+  uint4 xo[kWideMaxP];
+  unsigned char ev[kWideMaxP];
+  unsigned short xstart[kWideMaxP + 2];
+  unsigned short xoff[2 * kMaxEdgesFast];
+};
+
 // lambda-derived scales of the exponential draws, refreshed on the device after every M-step and mirrored into
 // __constant__ memory so that they are immediate constant-bank operands of the FMULs.
 struct FwdScale {
-  float c[kFastMaxP];  // -ln2 / lambda at topological position k:  Z = log2(u) * c
+  float c[kWideMaxP];  // -ln2 / lambda at topological position k:  Z = log2(u) * c
   float cs;            // -ln2 / lambda_s
   int flip;            // 1 if eps > 1/2 (weights increase with the Hamming distance)
   int pad[2];

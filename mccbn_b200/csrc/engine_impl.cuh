@@ -43,7 +43,9 @@ struct CondLauncher {
 
 void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neighborhood_dist, bool times_given,
                                       uint32_t seed, int update_params, bool per_obs_out, int precision) {
-  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");
+  if (p > kFastMaxP && scheme != kForward)
+    throw Error(MCCBN_ERR_ARG, "32 < p <= 64 is supported by the forward scheme only");
   cudaStream_t s = ctx->stream;
   const int iter = iter_host[c];
   bind_scales(c);
@@ -52,7 +54,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
   int L_eff = L;
 
   if (scheme == kForward) {
-    JitKernel* jk = precision == 1 ? nullptr : resolve_jit(flat[c], times_given, L);
+    JitKernel* jk = (precision == 1 || p > kFastMaxP) ? nullptr : resolve_jit(flat[c], times_given, L);
     choose_chunks(L, chunks, chunk_len, grid_x, jk ? jk->blocks_per_sm : 0);
     n_items = (long long)N * chunks;
     FwdArgs a;
@@ -1480,7 +1482,7 @@ int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int
   MCCBN_TRY
   c = get_ctx(c);
   const Scheme sc = parse_scheme(sampling);
-  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");
   Candidate M;
   {
     FlatPoset f;

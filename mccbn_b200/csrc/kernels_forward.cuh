@@ -140,8 +140,11 @@ __device__ __forceinline__ float4 lds128_f(uint32_t saddr) {
 // max over the parents of node k (0 without parents): two unconditional loads (absent parents read the dummy
 // row, which holds 0); nodes with in-degree > 2 (warp-uniform test) read four more rows unconditionally, and only
 // in-degree > 6 falls back to a loop.
-template <typename real>
-__device__ __forceinline__ real parents_max(const PosetProg& pg, const unsigned multi_mask, const int k,
+__device__ __forceinline__ int popc_word(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int popc_word(uint64_t x) { return __popcll(x); }
+
+template <typename real, typename Prog>
+__device__ __forceinline__ real parents_max(const Prog& pg, const typename Prog::word_t multi_mask, const int k,
                                             const uint32_t tcol_s) {
   const uint2 o = pg.off[k];
   real m = max(lds_at<real>(tcol_s + o.x), lds_at<real>(tcol_s + o.y));
@@ -166,15 +169,17 @@ __device__ __forceinline__ real parents_max(const PosetProg& pg, const unsigned 
 // have scale 0 and no parents, so their T is 0 and the caller's valid_mask removes them from X.
 // Random stream of a sample (fp32): field 0 = sampling time, field k + 1 = node k (field_u01); Philox block b is
 // generated right before the first field that touches it, and only if that field belongs to a real node.
-template <typename real, int PMAX, bool TIMES_GIVEN>
-__device__ __forceinline__ void sample_forward(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zrow_s,
+template <typename real, int PMAX, bool TIMES_GIVEN, typename Prog>
+__device__ __forceinline__ void sample_forward(const Prog& pg, const uint32_t tcol_s, const uint32_t zrow_s,
                                                const uint32_t l, const uint32_t gi, const uint32_t k0,
                                                const uint32_t k1, const uint32_t cw, const real ts_given,
-                                               const ScaleSrc<real, PMAX> scale, uint32_t& X, real& Ts_out) {
+                                               const ScaleSrc<real, PMAX> scale, typename Prog::word_t& X,
+                                               real& Ts_out) {
+  typedef typename Prog::word_t word_t;
   constexpr uint32_t kRow = kFwdBlock * sizeof(real);
-  const unsigned multi_mask = pg.multi_mask;
+  const word_t multi_mask = pg.multi_mask;
   real Ts = ts_given;
-  X = 0u;
+  X = 0;
   if constexpr (sizeof(real) == 4) {
     constexpr int NB = fwd_blocks_for_fields(PMAX + 1);
     uint32_t W[4 * NB];
@@ -198,7 +203,7 @@ __device__ __forceinline__ void sample_forward(const PosetProg& pg, const uint32
       sts_at_f(tcol_s + k * kRow, t);
       zq[k & 3] = e;
       if ((k & 3) == 3) sts128_f(zrow_s + (uint32_t)(k - 3) * 4u, zq[0], zq[1], zq[2], zq[3]);
-      if (t <= Ts) X |= (1u << k);
+      if (t <= Ts) X |= ((word_t)1 << k);
     }
   } else {
     constexpr int UPB = RealTraits<double>::kUniPerBlock;
@@ -214,7 +219,7 @@ __device__ __forceinline__ void sample_forward(const PosetProg& pg, const uint32
       const double t = fma(e, scale(k), parents_max<real>(pg, multi_mask, k, tcol_s));
       sts_at_d(tcol_s + k * kRow, t);
       sts_at_d(zrow_s + (uint32_t)k * 8u, e);
-      if (t <= Ts) X |= (1u << k);
+      if (t <= Ts) X |= ((word_t)1 << k);
     }
   }
   X &= pg.valid_mask;
@@ -222,17 +227,17 @@ __device__ __forceinline__ void sample_forward(const PosetProg& pg, const uint32
 }
 
 // observed genotype word (event-id bit order) -> topological-position bit order
-template <int PMAX>
-__device__ __forceinline__ uint32_t to_topo_bits(const PosetProg& pg, const uint64_t yw) {
-  uint32_t yt = 0u;
+template <int PMAX, typename Prog>
+__device__ __forceinline__ typename Prog::word_t to_topo_bits(const Prog& pg, const uint64_t yw) {
+  typename Prog::word_t yt = 0;
 #pragma unroll
   for (int k = 0; k < PMAX; ++k)
-    if (k < pg.p) yt |= (uint32_t)((yw >> pg.ev[k]) & 1ull) << k;
+    if (k < pg.p) yt |= (typename Prog::word_t)((yw >> pg.ev[k]) & 1ull) << k;
   return yt;
 }
 
-template <typename real, int PMAX>
-__device__ __forceinline__ void load_scales_fp64(const PosetProg& pg, const DevModel* __restrict__ mdl, real* s_scale) {
+template <typename real, int PMAX, typename Prog>
+__device__ __forceinline__ void load_scales_fp64(const Prog& pg, const DevModel* __restrict__ mdl, real* s_scale) {
   if (sizeof(real) == 8) {
     for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock)
       s_scale[t] = t < pg.p ? (real)(-1.0 / mdl->lambda[pg.ev[t]]) : (t == PMAX ? (real)(-1.0 / mdl->lambda_s) : (real)0);
@@ -257,16 +262,19 @@ __host__ __device__ constexpr size_t fwd_smem_bytes(bool stages_t = true) {
 template <typename real, int PMAX, bool TIMES_GIVEN>
 struct GenericSampler {
   static constexpr bool kStagesT = true;
-  __device__ __forceinline__ void operator()(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zrow_s,
+  template <typename Prog>
+  __device__ __forceinline__ void operator()(const Prog& pg, const uint32_t tcol_s, const uint32_t zrow_s,
                                              const uint32_t l, const uint32_t gi, const uint32_t k0,
                                              const uint32_t k1, const uint32_t cw, const real ts_given,
-                                             const ScaleSrc<real, PMAX> scale, uint32_t& X, real& Ts_out) const {
+                                             const ScaleSrc<real, PMAX> scale, typename Prog::word_t& X,
+                                             real& Ts_out) const {
     sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zrow_s, l, gi, k0, k1, cw, ts_given, scale, X, Ts_out);
   }
 };
 
-template <typename real, int PMAX, bool TIMES_GIVEN, typename Sampler>
-__device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const PosetProg& pg, const Sampler sampler) {
+template <typename real, int PMAX, bool TIMES_GIVEN, typename Sampler, typename Prog>
+__device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog& pg, const Sampler sampler) {
+  typedef typename Prog::word_t word_t;
   // dynamic shared memory (fwd_smem_bytes): [rows 0..PMAX-1 staged T_k, row PMAX the dummy row (0),] then one row
   // per thread of staged e_k = log(u_k) (ZStage; frees PMAX registers per thread)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -300,7 +308,7 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Poset
   for (long long item = gw; item < a.n_items; item += nw) {
     const int i = (int)(item / a.chunks);
     const int ch = (int)(item - (long long)i * a.chunks);
-    const uint32_t yt = to_topo_bits<PMAX>(pg, a.obs_bits[i]);
+    const word_t yt = to_topo_bits<PMAX>(pg, a.obs_bits[i]);
     const real ts_given = TIMES_GIVEN ? (real)a.times[i] : (real)0;
     const uint32_t gi = (uint32_t)(a.obs_offset + i);
 
@@ -315,10 +323,10 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Poset
     for (int l0 = l_begin; l0 < l_end; l0 += 32) {
       const int l = l0 + lane;
       const bool valid = l < l_end;
-      uint32_t X;
+      word_t X;
       real Ts;
       sampler(pg, tcol_s, zrow_s, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given, scale, X, Ts);
-      const int d = __popc(X ^ yt);
+      const int d = popc_word((word_t)(X ^ yt));
       const int de = flip ? p - d : d;  // weights decrease in `de`
       const int dmin = __reduce_min_sync(0xffffffffu, valid ? de : (1 << 19));
       if (dmin < dref) {  // warp-uniform: a better sample arrived, rescale the running sums
@@ -366,18 +374,22 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Poset
       // natural-log scale of the record: true w = exp(scale) * w', scale = log(base) + dref * log(r)
       out[4] = mdl->log_base + (dref > 0 ? (double)dref * mdl->log_r : 0.0);
     }
-    double mine = 0.0;
+    double mine = 0.0, mine_hi = 0.0;  // lane k owns slots k and (p > 32) k + 32
 #pragma unroll
     for (int k = 0; k < PMAX; ++k) {
       if (k < p) {
         double v = (double)acc[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == (k & 31)) mine = v;
+        if (lane == (k & 31)) {
+          if (k < 32) mine = v;
+          else mine_hi = v;
+        }
       }
     }
     // acc holds sum w' e_k: the waiting time is Z_k = e_k c_k (c_k = -ln2/lambda_k in fp32, -1/lambda_k in fp64)
     if (lane < p) out[kStatHdr + lane] = mine * (double)scale(lane);
+    if (PMAX > 32 && lane + 32 < p) out[kStatHdr + 32 + lane] = mine_hi * (double)scale(lane + 32);
   }
 }
 
@@ -385,6 +397,14 @@ template <typename real, int PMAX, bool TIMES_GIVEN>
 __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? (PMAX >= MCCBN_FWD_BIGP ? MCCBN_FWD_MINB_BIG : 6) : 1)
     estep_forward_kernel(const FwdArgs a, const __grid_constant__ PosetProg pg) {
   estep_forward_body<real, PMAX, TIMES_GIVEN>(a, pg, GenericSampler<real, PMAX, TIMES_GIVEN>{});
+}
+
+// 32 < p <= 64: the same body on 64-bit genotype words (PosetProgWide); two resident blocks per SM
+constexpr int kFwdWideMinB = 2;
+template <int PMAX, bool TIMES_GIVEN>
+__global__ void __launch_bounds__(kFwdBlock, kFwdWideMinB)
+    estep_forward_wide_kernel(const FwdArgs a, const __grid_constant__ PosetProgWide pg) {
+  estep_forward_body<float, PMAX, TIMES_GIVEN>(a, pg, GenericSampler<float, PMAX, TIMES_GIVEN>{});
 }
 
 // Per-sample dump for ONE observation (the `_importance_weight_genotype` seam, src/mcem_hcbn.cpp:866-912):

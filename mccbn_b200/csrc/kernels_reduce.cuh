@@ -44,20 +44,21 @@ __global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) {
   const DevPoset* __restrict__ pos = a.poset;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int PS = a.PS;
-  const int sA = lane, sB = lane + 32;
-  double accA = 0.0, accB = 0.0;
+  const int sA = lane, sB = lane + 32, sC = lane + 64;  // PS <= 69: lanes 0..4 also own a third slot
+  double accA = 0.0, accB = 0.0, accC = 0.0;
 
   for (int i = blockIdx.x * kFinWarps + warp; i < a.N; i += gridDim.x * kFinWarps) {
     const double* rec = a.part + (size_t)i * a.chunks * PS;
     double M = rec[4];
     for (int c = 1; c < a.chunks; ++c) M = fmax(M, rec[(size_t)c * PS + 4]);
     const bool any = M > -INFINITY;
-    double vA = 0.0, vB = 0.0;
+    double vA = 0.0, vB = 0.0, vC = 0.0;
     for (int c = 0; c < a.chunks; ++c) {
       const double* rc = rec + (size_t)c * PS;
       const double s = any ? exp(rc[4] - M) : 0.0;
       if (sA < PS) vA += (sA == 1 ? s * s : (sA == 3 ? 1.0 : s)) * rc[sA];
       if (sB < PS) vB += s * rc[sB];
+      if (sC < PS) vC += s * rc[sC];
     }
     const double W = __shfl_sync(0xffffffffu, vA, 0);
     const double npos = __shfl_sync(0xffffffffu, vA, 3);
@@ -89,9 +90,15 @@ __global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) {
       accB += ok ? wt * ez : 0.0;
       if (a.Tdiff) a.Tdiff[(size_t)pos->ev[sB - kStatHdr] * a.N + i] = ez;
     }
+    if (sC < PS) {
+      const double ez = vC / W;
+      accC += ok ? wt * ez : 0.0;
+      if (a.Tdiff) a.Tdiff[(size_t)pos->ev[sC - kStatHdr] * a.N + i] = ez;
+    }
   }
   if (sA < PS) s_acc[warp][sA] = accA;
   if (sB < PS) s_acc[warp][sB] = accB;
+  if (sC < PS) s_acc[warp][sC] = accC;
   __syncthreads();
   for (int s = threadIdx.x; s < PS; s += kFinBlock) {
     double t = 0.0;
@@ -183,9 +190,9 @@ __device__ inline void prepare_tables(const DevPoset* __restrict__ pos, DevModel
     mdl->log_base = flip ? p * le : p * l1;
     mdl->log_r = flip ? (l1 - le) : (le - l1);
   }
-  if (sc && p <= kFastMaxP) {
+  if (sc && p <= kWideMaxP) {
     const double kLn2 = 0.693147180559945309417;
-    for (int k = threadIdx.x; k < kFastMaxP; k += blockDim.x)
+    for (int k = threadIdx.x; k < kWideMaxP; k += blockDim.x)
       sc->c[k] = k < p ? (float)(-kLn2 / mdl->lambda[pos->ev[k]]) : 0.f;
     if (threadIdx.x == 0) {
       sc->cs = (float)(-kLn2 / mdl->lambda_s);

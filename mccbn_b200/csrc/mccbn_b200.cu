@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <mutex>
+#include <type_traits>
 
 #include "engine.cuh"
 #include "jit.cuh"
@@ -78,22 +79,25 @@ static void fill_dev_poset(const FlatPoset& f, DevPoset& d) {
 namespace mccbn {
 
 // kernel-parameter program of a poset for a given unroll width and staging element size
-static PosetProg build_prog(const FlatPoset& f, int pmax, int elem_bytes) {
-  PosetProg g;
+template <typename Prog>
+static Prog build_prog_t(const FlatPoset& f, int pmax, int elem_bytes) {
+  typedef typename Prog::word_t word_t;
+  constexpr int kMaxNodes = (int)(sizeof(word_t) * 8);
+  Prog g;
   std::memset(&g, 0, sizeof(g));
   g.p = f.p;
-  g.store_mask = (unsigned)f.has_children_pos;
-  g.valid_mask = f.p >= 32 ? 0xffffffffu : ((1u << f.p) - 1u);
+  g.store_mask = (word_t)f.has_children_pos;
+  g.valid_mask = f.p >= kMaxNodes ? ~(word_t)0 : (((word_t)1 << f.p) - 1);
   g.one_bits = 0x3f800000u;
   const unsigned dummy = (unsigned)pmax * kFwdBlock * elem_bytes;
   int x = 0;
-  for (int k = 0; k < kFastMaxP; ++k) {
+  for (int k = 0; k < kMaxNodes; ++k) {
     g.off[k] = make_uint2(dummy, dummy);
     g.xo[k] = make_uint4(dummy, dummy, dummy, dummy);
     g.xstart[k] = (unsigned short)x;
     if (k >= f.p) continue;
     g.ev[k] = (unsigned char)f.topo[k];
-    g.parent_mask[k] = (unsigned)f.parent_pos[k];
+    if constexpr (std::is_same<Prog, PosetProg>::value) g.parent_mask[k] = (unsigned)f.parent_pos[k];
     int n = 0;
     for (uint64_t m = f.parent_pos[k]; m; m &= m - 1, ++n) {
       const unsigned row = (unsigned)ctz64(m);
@@ -105,15 +109,21 @@ static PosetProg build_prog(const FlatPoset& f, int pmax, int elem_bytes) {
         case 3: g.xo[k].y = o; break;
         case 4: g.xo[k].z = o; break;
         case 5: g.xo[k].w = o; break;
-        default: g.xoff[x++] = (unsigned short)(row * kFwdBlock * 4); break;
+        default:
+          if (x >= (int)(sizeof(g.xoff) / sizeof(g.xoff[0]))) throw Error(MCCBN_ERR_ARG, "poset has too many edges");
+          g.xoff[x++] = (unsigned short)(row * kFwdBlock * 4);
+          break;
       }
     }
-    if (n > 2) g.multi_mask |= 1u << k;
-    if (n > 6) g.huge_mask |= 1u << k;
+    if (n > 2) g.multi_mask |= (word_t)1 << k;
+    if (n > 6) g.huge_mask |= (word_t)1 << k;
   }
-  g.xstart[kFastMaxP] = g.xstart[kFastMaxP + 1] = (unsigned short)x;
-  for (int k = f.p; k < kFastMaxP; ++k) g.xstart[k] = (unsigned short)x;
+  g.xstart[kMaxNodes] = g.xstart[kMaxNodes + 1] = (unsigned short)x;
+  for (int k = f.p; k < kMaxNodes; ++k) g.xstart[k] = (unsigned short)x;
   return g;
+}
+static PosetProg build_prog(const FlatPoset& f, int pmax, int elem_bytes) {
+  return build_prog_t<PosetProg>(f, pmax, elem_bytes);
 }
 
 }  // namespace mccbn
@@ -268,7 +278,27 @@ struct mccbn_problem {
     }                                                                                                   \
   } while (0)
     if constexpr (sizeof(real) == 8) {
+      if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the fp64 validation mode supports p <= 32");
       MCCBN_FWD(32);
+    } else if (p > kFastMaxP) {
+      // 32 < p <= 64: 64-bit genotype words, generic kernel
+#define MCCBN_FWD_WIDE(PM)                                                                                  \
+  do {                                                                                                      \
+    const PosetProgWide pg = build_prog_t<PosetProgWide>(f, PM, 4);                                         \
+    constexpr size_t sm = fwd_smem_bytes<float, PM>();                                                      \
+    if (times_given) {                                                                                      \
+      static bool once = (optin_smem(estep_forward_wide_kernel<PM, true>, sm), true);                       \
+      (void)once;                                                                                           \
+      estep_forward_wide_kernel<PM, true><<<grid, kFwdBlock, sm, s>>>(a, pg);                               \
+    } else {                                                                                                \
+      static bool once = (optin_smem(estep_forward_wide_kernel<PM, false>, sm), true);                      \
+      (void)once;                                                                                           \
+      estep_forward_wide_kernel<PM, false><<<grid, kFwdBlock, sm, s>>>(a, pg);                              \
+    }                                                                                                       \
+  } while (0)
+      if (p <= 48) MCCBN_FWD_WIDE(48);
+      else MCCBN_FWD_WIDE(64);
+#undef MCCBN_FWD_WIDE
     } else {
       if (p <= 4) MCCBN_FWD(4);
       else if (p <= 8) MCCBN_FWD(8);
@@ -289,7 +319,7 @@ struct mccbn_problem {
   // grid is exactly one resident wave, every warp strides over ~24 items
   void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x, int blocks_per_sm = 0) const {
     const int warps_per_block = kFwdBlock / 32;
-    if (blocks_per_sm <= 0) blocks_per_sm = p > MCCBN_FWD_BIGP - 4 ? MCCBN_FWD_MINB_BIG : 6;
+    if (blocks_per_sm <= 0) blocks_per_sm = p > kFastMaxP ? kFwdWideMinB : (p > MCCBN_FWD_BIGP - 4 ? MCCBN_FWD_MINB_BIG : 6);
     const int resident_blocks = ctx->sm_count * blocks_per_sm;  // blocks of 4 warps
     const long long total_warps = (long long)resident_blocks * warps_per_block;
     long long want_items = total_warps * 24;
@@ -362,7 +392,7 @@ struct mccbn_problem {
   }
   // make candidate c's scales the __constant__ operands of the next sampling kernel (stream-ordered)
   void bind_scales(int c) {
-    if (p <= kFastMaxP)
+    if (p <= kWideMaxP)
       MCCBN_CUDA(cudaMemcpyToSymbolAsync(c_scale, scales.ptr + c, sizeof(FwdScale), 0, cudaMemcpyDeviceToDevice,
                                          ctx->stream));
   }

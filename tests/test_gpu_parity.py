@@ -393,3 +393,67 @@ def test_add_remove_proposal_support_and_times_given(oracle):
     mo, so = _mean_se(o, range(1001, 1025))
     z = (mg - mo) / np.sqrt(sg ** 2 + so ** 2 + 1e-300)
     assert np.nanmax(np.abs(z)) < 4.5, np.nanmax(np.abs(z))
+
+
+# ---------------------------------------------------------------- 32 < p <= 64 (forward scheme, 64-bit genotype words)
+@pytest.mark.parametrize("p", [33, 40, 48, 57, 64])
+def test_wide_forward_k1_empty_poset(p):
+    """exact answer K1 (empty poset, sampling times given) for p beyond one 32-bit genotype word.  Forward sampling
+    cannot resolve P(Y) for 40 free events with a few thousand samples, so all but six events are (almost) certain to
+    have occurred (lambda t >> 1); the observations disagree with two of the certain events -- one of them the last
+    bit of the 64-bit word path -- which multiplies P(Y) by known factors, and are random on the six free events."""
+    N = 6
+    rng = np.random.default_rng(p)
+    lam = np.full(p, 80.0)
+    free = rng.choice(p, 6, replace=False)
+    lam[free] = rng.uniform(0.5, 2.0, 6)
+    poset = np.zeros((p, p), np.int32)
+    obs = np.ones((N, p), np.int32)
+    obs[:, free] = rng.integers(0, 2, (N, 6))
+    sure = np.setdiff1d(np.arange(p), free)
+    obs[:, sure[-1]] = 0          # the highest certain event: observed as not mutated (one noise flip)
+    obs[::2, sure[0]] = 0
+    times = rng.uniform(0.3, 2.0, N)
+    ex = np.array([exact.k1_empty_poset(obs[i], lam, 0.05, times[i]) for i in range(N)])
+    L = 4096
+
+    def est(seed):
+        r = mc.importance_weight(obs, L, poset, lam, 0.05, time=times, seed=seed)
+        return np.concatenate([r["w"] / L, r["dist"]])
+
+    mean, se = _mean_se(est, range(300, 324))
+    ref = np.concatenate([ex[:, 0], ex[:, 1]])
+    assert np.abs((mean - ref) / np.maximum(se, 1e-300)).max() < 4.5
+    assert np.all(ref[N:] >= 1.0)  # at least the forced flip
+
+
+@pytest.mark.parametrize("p,times", [(36, False), (50, True), (64, False)])
+def test_wide_forward_matches_oracle(oracle, p, times):
+    """per-observation log sum w, E[d], E[Z] and the MCEM fixed point for p > 32: GPU (Philox) vs oracle (mt19937)"""
+    c = synth.make_config(p, 8, eps=0.05, seed=p, density=0.08)
+    t = c["times"] if times else None
+    L = 1024
+
+    def run(fn):
+        def est(seed):
+            r = fn(seed)
+            return np.concatenate([np.log(r["w"] / L), r["dist"], r["Tdiff"].ravel()])
+        return est
+
+    g = run(lambda s: mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.1, time=t, seed=s))
+    o = run(lambda s: oracle.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.1, times=t, seed=s, thrds=4))
+    mg, sg = _mean_se(g, range(1, 17))
+    mo, so = _mean_se(o, range(1001, 1017))
+    z = (mg - mo) / np.sqrt(sg ** 2 + so ** 2 + 1e-300)
+    assert np.nanmax(np.abs(z)) < 4.5, np.nanmax(np.abs(z))
+    # one full MCEM run stays finite and moves towards the generating parameters
+    c2 = synth.make_config(p, 300, eps=0.05, seed=p + 1, density=0.08)
+    r = mc.MCEM_hcbn(c2["lambda0"], c2["poset"], c2["obs"], L=64, eps=0.1, max_iter=40, update_step_size=20, seed=3)
+    assert np.all(np.isfinite(r["lambda_"])) and 0 < r["eps"] < 0.3 and np.isfinite(r["llhood"])
+
+
+def test_wide_other_schemes_are_rejected():
+    c = synth.make_config(40, 5, eps=0.05, seed=1, density=0.08)
+    with pytest.raises(mc.MccbnError) as e:
+        mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], 0.1, L=64, sampling="backward", seed=1)
+    assert "forward scheme only" in str(e.value)
