@@ -79,6 +79,7 @@ struct NcclApi {
 // cached block is never in use by in-flight work.  MCCBN_DEVICE_CACHE_MB caps the cache (default 4096, 0 = off).
 struct DeviceCache {
   std::mutex mu;
+  unsigned long long epoch = 0;  // bumped by every allocation: captured CUDA graphs hold raw pointers
   std::multimap<std::pair<int, size_t>, void*> free_blocks;  // (device, bytes) -> block
   std::map<void*, std::pair<int, size_t>> live;               // block -> (device, bytes)
   size_t cached_bytes = 0, cap_bytes = (size_t)4096 << 20;
@@ -98,6 +99,7 @@ struct DeviceCache {
       auto it = free_blocks.lower_bound({dev, want});
       if (it != free_blocks.end() && it->first.first == dev && it->first.second <= 2 * want) {
         void* p = it->second;
+        ++epoch;
         cached_bytes -= it->first.second;
         live[p] = it->first;
         free_blocks.erase(it);
@@ -105,6 +107,7 @@ struct DeviceCache {
       }
     }
     void* p = nullptr;
+    ++epoch;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
       cudaGetLastError();

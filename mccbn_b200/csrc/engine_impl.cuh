@@ -185,7 +185,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
   do {                                                                                                          \
     const PosetProg pg = build_prog(flat[c], PMX, 4);                                                           \
     pool_generate_kernel<PMX><<<ggen, kFwdBlock, fwd_smem_bytes<float, PMX>(), s>>>(Tp, Mp, Zp, K, kgen.k0,     \
-                                                                                    kgen.k1, eval_id[c], pg);   \
+                                                                                    kgen.k1, eval_id[c],       \
+                                                                                    models.ptr + c, pg);        \
     if (times_given)                                                                                            \
       estep_pool_kernel<PMX, true><<<grid, kPoolBlock, 0, s>>>(a, pg);                                          \
     else                                                                                                        \
@@ -287,8 +288,7 @@ static std::vector<EmResult> run_mcem_multi(mccbn_problem& pb, const std::vector
         R.avg_llhood = 0.0;
       }
       n_run[r] = std::min(R.boundary, ctl.max_iter) - R.iter;
-      for (unsigned t = 0; t < n_run[r]; ++t)
-        pb.enqueue_iteration(R.slot, scheme, (int)L, ctl.neighborhood_dist, times_given, seed, 1, false, precision);
+      pb.enqueue_iterations(R.slot, (int)n_run[r], scheme, (int)L, ctl.neighborhood_dist, times_given, seed, 1, precision);
       rows[r].resize((size_t)n_run[r] * stride);
       MCCBN_CUDA(cudaMemcpyAsync(rows[r].data(), pb.trace_of(R.slot) + (size_t)R.iter * stride,
                                  sizeof(double) * rows[r].size(), cudaMemcpyDeviceToHost, pb.ctx->stream));
@@ -613,9 +613,8 @@ int mccbn_problem_em_iterations(mccbn_problem* pb, unsigned L, const char* sampl
   MCCBN_TRY
   get_ctx(pb->ctx);
   const Scheme sc = parse_scheme(sampling);
-  for (int t = 0; t < n_iter; ++t)
-    pb->enqueue_iteration(0, sc, (int)L, neighborhood_dist, sampling_times_available != 0, (uint32_t)seed, update_params,
-                          false, 0);
+  pb->enqueue_iterations(0, n_iter, sc, (int)L, neighborhood_dist, sampling_times_available != 0, (uint32_t)seed,
+                         update_params, 0);
   MCCBN_CATCH
 }
 

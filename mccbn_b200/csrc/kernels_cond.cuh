@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
   const long long gw = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * kWarps;
   const uint32_t cw = a.cw;
+  const uint32_t key1 = iter_key(a.key1, mdl);
   const uint32_t eps_thr = (MODE == kCondBernoulli) ? (uint32_t)fmin(mdl->eps * 4294967296.0, 4294967295.0) : 0u;
 
   for (long long item = gw; item < a.n_items; item += nw) {
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
     auto consume = [&](const uint32_t l, const uint32_t Xt, const int d, const bool valid, const real lw2_extra) {
       real Z[PMAX];
       real Ts;
-      const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(pg, tcol_s, s_lam2, s_inv, l, gi, a.key0, a.key1, cw,
+      const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(pg, tcol_s, s_lam2, s_inv, l, gi, a.key0, key1, cw,
                                                                     ts_given, Xt, Z, Ts);
       const real lw2 = lw2s + lw2_extra;
       const bool ok = valid && (lw2 > (real)-1e30);  // F <= 0 (incompatible) gives NaN / -inf -> not ok
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
       const int l_begin = ch * a.chunk_len, l_end = min(a.L, l_begin + a.chunk_len);
       for (int l0 = l_begin; l0 < l_end; l0 += 32) {
         const int l = l0 + lane;
-        const uint4 rc = philox4x32_10((uint32_t)l, gi, 64u, cw, a.key0, a.key1);
+        const uint4 rc = philox4x32_10((uint32_t)l, gi, 64u, cw, a.key0, key1);
         const real u = cond_uniform<real>(rc, 0);
         int cidx = 0;
         for (int k = 0; k < p; ++k) cidx += (s_cdf[w][k] <= u) ? 1 : 0;  // broadcast reads
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
 #pragma unroll
           for (int k = 0; k < PMAX; ++k) {
             if (k < p) {
-              if ((k & 3) == 0) rc = philox4x32_10((uint32_t)l, gi, 64u + (uint32_t)(k >> 2), cw, a.key0, a.key1);
+              if ((k & 3) == 0) rc = philox4x32_10((uint32_t)l, gi, 64u + (uint32_t)(k >> 2), cw, a.key0, key1);
               const uint32_t bits = (k & 3) == 0 ? rc.x : ((k & 3) == 1 ? rc.y : ((k & 3) == 2 ? rc.z : rc.w));
               Xt ^= (bits < eps_thr) ? (1u << k) : 0u;
             }

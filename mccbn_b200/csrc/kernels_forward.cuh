@@ -40,10 +40,17 @@ struct FwdArgs {
   int chunk_len;             // samples per chunk (multiple of 32)
   long long n_items;         // N * chunks
   long long obs_offset;      // global index of local observation 0
-  uint32_t key0, key1;       // Philox key (seed, iteration tag)
+  uint32_t key0, key1;       // Philox key (seed, iteration tag); the iteration field of key1 is taken from
+                             // model->iter on the device (iter_key), so that a captured CUDA graph of one EM iteration
+                             // can be replayed
   uint32_t cw;               // Philox counter word 3 (evaluation / candidate id)
   int PS;                    // record stride = kStatHdr + p
 };
+
+// key word 1 = (EM iteration << 4) | purpose (make_key, philox.cuh); the iteration is read from the model on the device
+__device__ __forceinline__ uint32_t iter_key(const uint32_t key1, const DevModel* __restrict__ mdl) {
+  return ((uint32_t)mdl->iter << 4) | (key1 & 0xFu);
+}
 
 template <typename real>
 struct RealTraits;
@@ -304,6 +311,7 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog&
   const long long gw = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * kWarps;
   const int flip = mdl->flip;
+  const uint32_t key1 = iter_key(a.key1, mdl);
 
   for (long long item = gw; item < a.n_items; item += nw) {
     const int i = (int)(item / a.chunks);
@@ -325,7 +333,7 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog&
       const bool valid = l < l_end;
       word_t X;
       real Ts;
-      sampler(pg, tcol_s, zrow_s, (uint32_t)l, gi, a.key0, a.key1, a.cw, ts_given, scale, X, Ts);
+      sampler(pg, tcol_s, zrow_s, (uint32_t)l, gi, a.key0, key1, a.cw, ts_given, scale, X, Ts);
       const int d = popc_word((word_t)(X ^ yt));
       const int de = flip ? p - d : d;  // weights decrease in `de`
       const int dmin = __reduce_min_sync(0xffffffffu, valid ? de : (1 << 19));

@@ -38,8 +38,10 @@ constexpr int kPoolTile = 64;    // pool entries per shared-memory tile
 template <int PMAX>
 __global__ void __launch_bounds__(kFwdBlock) pool_generate_kernel(float* __restrict__ Tp, uint32_t* __restrict__ Mp,
                                                                   float* __restrict__ Zp, int K, uint32_t key0,
-                                                                  uint32_t key1, uint32_t cw,
+                                                                  uint32_t key1_purpose, uint32_t cw,
+                                                                  const DevModel* __restrict__ mdl,
                                                                   const __grid_constant__ PosetProg pg) {
+  const uint32_t key1 = iter_key(key1_purpose, mdl);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_T = reinterpret_cast<float*>(smem_raw);
   using ZS = ZStage<float, PMAX>;
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a
   const int p = pg.p;
   for (int t = threadIdx.x; t < kRtabN; t += kPoolBlock) s_rtab[t] = mdl->rtab[t];
   const int flip = mdl->flip;
+  const uint32_t key1 = iter_key(a.key1, mdl);
   const int ch = blockIdx.y;
   const int i = blockIdx.x * kPoolBlock + threadIdx.x;
   const bool live = i < a.N;
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a
       float Ts = ts_given;
       if (!TIMES_GIVEN) {
         const int k = k0 + kk;
-        if ((kk & 3) == 0) r = philox4x32_10((uint32_t)(k >> 2), gi, 0u, a.cw, a.key0, a.key1);
+        if ((kk & 3) == 0) r = philox4x32_10((uint32_t)(k >> 2), gi, 0u, a.cw, a.key0, key1);
         const uint32_t bits = (kk & 3) == 0 ? r.x : ((kk & 3) == 1 ? r.y : ((kk & 3) == 2 ? r.z : r.w));
         Ts = fast_lg2(u01_open0(bits)) * cs;
       }
