@@ -254,6 +254,10 @@ int mccbn_set_jit(mccbn_ctx* ctx, int mode);
  * output, source = generated CUDA text (either may be NULL) */
 int mccbn_jit_compile_forward(const int* poset, int p, int times_given, size_t* cubin_bytes, double* compile_ms,
                               char* log, size_t loglen, char* source, size_t sourcelen, char* err, size_t errlen);
+/* the same for the conditional-proposal kernels; mode: 0 backward, 1 bernoulli, 2 OT-CBN, 3 add-remove */
+int mccbn_jit_compile_conditional(const int* poset, int p, int times_given, int mode, size_t* cubin_bytes,
+                                  double* compile_ms, char* log, size_t loglen, char* source, size_t sourcelen,
+                                  char* err, size_t errlen);
 
 /* Host-only test seam for the poset edit operations the annealer uses (Model::add_edge, remove_edge, add_relation,
  * remove_relation, transitive_reduction_dag, swap_node; src/model_impl.cpp:145-316; the reference exposes the

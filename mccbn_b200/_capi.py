@@ -41,7 +41,7 @@ SYMBOLS = [
     "mccbn_neighbors", "mccbn_initialize_lambda", "mccbn_forward_from_times", "mccbn_estep_forward_from_times",
     "mccbn_conditional_from_uniforms", "mccbn_problem_create", "mccbn_problem_destroy", "mccbn_problem_set_model",
     "mccbn_problem_em_iterations", "mccbn_problem_read", "mccbn_problem_stream", "mccbn_microbench_philox",
-    "mccbn_poset_edit", "mccbn_set_jit", "mccbn_jit_compile_forward", "mccbn_sample_genotypes", "mccbn_sample_times",
+    "mccbn_poset_edit", "mccbn_set_jit", "mccbn_jit_compile_forward", "mccbn_jit_compile_conditional", "mccbn_sample_genotypes", "mccbn_sample_times",
     "mccbn_generate_genotypes", "mccbn_scale_path_to_mutation", "mccbn_cbn_density_log",
     "mccbn_complete_log_likelihood", "mccbn_draw_sample", "mccbn_coin_tossing", "mccbn_generate_mutation_times",
 ]

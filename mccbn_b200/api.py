@@ -462,6 +462,20 @@ def generate_mutation_times(obs, poset, lambda_, times=None, lambda_s=1.0, seed=
     return dict(Tdiff=T, proposal_density=dens, sampling_time=ts)
 
 
+def jit_compile_conditional(poset, mode=0, times_given=False):
+    """Host-only: generate + compile the specialised conditional-proposal kernel of a poset (mode 0 backward,
+    1 bernoulli, 2 OT-CBN, 3 add-remove); returns dict(cubin_bytes, ms, log, source)."""
+    poset = i32(poset)
+    n, ms = C.c_size_t(0), C.c_double(0)
+    log = C.create_string_buffer(1 << 16)
+    src = C.create_string_buffer(1 << 18)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_jit_compile_conditional(ptr(poset), poset.shape[0], int(times_given), int(mode), C.byref(n),
+                                                     C.byref(ms), log, C.c_size_t(len(log)), src, C.c_size_t(len(src)),
+                                                     *e.args))
+    return dict(cubin_bytes=n.value, ms=ms.value, log=log.value.decode(), source=src.value.decode())
+
+
 POSET_OPS = dict(add_edge=0, remove_edge=1, add_relation=2, remove_relation=3, transitive_reduction=4, swap_node=5)
 
 

@@ -133,9 +133,16 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.PS = PS();
     const int warps_per_block = kFwdBlock / 32;
     long long blocks = (n_items + warps_per_block - 1) / warps_per_block;
+    JitKernel* jkc = precision == 1 ? nullptr : resolve_jit_cond(flat[c], times_given, mode, (double)N * (double)a.L);
     // one resident wave: MCCBN_COND_MINB blocks per SM for the fp32 kernels, 1 for the fp64 validation mode
-    grid_x = (int)std::max(1LL, std::min<long long>(blocks, (long long)ctx->sm_count * (precision == 1 ? 1 : MCCBN_COND_MINB)));
-    if (precision == 1) {
+    const int per_sm = jkc ? jkc->blocks_per_sm : (precision == 1 ? 1 : MCCBN_COND_MINB);
+    grid_x = (int)std::max(1LL, std::min<long long>(blocks, (long long)ctx->sm_count * per_sm));
+    if (jkc) {
+      PosetProg pgc = build_prog(flat[c], jkc->pmax, 4);
+      CondArgs args = a;
+      void* params[] = {(void*)&args, (void*)&pgc};
+      MCCBN_CUDA(cudaLaunchKernel((const void*)jkc->kern, dim3(grid_x), dim3(kFwdBlock), params, 0, s));
+    } else if (precision == 1) {
       CondLauncher::go<double, 32>(a, flat[c], times_given, mode, grid_x, s);
     } else if (p <= 16) {
       CondLauncher::go<float, 16>(a, flat[c], times_given, mode, grid_x, s);
@@ -1435,6 +1442,28 @@ int mccbn_jit_compile_forward(const int* poset, int p, int times_given, size_t* 
   flatten_or_throw(poset, p, P, f);
   static NvrtcApi rtc;
   const std::string src = generate_forward_source(f, times_given != 0, jit_default_minb());
+  if (source && sourcelen) std::snprintf(source, sourcelen, "%s", src.c_str());
+  JitCompiled cc;
+  const bool ok = jit_compile(rtc, src, cc);
+  if (log && loglen) std::snprintf(log, loglen, "%s", cc.log.c_str());
+  if (cubin_bytes) *cubin_bytes = cc.cubin.size();
+  if (compile_ms) *compile_ms = cc.compile_ms;
+  if (!ok) throw Error(MCCBN_ERR_CUDA, "NVRTC compilation failed: " + cc.log);
+  MCCBN_CATCH
+}
+
+// the same for the conditional-proposal kernels; mode: 0 backward, 1 bernoulli, 2 OT-CBN, 3 add-remove
+int mccbn_jit_compile_conditional(const int* poset, int p, int times_given, int mode, size_t* cubin_bytes,
+                                  double* compile_ms, char* log, size_t loglen, char* source, size_t sourcelen,
+                                  char* err, size_t errlen) {
+  MCCBN_TRY
+  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the conditional kernels support p <= 32");
+  if (mode < 0 || mode > 3) throw Error(MCCBN_ERR_ARG, "mode must be 0..3");
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  static NvrtcApi rtc;
+  const std::string src = generate_cond_source(f, times_given != 0, mode, JitCache::cond_minb());
   if (source && sourcelen) std::snprintf(source, sourcelen, "%s", src.c_str());
   JitCompiled cc;
   const bool ok = jit_compile(rtc, src, cc);

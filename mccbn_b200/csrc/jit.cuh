@@ -27,6 +27,7 @@
 #include "_embedded_sources.inc"
 #include "engine.cuh"
 #include "kernels_forward.cuh"
+#include "kernels_cond.cuh"
 
 namespace mccbn {
 
@@ -237,6 +238,71 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
   return s.str();
 }
 
+// ---- conditional proposal (backward / bernoulli / OT-CBN / add-remove): the same idea for estep_conditional_body ----
+// Same random stream and arithmetic as sample_conditional (kernels_cond.cuh): uniform ui = k (+1 when the sampling
+// time is drawn) is word ui % 4 of Philox block ui / 4.
+static std::string generate_cond_source(const FlatPoset& f, bool times_given, int mode, int minb) {
+  const int p = f.p, pmax = jit_pmax(p);
+  std::ostringstream s;
+  s << "#include \"kernels_cond.cuh\"\n"
+       "namespace mccbn {\n"
+       "struct SpecCondSampler {\n"
+       "  static constexpr bool kStagesT = false;\n"
+       "  __device__ __forceinline__ float operator()(const PosetProg& pg, const uint32_t tcol_s,\n"
+       "      const float* __restrict__ s_lam2, const float* __restrict__ s_inv, const uint32_t l, const uint32_t gi,\n"
+       "      const uint32_t k0, const uint32_t k1, const uint32_t cw, const float ts_given, const uint32_t Xt,\n"
+       "      float (&Z)[" << pmax << "], float& Ts_out) const {\n"
+       "    float Ts = ts_given;\n"
+       "    float lw2 = 0.0f;\n";
+  const char* comp[4] = {".x", ".y", ".z", ".w"};
+  int generated = 0;
+  auto need_block = [&](int b) {
+    while (generated <= b) {
+      s << "    const uint4 r" << generated << " = philox4x32_10(l, gi, " << generated << "u, cw, k0, k1);\n";
+      ++generated;
+    }
+  };
+  if (!times_given) {
+    need_block(0);
+    s << "    Ts = CondMath<float>::z_of(CondMath<float>::u01(r0.x), 1.0f, s_inv[" << pmax << "]);\n";
+  }
+  for (int k = 0; k < p; ++k) {
+    const int ui = k + (times_given ? 0 : 1);
+    need_block(ui / 4);
+    std::vector<std::string> terms;
+    for (uint64_t m = f.parent_pos[k]; m; m &= m - 1) terms.push_back("t" + std::to_string(ctz64(m)));
+    while (terms.size() > 1) {
+      std::vector<std::string> nxt;
+      for (size_t i = 0; i + 1 < terms.size(); i += 2) nxt.push_back("fmaxf(" + terms[i] + ", " + terms[i + 1] + ")");
+      if (terms.size() & 1) nxt.push_back(terms.back());
+      terms.swap(nxt);
+    }
+    const std::string K = std::to_string(k);
+    s << "    const float m" << K << " = " << (terms.empty() ? "0.0f" : terms[0]) << ";\n"
+      << "    const bool x" << K << " = (Xt >> " << K << ") & 1u;\n"
+      << "    const float a" << K << " = Ts - m" << K << ";\n"
+      << "    const float Fx" << K << " = CondMath<float>::F_of(a" << K << ", s_lam2[" << K << "]);\n"
+      << "    const float z" << K << " = CondMath<float>::z_of(CondMath<float>::u01(r" << (ui / 4) << comp[ui % 4] << "), x" << K
+      << " ? Fx" << K << " : 1.0f, s_inv[" << K << "]);\n"
+      << "    const float t" << K << " = (x" << K << " ? m" << K << " : fmaxf(m" << K << ", Ts)) + z" << K << ";\n"
+      << "    Z[" << K << "] = t" << K << " - m" << K << ";\n"
+      << "    lw2 += x" << K << " ? CondMath<float>::lg2(Fx" << K << ") : -s_lam2[" << K << "] * fmaxf(a" << K << ", 0.0f);\n";
+  }
+  for (int k = p; k < pmax; ++k) s << "    Z[" << k << "] = 0.0f;\n";
+  s << "    Ts_out = Ts;\n"
+       "    return lw2;\n"
+       "  }\n"
+       "};\n"
+       "}  // namespace mccbn\n"
+       "extern \"C\" __global__ void __launch_bounds__(mccbn::kFwdBlock, "
+    << minb << ") mccbn_cond_spec(const mccbn::CondArgs a,\n"
+       "    const __grid_constant__ mccbn::PosetProg pg) {\n"
+       "  mccbn::estep_conditional_body<float, " << pmax << ", " << (times_given ? "true" : "false") << ", " << mode
+    << ">(a, pg, mccbn::SpecCondSampler{});\n"
+       "}\n";
+  return s.str();
+}
+
 struct JitCompiled {
   std::vector<char> cubin;
   std::string log;
@@ -249,11 +315,11 @@ static bool jit_compile(NvrtcApi& rtc, const std::string& src, JitCompiled& out)
     out.log = "libnvrtc.so.12 could not be loaded";
     return false;
   }
-  const char* hdr_src[] = {kSrc_device_types_cuh, kSrc_philox_cuh, kSrc_kernels_forward_cuh};
-  const char* hdr_name[] = {"device_types.cuh", "philox.cuh", "kernels_forward.cuh"};
+  const char* hdr_src[] = {kSrc_device_types_cuh, kSrc_philox_cuh, kSrc_kernels_forward_cuh, kSrc_kernels_cond_cuh};
+  const char* hdr_name[] = {"device_types.cuh", "philox.cuh", "kernels_forward.cuh", "kernels_cond.cuh"};
   NvrtcApi::program_t prog = nullptr;
   const auto t0 = std::chrono::steady_clock::now();
-  int rc = rtc.CreateProgram(&prog, src.c_str(), "mccbn_fwd_spec.cu", 3, hdr_src, hdr_name);
+  int rc = rtc.CreateProgram(&prog, src.c_str(), "mccbn_spec.cu", 4, hdr_src, hdr_name);
   if (rc != 0) {
     out.log = std::string("nvrtcCreateProgram: ") + rtc.GetErrorString(rc);
     return false;
@@ -318,8 +384,10 @@ static std::string jit_cache_path(const std::string& src) {
     made = dir;
   }
   char name[64];
-  std::snprintf(name, sizeof name, "/fwd_%016llx.cubin", (unsigned long long)fnv1a64(src + kSrc_kernels_forward_cuh + kSrc_philox_cuh + kSrc_device_types_cuh +
-                                                    (std::getenv("MCCBN_JIT_PTXAS_O") ? std::getenv("MCCBN_JIT_PTXAS_O") : "")));
+  std::snprintf(name, sizeof name, "/spec_%016llx.cubin",
+                (unsigned long long)fnv1a64(src + kSrc_kernels_forward_cuh + kSrc_kernels_cond_cuh + kSrc_philox_cuh +
+                                            kSrc_device_types_cuh +
+                                            (std::getenv("MCCBN_JIT_PTXAS_O") ? std::getenv("MCCBN_JIT_PTXAS_O") : "")));
   return dir + name;
 }
 
@@ -337,14 +405,31 @@ struct JitCache {
 
   // `only_if_cached`: do not compile, return the kernel only if it is already in memory or on disk
   JitKernel* get(const FlatPoset& f, bool times_given, bool only_if_cached = false) {
-    const std::string key = jit_key(f, times_given, minb);
+    return get_kernel(jit_key(f, times_given, minb), [&] { return generate_forward_source(f, times_given, minb); },
+                      "mccbn_fwd_spec", /*forward=*/true, f.p, only_if_cached);
+  }
+  // conditional-proposal kernels (mode = CondMode); they keep their scales in shared memory, no __constant__ symbol
+  JitKernel* get_cond(const FlatPoset& f, bool times_given, int mode, bool only_if_cached = false) {
+    const int mb = cond_minb();
+    return get_kernel("c" + std::to_string(mode) + jit_key(f, times_given, mb),
+                      [&] { return generate_cond_source(f, times_given, mode, mb); }, "mccbn_cond_spec",
+                      /*forward=*/false, f.p, only_if_cached);
+  }
+  static int cond_minb() {
+    if (const char* e = std::getenv("MCCBN_JIT_COND_MINB")) return std::max(1, std::min(8, std::atoi(e)));
+    return 2;  // cfg 5 backward: 2 / 3 / 4 resident blocks = 3.18 / 3.67 / 15.1 ms (4 blocks: 128 registers, spills in the loop)
+  }
+
+  template <typename SrcFn>
+  JitKernel* get_kernel(const std::string& key, SrcFn make_src, const char* kname, bool forward, int p,
+                        bool only_if_cached) {
     auto it = kernels.find(key);
     if (it != kernels.end()) return it->second.ok ? &it->second : nullptr;
     if (only_if_cached) {
       // this lookup sits on the per-iteration path of small problems: remember that the disk cache has no kernel for
       // this poset instead of regenerating and hashing the source every time
       if (disk_misses.count(key)) return nullptr;
-      const std::string p0 = jit_cache_path(generate_forward_source(f, times_given, minb));
+      const std::string p0 = jit_cache_path(make_src());
       FILE* fp = p0.empty() ? nullptr : std::fopen(p0.c_str(), "rb");
       if (!fp) {
         if (disk_misses.size() > 4096) disk_misses.clear();
@@ -355,7 +440,7 @@ struct JitCache {
     }
     JitKernel jk;
     JitCompiled cc;
-    const std::string src = generate_forward_source(f, times_given, minb);
+    const std::string src = make_src();
     const std::string path = jit_cache_path(src);
     bool have = false;
     if (!path.empty()) {
@@ -384,19 +469,20 @@ struct JitCache {
     }
     if (have) {
       cudaError_t e = cudaLibraryLoadData(&jk.lib, cc.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-      if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.kern, jk.lib, "mccbn_fwd_spec");
-      size_t bytes = 0;
-      if (e == cudaSuccess) e = cudaLibraryGetGlobal(&jk.scale_sym, &bytes, jk.lib, "_ZN5mccbn7c_scaleE");
+      if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.kern, jk.lib, kname);
+      size_t bytes = sizeof(FwdScale);
+      if (e == cudaSuccess && forward) e = cudaLibraryGetGlobal(&jk.scale_sym, &bytes, jk.lib, "_ZN5mccbn7c_scaleE");
       if (e == cudaSuccess && bytes == sizeof(FwdScale)) {
         jk.ok = true;
-        jk.pmax = jit_pmax(f.p);
-        jk.smem = (size_t)(((jk.pmax / 4) | 1) * 16) * kFwdBlock;  // ZStage<float, pmax>::kRowBytes per thread
+        jk.pmax = jit_pmax(p);
+        // forward: ZStage<float, pmax>::kRowBytes per thread of dynamic shared memory; conditional: static only
+        jk.smem = forward ? (size_t)(((jk.pmax / 4) | 1) * 16) * kFwdBlock : 0;
         jk.compile_ms = cc.compile_ms;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)jk.kern, kFwdBlock, jk.smem) != cudaSuccess ||
             nb <= 0) {
           cudaGetLastError();
-          nb = minb;  // the launch bound the kernel was compiled for
+          nb = forward ? minb : cond_minb();  // the launch bound the kernel was compiled for
         }
         if (const char* e = std::getenv("MCCBN_JIT_RESIDENT")) nb = std::max(1, std::min(nb, std::atoi(e)));
         jk.blocks_per_sm = nb;
@@ -409,9 +495,8 @@ struct JitCache {
       std::fprintf(stderr, "mccbn_b200: NVRTC specialisation failed, using the generic kernel\n%s\n", cc.log.c_str());
     }
     if (std::getenv("MCCBN_JIT_VERBOSE"))
-      std::fprintf(stderr, "mccbn_b200: specialised forward kernel p=%d %s: %s in %.0f ms\n%s\n", f.p,
-                   times_given ? "times given" : "times sampled", jk.ok ? "compiled" : "FAILED", cc.compile_ms,
-                   cc.log.c_str());
+      std::fprintf(stderr, "mccbn_b200: specialised kernel %s p=%d: %s in %.0f ms\n%s\n", kname, p,
+                   jk.ok ? "compiled" : "FAILED", cc.compile_ms, cc.log.c_str());
     auto res = kernels.emplace(key, jk);
     return res.first->second.ok ? &res.first->second : nullptr;
   }

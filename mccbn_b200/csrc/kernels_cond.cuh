@@ -125,13 +125,28 @@ __device__ __forceinline__ bool compatible_topo(const PosetProg& pg, const uint3
   return bad == 0u;
 }
 
-template <typename real, int PMAX, bool TIMES_GIVEN, int MODE>
 #ifndef MCCBN_COND_MINB
 #define MCCBN_COND_MINB 4  // resident blocks per SM (ncu r1e: 2 blocks left the schedulers at IPC 0.9 of 2.5)
 #endif
-__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB : 1)
-    estep_conditional_kernel(const CondArgs a, const __grid_constant__ PosetProg pg) {
-  __shared__ real s_T[(PMAX + 1) * kFwdBlock];
+
+// The generic sampler interprets the poset program at run time (event times staged in shared memory); a
+// poset-specialised sampler generated by jit.cuh has the same call signature with the poset unrolled into straight-line
+// code (event times in registers, no parent loads / stores).
+template <typename real, int PMAX, bool TIMES_GIVEN>
+struct GenericCondSampler {
+  static constexpr bool kStagesT = true;
+  __device__ __forceinline__ real operator()(const PosetProg& pg, const uint32_t tcol_s, const real* __restrict__ s_lam2,
+                                             const real* __restrict__ s_inv, const uint32_t l, const uint32_t gi,
+                                             const uint32_t k0, const uint32_t k1, const uint32_t cw, const real ts_given,
+                                             const uint32_t Xt, real (&Z)[PMAX], real& Ts_out) const {
+    return sample_conditional<real, PMAX, TIMES_GIVEN>(pg, tcol_s, s_lam2, s_inv, l, gi, k0, k1, cw, ts_given, Xt, Z,
+                                                       Ts_out);
+  }
+};
+
+template <typename real, int PMAX, bool TIMES_GIVEN, int MODE, typename Sampler>
+__device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const PosetProg& pg, const Sampler sampler) {
+  __shared__ real s_T[Sampler::kStagesT ? (PMAX + 1) * kFwdBlock : 1];
   __shared__ real s_lam2[PMAX + 1];
   __shared__ real s_inv[PMAX + 1];
   __shared__ real s_lpyx2[68];  // log2 P(Y|X) by Hamming distance
@@ -149,8 +164,8 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
   const int p = pg.p;
   const int lane = threadIdx.x & 31;
   constexpr int kWarps = kFwdBlock / 32;
-  s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;  // dummy parent row
-  const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
+  if (Sampler::kStagesT) s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;  // dummy parent row
+  const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + (Sampler::kStagesT ? threadIdx.x : 0));
   const double kLog2e = 1.44269504088896340736;
 
   for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock) {
@@ -165,7 +180,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
       // log_bernoulli_process (src/mcem_hcbn.cpp:84-100), incl. the eps == 0 special case
       const double eps = mdl->eps;
       if (eps == 0.0)
-        lp = d ? log(eps + DBL_EPSILON) * d + log1p(-eps - DBL_EPSILON) * (p - d) : 0.0;
+        lp = d ? log(eps + 2.2204460492503131e-16 /* DBL_EPSILON */) * d + log1p(-eps - 2.2204460492503131e-16 /* DBL_EPSILON */) * (p - d) : 0.0;
       else
         lp = log(eps) * d + log1p(-eps) * (p - d);
     }
@@ -214,8 +229,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
     auto consume = [&](const uint32_t l, const uint32_t Xt, const int d, const bool valid, const real lw2_extra) {
       real Z[PMAX];
       real Ts;
-      const real lw2s = sample_conditional<real, PMAX, TIMES_GIVEN>(pg, tcol_s, s_lam2, s_inv, l, gi, a.key0, key1, cw,
-                                                                    ts_given, Xt, Z, Ts);
+      const real lw2s = sampler(pg, tcol_s, s_lam2, s_inv, l, gi, a.key0, key1, cw, ts_given, Xt, Z, Ts);
       const real lw2 = lw2s + lw2_extra;
       const bool ok = valid && (lw2 > (real)-1e30);  // F <= 0 (incompatible) gives NaN / -inf -> not ok
       if (ok && lw2 > mref) {  // rare after the first few samples: move the reference up (with head-room)
@@ -362,7 +376,7 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
       out[2] = v2;
       out[3] = v3;
       // natural-log scale of this record: true weights = exp(lscale) * relative weights
-      out[4] = (mmax > (real)-1e29) ? (double)mmax * 0.693147180559945309417 + lscale_extra : -INFINITY;
+      out[4] = (mmax > (real)-1e29) ? (double)mmax * 0.693147180559945309417 + lscale_extra : -__longlong_as_double(0x7ff0000000000000LL) /* -inf */;
     }
     double mine = 0.0;
 #pragma unroll
@@ -376,6 +390,12 @@ __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB
     }
     if (lane < p) out[kStatHdr + lane] = mine;
   }
+}
+
+template <typename real, int PMAX, bool TIMES_GIVEN, int MODE>
+__global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? MCCBN_COND_MINB : 1)
+    estep_conditional_kernel(const CondArgs a, const __grid_constant__ PosetProg pg) {
+  estep_conditional_body<real, PMAX, TIMES_GIVEN, MODE>(a, pg, GenericCondSampler<real, PMAX, TIMES_GIVEN>{});
 }
 
 }  // namespace mccbn

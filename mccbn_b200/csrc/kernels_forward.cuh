@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpAr
   }
 }
 
+#ifndef __CUDACC_RTC__  // not part of the NVRTC-specialised modules
 // generate_genotypes (src/mcem_hcbn.cpp:215-236): X_kj = [T_sum(k, j) <= T_s(k)]; T_s ~ Exp(lambda_s) unless given.
 // One thread per row; T_sum is N x p column-major by event id, the output an N x p int matrix.
 __global__ void generate_genotypes_kernel(const double* __restrict__ T_sum, double* __restrict__ T_sampling,
@@ -484,5 +485,7 @@ __global__ void generate_genotypes_kernel(const double* __restrict__ T_sum, doub
     for (int j = 0; j < p; ++j) samples[(size_t)j * N + i] = T_sum[(size_t)j * N + i] <= ts ? 1 : 0;
   }
 }
+
+#endif  // __CUDACC_RTC__
 
 }  // namespace mccbn

@@ -252,6 +252,20 @@ struct mccbn_problem {
     return ctx->jit->get(f, times_given, /*only_if_cached=*/mode < 0 && !worth);
   }
 
+  // the same policy for the conditional-proposal kernels (backward / bernoulli / OT-CBN / add-remove)
+  JitKernel* resolve_jit_cond(const FlatPoset& f, bool times_given, int mode, double samples_per_estep) {
+    int jm = ctx->jit_mode;
+    if (jm < 0) {
+      const char* e = std::getenv("MCCBN_JIT");
+      if (e && std::strcmp(e, "0") == 0) jm = 0;
+      else if (e && std::strcmp(e, "1") == 0) jm = 1;
+    }
+    if (jm == 0) return nullptr;
+    if (!ctx->jit) ctx->jit = new JitCache();
+    const bool worth = samples_per_estep * (double)std::max(1, expected_esteps) >= 5e9;
+    return ctx->jit->get_cond(f, times_given, mode, /*only_if_cached=*/jm < 0 && !worth);
+  }
+
   void launch_forward_jit(JitKernel* jk, const FwdArgs& a, const FlatPoset& f, int c, int grid) {
     cudaStream_t s = ctx->stream;
     MCCBN_CUDA(cudaMemcpyAsync(jk->scale_sym, scales.ptr + c, sizeof(FwdScale), cudaMemcpyDeviceToDevice, s));

@@ -36,3 +36,35 @@ def test_specialised_mcem_matches_generic():
         mc.set_jit(-1)
     np.testing.assert_allclose(j["lambda_"], g["lambda_"], rtol=1e-4)
     assert abs(j["eps"] - g["eps"]) < 1e-5 and abs(j["llhood"] - g["llhood"]) < 1e-3 * abs(g["llhood"])
+
+
+@pytest.mark.parametrize("sampling,p,kw", [("backward", 9, dict(neighborhood_dist=1)), ("backward", 25, dict(neighborhood_dist=1)),
+                                           ("bernoulli", 14, {}), ("add-remove", 20, {})])
+def test_specialised_conditional_equals_generic(sampling, p, kw):
+    """NVRTC poset-specialised conditional-proposal kernel: same Philox stream and arithmetic as the generic kernel"""
+    c = synth.make_config(p, 40, eps=0.0 if sampling == "bernoulli" else 0.06, seed=p, density=0.2)
+    L = 26 * 20 if sampling == "backward" else 640
+    try:
+        mc.set_jit(0)
+        g = mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.07, sampling=sampling, seed=11, **kw)
+        mc.set_jit(1)
+        j = mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.07, sampling=sampling, seed=11, **kw)
+    finally:
+        mc.set_jit(-1)
+    for k in ("w", "w_sqrt", "dist", "Tdiff"):
+        np.testing.assert_allclose(j[k], g[k], rtol=1e-5, atol=1e-30, err_msg=k)
+    if "L_eff" in g:
+        assert np.array_equal(j["L_eff"], g["L_eff"])
+
+
+def test_specialised_otcbn_matches_generic():
+    c = synth.make_config(10, 200, eps=0.0, seed=4, density=0.25)
+    kw = dict(max_iter=30, nrOfSamples=8, seed=5)
+    try:
+        mc.set_jit(0)
+        g = mc.estimate_mutation_rates(c["poset"], c["obs"], **kw)
+        mc.set_jit(1)
+        j = mc.estimate_mutation_rates(c["poset"], c["obs"], **kw)
+    finally:
+        mc.set_jit(-1)
+    np.testing.assert_allclose(j["lambda_"], g["lambda_"], rtol=1e-4)
