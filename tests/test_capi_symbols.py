@@ -106,3 +106,19 @@ def test_jit_source_generation_and_nvrtc_compile():
     assert r["source"].count("(uint64_t)0xD2511F53u") == 10 * 2  # 10 uniforms of 24 bits = 2 Philox blocks x 10 rounds
     assert r["source"].count("fmaxf(") == sum(max(0, int(d) - 1) for d in c["poset"].sum(axis=0))  # |E| - #non-roots
     assert "registers" in r["log"]
+
+
+def test_jit_conditional_source_generation_and_nvrtc_compile():
+    """the conditional-proposal specialisation (backward / bernoulli / OT-CBN / add-remove) is a pure compiler step too"""
+    c = synth.make_config(9, 5, seed=2, density=0.3)
+    for mode in (0, 3):
+        try:
+            r = mc.jit_compile_conditional(c["poset"], mode=mode)
+        except mc.MccbnError as e:
+            if "could not be loaded" in str(e):
+                pytest.skip("libnvrtc not available")
+            raise
+        assert r["cubin_bytes"] > 10000
+        assert "mccbn_cond_spec" in r["source"] and f"estep_conditional_body<float, 12, false, {mode}>" in r["source"]
+        assert r["source"].count("CondMath<float>::z_of(") == 9 + 1  # one draw per event + the sampling time
+        assert "spill stores" in r["log"]
