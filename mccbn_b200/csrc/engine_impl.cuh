@@ -826,8 +826,10 @@ int mccbn_importance_weight_genotype(mccbn_ctx* c, const int* genotype, unsigned
 // ---- forward simulators (src/mcem_hcbn.cpp:1012-1120): the generative model on the device -----------------------
 // One sample per thread through the fp64 forward sampler (53-bit uniforms): Z ~ Exp(lambda), T_s ~ Exp(lambda_s) unless
 // given, T_j = Z_j + max parents, X_j = [T_j <= T_s].  All outputs optional.
+// `given_times` != nullptr: the genotypes are formed on the device against the caller's per-sample sampling times.
 static void simulate_forward(mccbn_ctx* c, unsigned N, const int* poset, const double* lambda, int p, float lambda_s,
-                             int seed, double* T_sampling /* out */, int* samples, double* Tdiff, double* T_sum) {
+                             int seed, double* T_sampling /* out */, int* samples, double* Tdiff, double* T_sum,
+                             const double* given_times = nullptr) {
   if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox samplers support p <= 32");
   if (N == 0) return;
   Poset P;
@@ -849,7 +851,7 @@ static void simulate_forward(mccbn_ctx* c, unsigned N, const int* poset, const d
   std::memset(&a, 0, sizeof(a));
   a.model = pb.models.ptr;
   a.Z_out = dZ.ensure((size_t)N * p);
-  a.T_out = T_sum ? dT.ensure((size_t)N * p) : nullptr;
+  a.T_out = (T_sum || given_times) ? dT.ensure((size_t)N * p) : nullptr;
   a.dist_out = dD.ensure(N);
   a.X_out = dX.ensure(N);
   a.Ts_out = dTs.ensure(N);
@@ -864,6 +866,21 @@ static void simulate_forward(mccbn_ctx* c, unsigned N, const int* poset, const d
   forward_dump_kernel<double, 32, false><<<grid, kFwdBlock, sm, s>>>(a, pg);
   c->launches++;
   MCCBN_CUDA(cudaGetLastError());
+  if (given_times) {  // X_j = [T_j <= t_i] on the device (generate_genotypes_kernel)
+    DevBuf<double> dGiven;
+    DevBuf<int> dS;
+    MCCBN_CUDA(cudaMemcpyAsync(dGiven.ensure(N), given_times, sizeof(double) * N, cudaMemcpyHostToDevice, s));
+    dS.ensure((size_t)N * p);
+    generate_genotypes_kernel<<<std::min(1024u, (N + 255u) / 256u), 256, 0, s>>>(dT.ptr, dGiven.ptr, dS.ptr, (int)N, p,
+                                                                               1.0, 1, 0u, 0u);
+    c->launches++;
+    MCCBN_CUDA(cudaGetLastError());
+    if (samples) MCCBN_CUDA(cudaMemcpyAsync(samples, dS.ptr, sizeof(int) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+    if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, dZ.ptr, sizeof(double) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+    if (T_sum) MCCBN_CUDA(cudaMemcpyAsync(T_sum, dT.ptr, sizeof(double) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+    MCCBN_CUDA(cudaStreamSynchronize(s));
+    return;
+  }
   std::vector<uint32_t> hx(N);
   std::vector<double> hts(N), hT;
   MCCBN_CUDA(cudaMemcpyAsync(hx.data(), dX.ptr, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, s));
@@ -884,13 +901,9 @@ int mccbn_sample_genotypes(mccbn_ctx* c, unsigned N, const int* poset, const dou
   MCCBN_TRY
   c = get_ctx(c);
   if (sampling_times_available) {
-    // X_j = [T_j <= t_i] with the caller's per-sample times: simulate the event times, compare on the host
+    // X_j = [T_j <= t_i] with the caller's per-sample times
     if (!T_sampling) throw Error(MCCBN_ERR_ARG, "sampling times expected");
-    std::vector<double> T((size_t)N * p);
-    simulate_forward(c, N, poset, lambda, p, lambda_s, seed, nullptr, nullptr, Tdiff, T.data());
-    if (samples)
-      for (unsigned i = 0; i < N; ++i)
-        for (int j = 0; j < p; ++j) samples[(size_t)j * N + i] = T[(size_t)j * N + i] <= T_sampling[i] ? 1 : 0;
+    simulate_forward(c, N, poset, lambda, p, lambda_s, seed, nullptr, samples, Tdiff, nullptr, T_sampling);
   } else {
     simulate_forward(c, N, poset, lambda, p, lambda_s, seed, T_sampling, samples, Tdiff, nullptr);
   }

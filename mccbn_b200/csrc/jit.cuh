@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <chrono>
@@ -379,8 +380,9 @@ static std::string jit_cache_path(const std::string& src) {
   else if (const char* h = std::getenv("HOME")) dir = std::string(h) + "/.cache/mccbn_b200";
   if (dir.empty() || dir == "off") return "";
   static std::string made;  // create the directory once per process, not once per lookup
-  if (made != dir) {
-    (void)!system(("mkdir -p '" + dir + "' 2>/dev/null").c_str());
+  if (made != dir) {  // mkdir -p
+    for (size_t i = 1; i <= dir.size(); ++i)
+      if (i == dir.size() || dir[i] == '/') ::mkdir(dir.substr(0, i).c_str(), 0755);
     made = dir;
   }
   char name[64];

@@ -138,6 +138,9 @@ static void optin_smem(K kernel, size_t bytes) {
 }  // namespace mccbn
 
 struct mccbn_problem {
+  mccbn_problem() = default;
+  mccbn_problem(const mccbn_problem&) = delete;  // owns device buffers and graph handles
+  mccbn_problem& operator=(const mccbn_problem&) = delete;
   mccbn_ctx* ctx = nullptr;
   int N = 0, p = 0;
   int64_t obs_offset = 0, N_global = 0;
