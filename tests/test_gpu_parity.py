@@ -322,6 +322,37 @@ def test_full_size_config2_properties():
     assert np.abs(out["lambda_"] / c["lambdas"] - 1).max() < 0.25 and abs(out["eps"] - 0.05) < 0.01
 
 
+def test_full_size_config3_properties():
+    """BASELINE config 3 (p=30, N=100,000, L=10,000: 1e9 samples per E-step) at full size, through properties that
+    do not need the oracle: determinism, independence of the kernel variant and of the sharding, weight bounds."""
+    c = synth.make_config(30, 100000, eps=0.05, seed=10)
+    N, L = 100000, 10000
+    ctx = mc.Context(0)
+    try:
+        mc.set_jit(1, ctx=ctx)
+        ll = mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], 0.05, L=L, seed=1, ctx=ctx)
+        assert ll == mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], 0.05, L=L, seed=1, ctx=ctx)  # deterministic
+        assert ll != mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], 0.05, L=L, seed=2, ctx=ctx)
+        # sharding: observations are independent and the Philox counters carry the global index
+        parts = [mc.obs_loglikelihood(c["obs"][lo:hi], c["poset"], c["lambdas"], 0.05, L=L, seed=1, ctx=ctx, obs_offset=lo)
+                 for lo, hi in ((0, 12500), (12500, 50000), (50000, 100000))]
+        assert abs(sum(parts) - ll) <= 1e-7 * abs(ll)   # fp32 per-lane sums depend on the chunking chosen for N
+        # the generic kernel draws the same samples: same estimate up to fp32 summation order
+        mc.set_jit(0, ctx=ctx)
+        ll_generic = mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], 0.05, L=L, seed=1, ctx=ctx)
+        assert abs(ll_generic - ll) <= 1e-7 * abs(ll)
+        # bounds: every observation's estimate of P(Y) lies between the smallest and the largest possible weight
+        mc.set_jit(1, ctx=ctx)
+        r = mc.importance_weight(c["obs"][:20000], L, c["poset"], c["lambdas"], 0.05, seed=1, ctx=ctx)
+        assert np.all(r["w"] / L >= 0.05 ** 30 * (1 - 1e-5)) and np.all(r["w"] / L <= 0.95 ** 30 * (1 + 1e-5))
+        assert np.all(np.isfinite(r["Tdiff"])) and np.all(r["Tdiff"] > 0) and np.all((r["dist"] >= 0) & (r["dist"] <= 30))
+        assert abs(np.log(r["w"] / L).sum() - parts[0] - mc.obs_loglikelihood(
+            c["obs"][12500:20000], c["poset"], c["lambdas"], 0.05, L=L, seed=1, ctx=ctx, obs_offset=12500)) <= 1e-6 * abs(ll)
+    finally:
+        mc.set_jit(-1, ctx=ctx)
+        ctx.close()
+
+
 def test_pool_given_times_matches_forward_exact():
     """pool with sampling times available: X_k = [T_k <= t_i]; estimate against the K2' matrix-exponential answer."""
     c = synth.make_config(6, 10, eps=0.1, seed=31, density=0.3)
