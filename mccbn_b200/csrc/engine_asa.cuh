@@ -68,6 +68,48 @@ static void score_candidates(mccbn_problem& pb, std::vector<Candidate*>& cands, 
       return;
     }
   }
+  // Several GPUs (candidate-parallel annealing, pb.local_only): rank r fits the candidates q with q % world == r; the
+  // fitted (llhood, eps, lambda) of all candidates are then shared by one sum-exchange (each entry is non-zero on exactly
+  // one rank, so the sum is exact and every rank continues with bit-identical scores).
+  const int world = pb.local_only ? pb.ctx->world : 1, rank = pb.local_only ? pb.ctx->rank : 0;
+  if (world > 1 && cands.size() > 1) {
+    std::vector<Candidate*> mine;
+    std::vector<uint32_t> mine_ids;
+    for (size_t q = 0; q < cands.size(); ++q)
+      if ((int)(q % (size_t)world) == rank) {
+        mine.push_back(cands[q]);
+        mine_ids.push_back(eval_ids[q]);
+      }
+    pb.local_only = false;  // the recursive call must not split again ...
+    struct Restore {
+      mccbn_problem& pb;
+      ~Restore() { pb.local_only = true; }
+    } restore{pb};
+    const int saved_world = pb.ctx->world;
+    pb.ctx->world = 1;      // ... and its EM iterations stay local
+    try {
+      if (!mine.empty()) score_candidates(pb, mine, mine_ids, scheme, L, ctl, times_given, seed, lambda_s, precision);
+    } catch (...) {
+      pb.ctx->world = saved_world;
+      throw;
+    }
+    pb.ctx->world = saved_world;
+    const int stride = pb.p + 2;
+    std::vector<double> all(cands.size() * (size_t)stride, 0.0);
+    for (size_t q = 0; q < cands.size(); ++q)
+      if ((int)(q % (size_t)world) == rank) {
+        all[q * stride] = cands[q]->llhood;
+        all[q * stride + 1] = cands[q]->eps;
+        for (int j = 0; j < pb.p; ++j) all[q * stride + 2 + j] = cands[q]->lambda[j];
+      }
+    pb.exchange_sum(all);
+    for (size_t q = 0; q < cands.size(); ++q) {
+      cands[q]->llhood = all[q * stride];
+      cands[q]->eps = all[q * stride + 1];
+      cands[q]->lambda.assign(all.begin() + q * stride + 2, all.begin() + (q + 1) * stride);
+    }
+    return;
+  }
   size_t done = 0;
   while (done < cands.size()) {
     const size_t n = std::min(cands.size() - done, (size_t)(kMaxCand - 1));
@@ -275,8 +317,10 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
     std::printf("Initial observed Log-likelihood:%g\nFraction of compatible observations: %g\n", llhood,
                 fraction_compatible);
   }
-  std::ofstream f_temp(ctl_asa.outdir + "asa.txt");
-  std::ofstream f_par(ctl_asa.outdir + "params.txt");
+  // candidate-parallel runs: all ranks walk the same trajectory, rank 0 writes the files
+  const bool writer = !(pb.local_only && pb.ctx->rank != 0);
+  std::ofstream f_temp(writer ? ctl_asa.outdir + "asa.txt" : std::string("/dev/null"));
+  std::ofstream f_par(writer ? ctl_asa.outdir + "params.txt" : std::string("/dev/null"));
   if (!f_temp || !f_par) throw Error(MCCBN_ERR_IO, "cannot open output files in '" + ctl_asa.outdir + "'");
   f_temp << "step\t llhood\t temperature\t acceptance rate" << std::endl;
   f_par << "step\t llhood\t epsilon\t lambdas" << std::endl;
@@ -288,7 +332,9 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
   // batch > 0: fixed speculative batch size; batch < 0: automatic with upper bound -batch -- start at 2, double after a
   // batch without an accepted move, fall back to (position of the accepted move + 1) after an acceptance
   const unsigned batch_cap = (unsigned)std::max(1, batch < 0 ? -batch : batch);
-  unsigned batch_now = batch < 0 ? std::min(2u, batch_cap) : batch_cap;
+  // candidate-parallel over several GPUs: a batch smaller than the number of ranks leaves GPUs idle
+  const unsigned batch_floor = pb.local_only ? std::min(batch_cap, (unsigned)pb.ctx->world) : 1u;
+  unsigned batch_now = batch < 0 ? std::max(batch_floor, std::min(2u, batch_cap)) : batch_cap;
   unsigned iter = 1;
   while (iter < ctl_asa.max_iter) {
     // 3.0 speculative batch: proposals for steps iter, iter+1, ... assuming every earlier one is rejected
@@ -360,12 +406,12 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
         std::fill(memo_pres.begin(), memo_pres.end(), 0.0);
         rng_prop = pr.rng_after;  // discard the speculation beyond this step
         accepted_any = true;
-        if (batch < 0) batch_now = std::min(batch_cap, b + 1u);
+        if (batch < 0) batch_now = std::max(batch_floor, std::min(batch_cap, b + 1u));
       }
       if (llhood > llhood_ML) {  // :541-545
         llhood_ML = llhood;
         M_ML = M;
-        write_poset_file(M.poset, ctl_asa.outdir);
+        if (writer) write_poset_file(M.poset, ctl_asa.outdir);
       }
       f_par << iter << "\t" << llhood << "\t" << M.eps << "\t";
       stream_lambda(f_par, M.lambda);

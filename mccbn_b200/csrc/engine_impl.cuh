@@ -1534,6 +1534,8 @@ int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int
   pb.N = N;
   pb.p = p;
   pb.upload(obs, times, weights);
+  // several GPUs: candidate-parallel -- every rank is given ALL observations and fits its share of each speculative batch
+  pb.local_only = c->world > 1;
   initialize_candidate(pb, M, lambda_s, max_lambda);  // src/asa.cpp:640-642
   EmControl ctl;
   ctl.max_iter = max_iter_EM;
@@ -1558,6 +1560,7 @@ int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int
   if (batch <= 0) {
     const double work = (double)N * (double)L;  // samples per E-step of one candidate
     batch = -(int)std::max(1.0, std::min((double)(kMaxCand - 1), std::floor(2e6 / std::max(work, 1.0))));
+    if (c->world > 1) batch = -std::min(kMaxCand - 1, std::max(-batch, c->world));  // one candidate per GPU at least
   }
   const double ll = simulated_annealing(pb, M, actl, L, sc, ctl, sampling_times_available != 0, (uint32_t)seed,
                                         lambda_s, verbose != 0, batch);

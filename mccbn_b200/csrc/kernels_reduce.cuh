@@ -171,6 +171,22 @@ __device__ inline bool peer_pull(const PeerView& pv, int PS, double* st_out) {
   return s_ok != 0;
 }
 
+// Generic sum-exchange of a short vector (n <= kMaxPSlots) over the mailboxes: every rank pushes, then pulls the
+// rank-ordered sum back into `vec` (used by the annealer to share candidate scores between GPUs).  One block each.
+__global__ void push_vec_kernel(const double* __restrict__ vec, int n, const PeerView pv) {
+  const int par = (int)(pv.seq & 1ull);
+  for (int s = threadIdx.x; s < n; s += blockDim.x) {
+    const double t = vec[s];
+    for (int q = 0; q < pv.world; ++q) pv.box[q]->slot[par][pv.rank][s] = t;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < pv.world) st_release_sys(&pv.box[threadIdx.x]->flag[pv.rank], pv.seq);
+}
+__global__ void pull_vec_kernel(double* __restrict__ vec, int n, int* __restrict__ error_flag, const PeerView pv) {
+  if (!peer_pull(pv, n, vec) && threadIdx.x == 0) *error_flag = 1;
+}
+
 // Derived tables for the next E-step (device function, run by one block).
 __device__ inline void prepare_tables(const DevPoset* __restrict__ pos, DevModel* __restrict__ mdl,
                                       FwdScale* __restrict__ sc) {

@@ -161,6 +161,10 @@ struct mccbn_problem {
   FlatPoset flat[kMaxCand];
   int iter_host[kMaxCand];
   uint32_t eval_id[kMaxCand];
+  // candidate-parallel annealing: every rank holds ALL observations and scores its share of the candidate posets, so the
+  // EM iterations of this problem must not exchange statistics with the other ranks
+  bool local_only = false;
+  bool sharded() const { return ctx->world > 1 && !local_only; }
   unsigned long long xchg_seq[kMaxCand] = {};  // exchange number of the candidate's pending reduce_push
   PeerView peer_view(unsigned long long seq) const {
     PeerView pv;
@@ -378,7 +382,7 @@ struct mccbn_problem {
       return !(e && std::strcmp(e, "0") == 0);
     }();
     int done = 0;
-    if (enabled && ctx->world == 1 && n >= 3) {
+    if (enabled && !sharded() && n >= 3) {
       enqueue_iteration(c, scheme, L, neighborhood_dist, times_given, seed, update_params, false, precision);  // eager
       ++done;
       cudaStream_t s = ctx->stream;
@@ -458,7 +462,7 @@ struct mccbn_problem {
     fa.L_eff = L_eff;
     fa.uniform_fallback = uniform_fallback;
     finalize_kernel<<<fin_blocks, kFinBlock, 0, s>>>(fa);
-    if (ctx->world > 1 && ctx->peer_ready) {
+    if (sharded() && ctx->peer_ready) {
       xchg_seq[c] = ++ctx->xchg_seq;
       reduce_push_kernel<<<1, 64, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS(), peer_view(xchg_seq[c]));
     } else {
@@ -470,11 +474,11 @@ struct mccbn_problem {
   void run_mstep(int c, int update_params) {
     cudaStream_t s = ctx->stream;
     PeerView pv = peer_view(0);
-    if (ctx->world > 1 && ctx->peer_ready) {
+    if (sharded() && ctx->peer_ready) {
       pv = peer_view(xchg_seq[c]);  // the M-step kernel pulls the vectors pushed by reduce_push_kernel
     } else {
       pv.world = 1;
-      if (ctx->world > 1) {
+      if (sharded()) {
         if (!ctx->comm) throw Error(MCCBN_ERR_ARG, "world > 1 but neither the peer exchange nor NCCL is initialised");
         ctx->nccl.check(ctx->nccl.AllReduce(stats_of(c), stats_of(c), (size_t)PS(), NcclApi::kDouble, NcclApi::kSum,
                                             ctx->comm, s),
@@ -492,6 +496,38 @@ struct mccbn_problem {
     if (p <= kWideMaxP)
       MCCBN_CUDA(cudaMemcpyToSymbolAsync(c_scale, scales.ptr + c, sizeof(FwdScale), 0, cudaMemcpyDeviceToDevice,
                                          ctx->stream));
+  }
+
+  // element-wise sum over ranks of a host vector (every rank gets the rank-ordered sum): peer mailboxes or NCCL
+  DevBuf<double> xbuf;
+  DevBuf<int> xerr;
+  void exchange_sum(std::vector<double>& v) {
+    if (ctx->world <= 1 || v.empty()) return;
+    cudaStream_t s = ctx->stream;
+    const size_t n = v.size();
+    double* d = xbuf.ensure(n);
+    int* ef = xerr.ensure(1);
+    MCCBN_CUDA(cudaMemcpyAsync(d, v.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    MCCBN_CUDA(cudaMemsetAsync(ef, 0, sizeof(int), s));
+    if (ctx->peer_ready) {
+      for (size_t off = 0; off < n; off += kMaxPSlots) {
+        const int m = (int)std::min<size_t>(kMaxPSlots, n - off);
+        const PeerView pv = peer_view(++ctx->xchg_seq);
+        push_vec_kernel<<<1, 128, 0, s>>>(d + off, m, pv);
+        pull_vec_kernel<<<1, 128, 0, s>>>(d + off, m, ef, pv);
+        ctx->launches += 2;
+      }
+      MCCBN_CUDA(cudaGetLastError());
+    } else if (ctx->comm) {
+      ctx->nccl.check(ctx->nccl.AllReduce(d, d, n, NcclApi::kDouble, NcclApi::kSum, ctx->comm, s), "ncclAllReduce");
+    } else {
+      throw Error(MCCBN_ERR_ARG, "world > 1 but neither the peer exchange nor NCCL is initialised");
+    }
+    int herr = 0;
+    MCCBN_CUDA(cudaMemcpyAsync(v.data(), d, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    MCCBN_CUDA(cudaMemcpyAsync(&herr, ef, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MCCBN_CUDA(cudaStreamSynchronize(s));
+    if (herr) throw Error(MCCBN_ERR_CUDA, kMsgCommTimeout);
   }
 
   void read_model(int c, DevModel& dm) {

@@ -70,6 +70,29 @@ def main():
                 dist.barrier()
                 ctx.close()
                 say(sampling, exchange, "context closed")
+        # candidate-parallel annealing: every rank holds all observations and fits its share of each speculative batch;
+        # all ranks walk the same trajectory and end with the single-GPU result, bit for bit
+        import tempfile
+        ca = synth.make_config(8, 400, eps=0.05, seed=5, density=0.3)
+        start = np.zeros((8, 8), np.int32)
+        kw = dict(L=64, max_iter=40, update_step_size=20, max_iter_asa=30, seed=7)
+        os.environ["MCCBN_ASA_BATCH"] = "8"
+        ctx1 = mc.Context(local)
+        ref = mc.adaptive_simulated_annealing(start, ca["obs"], outdir=tempfile.mkdtemp() + "/", ctx=ctx1, **kw)
+        ctx1.close()
+        for exchange in ("peer", "nccl"):
+            ctx = mdist.init_context(local, dist, exchange=exchange)
+            out = tempfile.mkdtemp() + "/"
+            r = mc.adaptive_simulated_annealing(start, ca["obs"], outdir=out, ctx=ctx, **kw)
+            same = (np.array_equal(r["poset"], ref["poset"]) and np.array_equal(r["lambda_"], ref["lambda_"]) and
+                    r["eps"] == ref["eps"] and r["llhood"] == ref["llhood"])
+            flag = torch.tensor([1.0 if same else 0.0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            res[f"asa/{exchange}"] = {"identical_to_single_gpu_on_all_ranks": bool(flag.item() == 1.0),
+                                      "rank0_wrote_files": (rank != 0) or os.path.exists(out + "params.txt")}
+            say("asa", exchange, same)
+            dist.barrier()
+            ctx.close()
     except BaseException:
         # a rank that fails must not leave its peers waiting in a collective: take the whole job down
         import traceback

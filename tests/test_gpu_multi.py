@@ -27,7 +27,10 @@ def test_sharded_em_matches_single_gpu(world):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MULTI_GPU_RESULT ")][-1]
     res = json.loads(line[len("MULTI_GPU_RESULT "):])
-    assert set(res) == {"forward/peer", "forward/nccl", "backward/peer", "backward/nccl"}
+    assert set(res) == {"forward/peer", "forward/nccl", "backward/peer", "backward/nccl", "asa/peer", "asa/nccl"}
+    for key in ("asa/peer", "asa/nccl"):  # candidate-parallel annealing: the single-GPU result on every rank
+        v = res.pop(key)
+        assert v["identical_to_single_gpu_on_all_ranks"] and v["rank0_wrote_files"], (key, v)
     for key, v in res.items():
         assert v["identical_across_ranks"], key
         # same samples (Philox counters carry the global observation index); only the fp64 summation order differs
