@@ -464,9 +464,9 @@ struct mccbn_problem {
     finalize_kernel<<<fin_blocks, kFinBlock, 0, s>>>(fa);
     if (sharded() && ctx->peer_ready) {
       xchg_seq[c] = ++ctx->xchg_seq;
-      reduce_push_kernel<<<1, 64, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS(), peer_view(xchg_seq[c]));
+      reduce_push_kernel<<<1, 256, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS(), peer_view(xchg_seq[c]));
     } else {
-      reduce_stats_kernel<<<1, 64, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS());
+      reduce_stats_kernel<<<1, 256, 0, s>>>(blk.ptr, stats_of(c), fin_blocks, PS());
     }
     ctx->launches += 2;
     MCCBN_CUDA(cudaGetLastError());
