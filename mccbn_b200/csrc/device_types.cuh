@@ -77,6 +77,7 @@ struct PeerView {
   Mailbox* box[kMaxWorld];  // box[q] = rank q's mailbox mapped into this process (box[rank] is local memory)
   int rank, world;
   unsigned long long seq;   // number of this exchange (1, 2, ...), identical on all ranks
+  long long timeout_clocks; // give up waiting for a rank after this many SM clocks (a dead rank must not hang the GPU)
 };
 
 // Static "program" of one poset for the sampling kernels.  It is known to the host, so it travels as a

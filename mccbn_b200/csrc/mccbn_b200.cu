@@ -166,9 +166,13 @@ struct mccbn_problem {
   bool local_only = false;
   bool sharded() const { return ctx->world > 1 && !local_only; }
   unsigned long long xchg_seq[kMaxCand] = {};  // exchange number of the candidate's pending reduce_push
-  PeerView peer_view(unsigned long long seq) const {
+  // timeout: sharded EM iterations run in lock-step (30 s covers a first-call NVRTC compile on one rank); the annealer's score exchange waits for the
+  // slowest rank's whole MCEM fits (10 min).  MCCBN_PEER_TIMEOUT_S overrides both.
+  PeerView peer_view(unsigned long long seq, double timeout_s = 30.0) const {
     PeerView pv;
     std::memset(&pv, 0, sizeof(pv));
+    if (const char* e = std::getenv("MCCBN_PEER_TIMEOUT_S")) timeout_s = std::max(1e-3, std::atof(e));
+    pv.timeout_clocks = (long long)(timeout_s * 2.0e9);
     for (int q = 0; q < ctx->world && q < kMaxWorld; ++q) pv.box[q] = ctx->peer_box[q];
     pv.rank = ctx->rank;
     pv.world = ctx->world;
@@ -512,7 +516,7 @@ struct mccbn_problem {
     if (ctx->peer_ready) {
       for (size_t off = 0; off < n; off += kMaxPSlots) {
         const int m = (int)std::min<size_t>(kMaxPSlots, n - off);
-        const PeerView pv = peer_view(++ctx->xchg_seq);
+        const PeerView pv = peer_view(++ctx->xchg_seq, 600.0);
         push_vec_kernel<<<1, 128, 0, s>>>(d + off, m, pv);
         pull_vec_kernel<<<1, 128, 0, s>>>(d + off, m, ef, pv);
         ctx->launches += 2;
