@@ -209,8 +209,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
   } else {
     throw Error(MCCBN_ERR_ARG, "unknown sampling scheme");
   }
-  run_finalize(c, chunks, n_items, L_eff, 0, per_obs_out);
-  run_mstep(c, update_params);
+  run_finalize_mstep(c, chunks, n_items, L_eff, 0, per_obs_out, update_params);
 }
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -39,7 +39,7 @@ struct FinArgs {
 // Chunks are merged with a log-sum-exp over their scales.  Output stats: [0]=LL, [1]=N_eff, [2]=D,
 // [3]=#observations whose weights are all zero, [4]=0, [5+k]=S_k.
 // One warp per observation, lane s owns record slot s (and s+32): coalesced reads, no shuffles except broadcasts.
-__global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) {
+__device__ __forceinline__ void finalize_body(const FinArgs& a) {
   __shared__ double s_acc[kFinWarps][kMaxPS];
   const DevPoset* __restrict__ pos = a.poset;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) {
     a.blk_part[(size_t)blockIdx.x * PS + s] = t;
   }
 }
+
+__global__ void __launch_bounds__(kFinBlock) finalize_kernel(const FinArgs a) { finalize_body(a); }
 
 // second stage: sum of the block partials -> one value per slot, in a fixed order (lane l adds blocks l, l+32, ...;
 // the 32 lane sums are combined by a butterfly): deterministic, and 10x shorter than one thread per slot walking all
@@ -236,9 +238,9 @@ __global__ void prepare_kernel(const DevPoset* poset, DevModel* model, FwdScale*
 // Stage 6: M-step + trace row + tables for the next iteration.  One block.
 // stats may have been all-reduced across GPUs in between (identical on every rank => replicated M-step).
 // With a PeerView (world > 1) the kernel first pulls the statistic vectors of all ranks out of its mailbox.
-__global__ void mstep_kernel(double* __restrict__ st, const DevPoset* pos, DevModel* mdl, FwdScale* scale,
-                             double* trace, int trace_stride, int max_trace_rows, int PS, int update_params,
-                             const PeerView pv) {
+__device__ __forceinline__ void mstep_body(double* __restrict__ st, const DevPoset* pos, DevModel* mdl, FwdScale* scale,
+                                           double* trace, int trace_stride, int max_trace_rows, int PS, int update_params,
+                                           const PeerView& pv) {
   const int p = pos->p;
   if (pv.world > 1) {
     if (!peer_pull(pv, PS, st) && threadIdx.x == 0) mdl->comm_error = 1;
@@ -273,6 +275,48 @@ __global__ void mstep_kernel(double* __restrict__ st, const DevPoset* pos, DevMo
   __syncthreads();
   if (threadIdx.x == 0) mdl->iter = it + 1;
   if (update_params) prepare_tables(pos, mdl, scale);
+}
+
+__global__ void mstep_kernel(double* __restrict__ st, const DevPoset* pos, DevModel* mdl, FwdScale* scale,
+                             double* trace, int trace_stride, int max_trace_rows, int PS, int update_params,
+                             const PeerView pv) {
+  mstep_body(st, pos, mdl, scale, trace, trace_stride, max_trace_rows, PS, update_params, pv);
+}
+
+// Single-GPU tail of an EM iteration in ONE launch: per-observation finalize in every block; the block that finishes
+// last (ticket counter) sums the block partials and runs the M-step.  Small problems are bound by the latency of the
+// launch chain: three launches become one.
+struct FusedTail {
+  double* stats;
+  unsigned* counter;  // zero before the first launch; re-armed by the last block
+  const DevPoset* pos;
+  DevModel* mdl;
+  FwdScale* scale;
+  double* trace;
+  int trace_stride, max_trace_rows, update_params;
+};
+__global__ void __launch_bounds__(kFinBlock) finalize_mstep_kernel(const FinArgs a, const FusedTail t) {
+  finalize_body(a);
+  __shared__ unsigned s_ticket;
+  __threadfence();  // this block's partials are visible device-wide before it takes its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(t.counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  if (threadIdx.x == 0) *t.counter = 0u;
+  __threadfence();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int s = warp; s < a.PS; s += kFinWarps) {  // same order as slot_total; L2 loads: other blocks wrote the data
+    double v = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(a.blk_part + (size_t)b * a.PS + s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) t.stats[s] = v;
+  }
+  __syncthreads();
+  PeerView pv;
+  pv.world = 1;
+  mstep_body(t.stats, t.pos, t.mdl, t.scale, t.trace, t.trace_stride, t.max_trace_rows, a.PS, t.update_params, pv);
 }
 
 // ---- indexing kernels ---------------------------------------------------------------------------------------

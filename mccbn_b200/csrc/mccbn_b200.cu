@@ -442,7 +442,25 @@ struct mccbn_problem {
       enqueue_iteration(c, scheme, L, neighborhood_dist, times_given, seed, update_params, false, precision);
   }
 
-  void run_finalize(int c, int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out) {
+  // finalize + second-stage reduction + M-step; one fused launch on a single GPU (finalize_mstep_kernel)
+  DevBuf<unsigned> fuse_counter;
+  void run_finalize_mstep(int c, int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out,
+                          int update_params) {
+    static const bool fuse = [] {
+      const char* e = std::getenv("MCCBN_FUSE_TAIL");
+      return !(e && std::strcmp(e, "0") == 0);
+    }();
+    if (fuse && !sharded()) {
+      run_finalize(c, chunks, n_items, L_eff, uniform_fallback, per_obs_out, update_params, /*fused=*/true);
+      iter_host[c]++;
+    } else {
+      run_finalize(c, chunks, n_items, L_eff, uniform_fallback, per_obs_out);
+      run_mstep(c, update_params);
+    }
+  }
+
+  void run_finalize(int c, int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out,
+                    int update_params = 0, bool fused = false) {
     cudaStream_t s = ctx->stream;
     FinArgs fa;
     std::memset(&fa, 0, sizeof(fa));
@@ -465,6 +483,26 @@ struct mccbn_problem {
     fa.n_items = n_items;
     fa.L_eff = L_eff;
     fa.uniform_fallback = uniform_fallback;
+    if (fused) {
+      if (!fuse_counter.ptr) {
+        fuse_counter.ensure(1);
+        MCCBN_CUDA(cudaMemsetAsync(fuse_counter.ptr, 0, sizeof(unsigned), s));
+      }
+      FusedTail ft;
+      ft.stats = stats_of(c);
+      ft.counter = fuse_counter.ptr;
+      ft.pos = posets.ptr + c;
+      ft.mdl = models.ptr + c;
+      ft.scale = scales.ptr + c;
+      ft.trace = trace.ptr ? trace_of(c) : nullptr;
+      ft.trace_stride = p + 2;
+      ft.max_trace_rows = trace_rows;
+      ft.update_params = update_params;
+      finalize_mstep_kernel<<<fin_blocks, kFinBlock, 0, s>>>(fa, ft);
+      ctx->launches++;
+      MCCBN_CUDA(cudaGetLastError());
+      return;
+    }
     finalize_kernel<<<fin_blocks, kFinBlock, 0, s>>>(fa);
     if (sharded() && ctx->peer_ready) {
       xchg_seq[c] = ++ctx->xchg_seq;
