@@ -240,8 +240,8 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
 }
 
 // ---- conditional proposal (backward / bernoulli / OT-CBN / add-remove): the same idea for estep_conditional_body ----
-// Same random stream and arithmetic as sample_conditional (kernels_cond.cuh): uniform ui = k (+1 when the sampling
-// time is drawn) is word ui % 4 of Philox block ui / 4.
+// Same random stream and arithmetic as sample_conditional (kernels_cond.cuh): packed 24-bit fields, field 0 = sampling
+// time, field k + 1 = node k.
 static std::string generate_cond_source(const FlatPoset& f, bool times_given, int mode, int minb) {
   const int p = f.p, pmax = jit_pmax(p);
   std::ostringstream s;
@@ -255,7 +255,17 @@ static std::string generate_cond_source(const FlatPoset& f, bool times_given, in
        "      float (&Z)[" << pmax << "], float& Ts_out) const {\n"
        "    float Ts = ts_given;\n"
        "    float lw2 = 0.0f;\n";
+  // stream word 4 b + i is component i of Philox block b (variable r<b>); fields as in generate_forward_source
   const char* comp[4] = {".x", ".y", ".z", ".w"};
+  auto word = [&](int wi) { return "r" + std::to_string(wi / 4) + comp[wi % 4]; };
+  auto field = [&](int fi) {  // the expression field_u01_open1 folds to: u in [0, 1)
+    const int st = 24 * fi, wi = st / 32, o = st % 32;
+    std::string m;
+    if (o == 0) m = "((" + word(wi) + " & 0x7fffffu) | one)";
+    else if (o == 8) m = "((" + word(wi) + " >> 9) | 0x3f800000u)";
+    else m = "((__funnelshift_r(" + word(wi) + ", " + word(wi + 1) + ", " + std::to_string(o) + ") & 0x7fffffu) | one)";
+    return "(__uint_as_float(" + m + ") - 1.0f)";
+  };
   int generated = 0;
   auto need_block = [&](int b) {
     while (generated <= b) {
@@ -263,13 +273,11 @@ static std::string generate_cond_source(const FlatPoset& f, bool times_given, in
       ++generated;
     }
   };
-  if (!times_given) {
-    need_block(0);
-    s << "    Ts = CondMath<float>::z_of(CondMath<float>::u01(r0.x), 1.0f, s_inv[" << pmax << "]);\n";
-  }
+  s << "    const uint32_t one = pg.one_bits;\n";
+  need_block(0);
+  if (!times_given) s << "    Ts = CondMath<float>::z_of(" << field(0) << ", 1.0f, s_inv[" << pmax << "]);\n";
   for (int k = 0; k < p; ++k) {
-    const int ui = k + (times_given ? 0 : 1);
-    need_block(ui / 4);
+    need_block(fwd_field_block(k + 1));
     std::vector<std::string> terms;
     for (uint64_t m = f.parent_pos[k]; m; m &= m - 1) terms.push_back("t" + std::to_string(ctz64(m)));
     while (terms.size() > 1) {
@@ -283,8 +291,8 @@ static std::string generate_cond_source(const FlatPoset& f, bool times_given, in
       << "    const bool x" << K << " = (Xt >> " << K << ") & 1u;\n"
       << "    const float a" << K << " = Ts - m" << K << ";\n"
       << "    const float Fx" << K << " = CondMath<float>::F_of(a" << K << ", s_lam2[" << K << "]);\n"
-      << "    const float z" << K << " = CondMath<float>::z_of(CondMath<float>::u01(r" << (ui / 4) << comp[ui % 4] << "), x" << K
-      << " ? Fx" << K << " : 1.0f, s_inv[" << K << "]);\n"
+      << "    const float z" << K << " = CondMath<float>::z_of(" << field(k + 1) << ", x" << K << " ? Fx" << K
+      << " : 1.0f, s_inv[" << K << "]);\n"
       << "    const float t" << K << " = (x" << K << " ? m" << K << " : fmaxf(m" << K << ", Ts)) + z" << K << ";\n"
       << "    Z[" << K << "] = t" << K << " - m" << K << ";\n"
       << "    lw2 += x" << K << " ? CondMath<float>::lg2(Fx" << K << ") : -s_lam2[" << K << "] * fmaxf(a" << K << ", 0.0f);\n";

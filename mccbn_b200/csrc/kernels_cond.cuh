@@ -77,6 +77,8 @@ __device__ __forceinline__ real cond_uniform(const uint4& r, int w) {
 }
 
 // One conditional draw.  Xt = hidden genotype (topological bit order).  Returns log2 of P(Z)/q_Z.
+// Random stream (fp32): the same packed 24-bit fields as the forward sampler -- field 0 = sampling time, field k + 1 =
+// node k -- so p = 25 costs 5 Philox blocks instead of 7.
 template <typename real, int PMAX, bool TIMES_GIVEN>
 __device__ __forceinline__ real sample_conditional(const PosetProg& pg, const uint32_t tcol_s,
                                                    const real* __restrict__ s_lam2, const real* __restrict__ s_inv,
@@ -84,21 +86,41 @@ __device__ __forceinline__ real sample_conditional(const PosetProg& pg, const ui
                                                    const uint32_t k1, const uint32_t cw, const real ts_given,
                                                    const uint32_t Xt, real (&Z)[PMAX], real& Ts_out) {
   constexpr int UPB = RealTraits<real>::kUniPerBlock;
-  uint4 r = make_uint4(0, 0, 0, 0);
+  constexpr int NB = fwd_blocks_for_fields(PMAX + 1);
+  uint32_t W[4 * NB];             // fp32 path
+  uint4 r = make_uint4(0, 0, 0, 0);  // fp64 path
+  const uint32_t one = pg.one_bits;
   real Ts = ts_given;
-  if (!TIMES_GIVEN) {
+  if constexpr (sizeof(real) == 4) {
+    const uint4 r0 = philox4x32_10(l, gi, 0u, cw, k0, k1);
+    W[0] = r0.x, W[1] = r0.y, W[2] = r0.z, W[3] = r0.w;
+    if (!TIMES_GIVEN) Ts = CondMath<real>::z_of((real)field_u01_open1(W, 0, one), (real)1, s_inv[PMAX]);  // Exp(lambda_s)
+  } else if (!TIMES_GIVEN) {
     r = philox4x32_10(l, gi, 0u, cw, k0, k1);
-    const real u = cond_uniform<real>(r, 0);
-    Ts = CondMath<real>::z_of(u, (real)1, s_inv[PMAX]);  // Exp(lambda_s)
+    Ts = CondMath<real>::z_of(cond_uniform<real>(r, 0), (real)1, s_inv[PMAX]);
   }
   real lw2 = (real)0;
   const unsigned multi_mask = pg.multi_mask;
   // all PMAX slots run unconditionally; slots k >= p have lam2 = inv = 0 and X_k = 0: they contribute nothing
 #pragma unroll
   for (int k = 0; k < PMAX; ++k) {
-    const int ui = k + (TIMES_GIVEN ? 0 : 1);
-    if (ui % UPB == 0) r = philox4x32_10(l, gi, (uint32_t)(ui / UPB), cw, k0, k1);
-    const real u = cond_uniform<real>(r, ui % UPB);
+    real u;
+    if constexpr (sizeof(real) == 4) {
+      const int b = fwd_field_block(k + 1);
+      if (b != fwd_field_block(k)) {  // compile-time after unrolling: block b is first touched by node k
+        if (k < pg.p) {               // warp-uniform
+          const uint4 rb = philox4x32_10(l, gi, (uint32_t)b, cw, k0, k1);
+          W[4 * b + 0] = rb.x, W[4 * b + 1] = rb.y, W[4 * b + 2] = rb.z, W[4 * b + 3] = rb.w;
+        } else {
+          W[4 * b + 0] = W[4 * b + 1] = W[4 * b + 2] = W[4 * b + 3] = 0u;
+        }
+      }
+      u = (real)field_u01_open1(W, k + 1, one);
+    } else {
+      const int ui = k + (TIMES_GIVEN ? 0 : 1);
+      if (ui % UPB == 0) r = philox4x32_10(l, gi, (uint32_t)(ui / UPB), cw, k0, k1);
+      u = cond_uniform<real>(r, ui % UPB);
+    }
     const real m = parents_max<real>(pg, multi_mask, k, tcol_s);
     const bool xk = (Xt >> k) & 1u;
     const real a = Ts - m;

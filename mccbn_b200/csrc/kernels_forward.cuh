@@ -78,14 +78,24 @@ __host__ __device__ constexpr int fwd_blocks_for_fields(int nf) { return nf <= 0
 
 // `one` = 0x3f800000 held in a register (PosetProg::one_bits): with an immediate the compiler needs two LOP3 for
 // (x & mask) | one, with a register operand it is a single three-input LOP3.
+// field -> float in [1, 2) with the 23 field bits as mantissa
 template <int NW>
-__device__ __forceinline__ float field_u01(const uint32_t (&W)[NW], const int f, const uint32_t one) {
+__device__ __forceinline__ float field_f12(const uint32_t (&W)[NW], const int f, const uint32_t one) {
   const int s = 24 * f, wi = s >> 5, o = s & 31;
   uint32_t m;
   if (o == 0) m = (W[wi] & 0x7fffffu) | one;                                          // stream bits [s, s+23)
   else if (o == 8) m = (W[wi] >> 9) | 0x3f800000u;                                    // [s+1, s+24): one LEA.HI
   else m = (__funnelshift_r(W[wi], W[wi + 1 < NW ? wi + 1 : wi], o) & 0x7fffffu) | one;  // o = 16, 24: [s, s+23)
-  return 2.0f - __uint_as_float(m);
+  return __uint_as_float(m);
+}
+// u in (0, 1] (forward draws: log(u)); u in [0, 1) (conditional draws: inverse CDF of the truncated exponential)
+template <int NW>
+__device__ __forceinline__ float field_u01(const uint32_t (&W)[NW], const int f, const uint32_t one) {
+  return 2.0f - field_f12(W, f, one);
+}
+template <int NW>
+__device__ __forceinline__ float field_u01_open1(const uint32_t (&W)[NW], const int f, const uint32_t one) {
+  return field_f12(W, f, one) - 1.0f;
 }
 
 // Z staging: each thread owns a row of PMAX values (e_k) stored as 16-byte vectors; an odd number of vectors per
