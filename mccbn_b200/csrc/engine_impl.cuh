@@ -444,6 +444,7 @@ static void lambda_from_counts(const FlatPoset& f, const unsigned long long* cnt
 }
 }  // namespace mccbn
 
+#include <chrono>
 #include <functional>
 #include "engine_asa.cuh"
 
@@ -685,6 +686,12 @@ static void single_estep(mccbn_ctx* c, mccbn_problem& pb, const int* obs, const 
                          unsigned neighborhood_dist, float lambda_s, int times_available, int seed, int N, int p,
                          const mccbn_em_options* opt, bool per_obs) {
   const Scheme sc = parse_scheme(sampling);
+  static const bool trace = std::getenv("MCCBN_TRACE_E2E") != nullptr;  // dev: host time per phase of the one-call path
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  const auto t0 = now();
   Poset P;
   FlatPoset f;
   flatten_or_throw(poset, p, P, f);
@@ -693,12 +700,18 @@ static void single_estep(mccbn_ctx* c, mccbn_problem& pb, const int* obs, const 
   pb.p = p;
   pb.obs_offset = opt ? opt->obs_offset : 0;
   pb.N_global = (opt && opt->N_global > 0) ? opt->N_global : N;
+  const auto t1 = now();
   pb.upload(obs, times, weights);
+  const auto t2 = now();
   if (opt) pb.eval_id[0] = opt->stream_id;
   pb.ensure_trace(1);
   pb.set_model(0, f, lambda, eps, lambda_s, 1e6f);
+  const auto t3 = now();
   pb.enqueue_iteration(0, sc, (int)L, neighborhood_dist, times_available != 0, (uint32_t)seed, 0, per_obs,
                        opt ? opt->precision : 0);
+  if (trace)
+    std::fprintf(stderr, "mccbn e2e: flatten %.0f us, upload %.0f us, set_model %.0f us, enqueue %.0f us\n", us(t0, t1),
+                 us(t1, t2), us(t2, t3), us(t3, now()));
 }
 
 int mccbn_obs_log_likelihood(mccbn_ctx* c, const int* obs, const int* poset, const double* lambda, double eps,
