@@ -111,8 +111,9 @@ struct PosetProgWide {
   uint2 off[kWideMaxP];
   uint4 xo[kWideMaxP];
   unsigned char ev[kWideMaxP];
+  uint64_t parent_mask[kWideMaxP];  // parents of k as a bitmask over positions (compatibility checks)
   unsigned short xstart[kWideMaxP + 2];
-  unsigned short xoff[2 * kMaxEdgesFast];
+  unsigned short xoff[kMaxEdgesFast];
 };
 
 // lambda-derived scales of the exponential draws, refreshed on the device after every M-step and mirrored into

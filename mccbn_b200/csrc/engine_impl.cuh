@@ -44,8 +44,8 @@ struct CondLauncher {
 void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neighborhood_dist, bool times_given,
                                       uint32_t seed, int update_params, bool per_obs_out, int precision) {
   if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");
-  if (p > kFastMaxP && scheme != kForward)
-    throw Error(MCCBN_ERR_ARG, "32 < p <= 64 is supported by the forward scheme only");
+  if (p > kFastMaxP && (scheme == kPool || scheme == kAddRemove || precision == 1))
+    throw Error(MCCBN_ERR_ARG, "32 < p <= 64 is supported by the forward, backward and bernoulli schemes (fp32 path)");
   cudaStream_t s = ctx->stream;
   const int iter = iter_host[c];
   bind_scales(c);
@@ -133,11 +133,20 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.PS = PS();
     const int warps_per_block = kFwdBlock / 32;
     long long blocks = (n_items + warps_per_block - 1) / warps_per_block;
-    JitKernel* jkc = precision == 1 ? nullptr : resolve_jit_cond(flat[c], times_given, mode, (double)N * (double)a.L);
+    // 32 < p <= 64 exists as a specialised kernel only: compile regardless of the work announced
+    JitKernel* jkc = precision == 1 ? nullptr
+                                    : resolve_jit_cond(flat[c], times_given, mode, (double)N * (double)a.L, p > kFastMaxP);
+    if (p > kFastMaxP && !jkc)
+      throw Error(MCCBN_ERR_CUDA, "32 < p <= 64 with this scheme needs the NVRTC-specialised kernel (libnvrtc unavailable?)");
     // one resident wave: MCCBN_COND_MINB blocks per SM for the fp32 kernels, 1 for the fp64 validation mode
     const int per_sm = jkc ? jkc->blocks_per_sm : (precision == 1 ? 1 : MCCBN_COND_MINB);
     grid_x = (int)std::max(1LL, std::min<long long>(blocks, (long long)ctx->sm_count * per_sm));
-    if (jkc) {
+    if (jkc && p > kFastMaxP) {
+      PosetProgWide pgc = build_prog_t<PosetProgWide>(flat[c], jkc->pmax, 4);
+      CondArgs args = a;
+      void* params[] = {(void*)&args, (void*)&pgc};
+      MCCBN_CUDA(cudaLaunchKernel((const void*)jkc->kern, dim3(grid_x), dim3(kFwdBlock), params, 0, s));
+    } else if (jkc) {
       PosetProg pgc = build_prog(flat[c], jkc->pmax, 4);
       CondArgs args = a;
       void* params[] = {(void*)&args, (void*)&pgc};
@@ -1482,7 +1491,8 @@ int mccbn_jit_compile_conditional(const int* poset, int p, int times_given, int 
                                   double* compile_ms, char* log, size_t loglen, char* source, size_t sourcelen,
                                   char* err, size_t errlen) {
   MCCBN_TRY
-  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the conditional kernels support p <= 32");
+  if (p > kWideMaxP || (p > kFastMaxP && mode == 3))
+    throw Error(MCCBN_ERR_ARG, "the conditional kernels support p <= 64 (add-remove: p <= 32)");
   if (mode < 0 || mode > 3) throw Error(MCCBN_ERR_ARG, "mode must be 0..3");
   Poset P;
   FlatPoset f;
@@ -1591,7 +1601,7 @@ int mccbn_MCEM(mccbn_ctx* c, const double* ilambda, const int* poset, const int*
   (void)topo_path;  // R passes my.topological.sort(poset) - 1; any valid order is equivalent, we derive our own
   MCCBN_TRY
   c = get_ctx(c);
-  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");
   Poset P;
   FlatPoset f;
   flatten_or_throw(poset, p, P, f);

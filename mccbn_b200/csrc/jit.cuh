@@ -244,14 +244,17 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
 // time, field k + 1 = node k.
 static std::string generate_cond_source(const FlatPoset& f, bool times_given, int mode, int minb) {
   const int p = f.p, pmax = jit_pmax(p);
+  // p > 32: 64-bit genotype words and the wide program; these sizes exist as specialised kernels only
+  const char* prog = p > kFastMaxP ? "PosetProgWide" : "PosetProg";
+  const char* word_t = p > kFastMaxP ? "uint64_t" : "uint32_t";
   std::ostringstream s;
   s << "#include \"kernels_cond.cuh\"\n"
        "namespace mccbn {\n"
        "struct SpecCondSampler {\n"
        "  static constexpr bool kStagesT = false;\n"
-       "  __device__ __forceinline__ float operator()(const PosetProg& pg, const uint32_t tcol_s,\n"
+       "  __device__ __forceinline__ float operator()(const " << prog << "& pg, const uint32_t tcol_s,\n"
        "      const float* __restrict__ s_lam2, const float* __restrict__ s_inv, const uint32_t l, const uint32_t gi,\n"
-       "      const uint32_t k0, const uint32_t k1, const uint32_t cw, const float ts_given, const uint32_t Xt,\n"
+       "      const uint32_t k0, const uint32_t k1, const uint32_t cw, const float ts_given, const " << word_t << " Xt,\n"
        "      float (&Z)[" << pmax << "], float& Ts_out) const {\n"
        "    float Ts = ts_given;\n"
        "    float lw2 = 0.0f;\n";
@@ -288,7 +291,7 @@ static std::string generate_cond_source(const FlatPoset& f, bool times_given, in
     }
     const std::string K = std::to_string(k);
     s << "    const float m" << K << " = " << (terms.empty() ? "0.0f" : terms[0]) << ";\n"
-      << "    const bool x" << K << " = (Xt >> " << K << ") & 1u;\n"
+      << "    const bool x" << K << " = (Xt >> " << K << ") & 1;\n"
       << "    const float a" << K << " = Ts - m" << K << ";\n"
       << "    const float Fx" << K << " = CondMath<float>::F_of(a" << K << ", s_lam2[" << K << "]);\n"
       << "    const float z" << K << " = CondMath<float>::z_of(" << field(k + 1) << ", x" << K << " ? Fx" << K
@@ -305,7 +308,7 @@ static std::string generate_cond_source(const FlatPoset& f, bool times_given, in
        "}  // namespace mccbn\n"
        "extern \"C\" __global__ void __launch_bounds__(mccbn::kFwdBlock, "
     << minb << ") mccbn_cond_spec(const mccbn::CondArgs a,\n"
-       "    const __grid_constant__ mccbn::PosetProg pg) {\n"
+       "    const __grid_constant__ mccbn::" << prog << " pg) {\n"
        "  mccbn::estep_conditional_body<float, " << pmax << ", " << (times_given ? "true" : "false") << ", " << mode
     << ">(a, pg, mccbn::SpecCondSampler{});\n"
        "}\n";

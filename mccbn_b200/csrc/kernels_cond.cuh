@@ -138,13 +138,13 @@ __device__ __forceinline__ real sample_conditional(const PosetProg& pg, const ui
 }
 
 // compatibility of a genotype in topological bit order: every mutated event has all parents mutated
-template <int PMAX>
-__device__ __forceinline__ bool compatible_topo(const PosetProg& pg, const uint32_t Xt) {
-  uint32_t bad = 0u;
+template <int PMAX, typename Prog>
+__device__ __forceinline__ bool compatible_topo(const Prog& pg, const typename Prog::word_t Xt) {
+  typename Prog::word_t bad = 0;
 #pragma unroll
   for (int k = 0; k < PMAX; ++k)
-    if (k < pg.p) bad |= ((Xt >> k) & 1u) ? (pg.parent_mask[k] & ~Xt) : 0u;
-  return bad == 0u;
+    if (k < pg.p) bad |= ((Xt >> k) & 1u) ? (pg.parent_mask[k] & ~Xt) : 0;
+  return bad == 0;
 }
 
 #ifndef MCCBN_COND_MINB
@@ -166,8 +166,10 @@ struct GenericCondSampler {
   }
 };
 
-template <typename real, int PMAX, bool TIMES_GIVEN, int MODE, typename Sampler>
-__device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const PosetProg& pg, const Sampler sampler) {
+template <typename real, int PMAX, bool TIMES_GIVEN, int MODE, typename Sampler, typename Prog>
+__device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const Prog& pg, const Sampler sampler) {
+  typedef typename Prog::word_t word_t;  // uint32_t (p <= 32) or uint64_t (specialised kernels only, p <= 64)
+  static_assert(MODE != kCondAddRemove || sizeof(word_t) == 4, "add-remove maps proposals to lanes: p <= 32");
   __shared__ real s_T[Sampler::kStagesT ? (PMAX + 1) * kFwdBlock : 1];
   __shared__ real s_lam2[PMAX + 1];
   __shared__ real s_inv[PMAX + 1];
@@ -208,7 +210,7 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
     }
     s_lpyx2[d] = (real)(lp * kLog2e);
   }
-  if (MODE == kCondAddRemove && threadIdx.x == 0) {
+  if constexpr (MODE == kCondAddRemove) if (threadIdx.x == 0) {
     double sc[PMAX];
     for (int k = 0; k < p; ++k) {  // topological order: parents before children
       uint32_t an = 1u << k;
@@ -238,7 +240,7 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
     const int i = (int)(item / a.chunks);
     const int ch = (int)(item - (long long)i * a.chunks);
     const uint64_t yw = a.obs_bits[i];
-    const uint32_t yt = to_topo_bits<PMAX>(pg, yw);
+    const word_t yt = to_topo_bits<PMAX>(pg, yw);
     const real ts_given = TIMES_GIVEN ? (real)a.times[i] : (real)0;
     const uint32_t gi = (uint32_t)(a.obs_offset + i);
 
@@ -248,7 +250,7 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
     real aw = (real)0, aw2 = (real)0, awd = (real)0, npos = (real)0;
     real mref = (real)-1e30;  // this lane's log2 reference
 
-    auto consume = [&](const uint32_t l, const uint32_t Xt, const int d, const bool valid, const real lw2_extra) {
+    auto consume = [&](const uint32_t l, const word_t Xt, const int d, const bool valid, const real lw2_extra) {
       real Z[PMAX];
       real Ts;
       const real lw2s = sampler(pg, tcol_s, s_lam2, s_inv, l, gi, a.key0, key1, cw, ts_given, Xt, Z, Ts);
@@ -284,7 +286,7 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
       const int g_begin = ch * a.chunk_len, g_end = min(a.n_ball, g_begin + a.chunk_len);
       for (int g = g_begin; g < g_end; ++g) {
         const uint64_t flip = a.ball[g];
-        const uint32_t Xt = to_topo_bits<PMAX>(pg, yw ^ flip);
+        const word_t Xt = to_topo_bits<PMAX>(pg, yw ^ flip);
         if (!compatible_topo<PMAX>(pg, Xt)) continue;  // warp-uniform
         const int d = __popcll(flip);
         for (int r0 = 0; r0 < a.reps; r0 += 32) {
@@ -360,7 +362,7 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
       const int l_begin = ch * a.chunk_len, l_end = min(a.L, l_begin + a.chunk_len);
       for (int l0 = l_begin; l0 < l_end; l0 += 32) {
         const int l = l0 + lane;
-        uint32_t Xt = yt;
+        word_t Xt = yt;
         if constexpr (MODE == kCondBernoulli) {
           // coin_tossing: flip each bit independently with probability eps (32 random bits per coin)
           uint4 rc = make_uint4(0, 0, 0, 0);
@@ -369,12 +371,12 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
             if (k < p) {
               if ((k & 3) == 0) rc = philox4x32_10((uint32_t)l, gi, 64u + (uint32_t)(k >> 2), cw, a.key0, key1);
               const uint32_t bits = (k & 3) == 0 ? rc.x : ((k & 3) == 1 ? rc.y : ((k & 3) == 2 ? rc.z : rc.w));
-              Xt ^= (bits < eps_thr) ? (1u << k) : 0u;
+              Xt ^= (bits < eps_thr) ? ((word_t)1 << k) : (word_t)0;
             }
           }
         }
         const bool comp = compatible_topo<PMAX>(pg, Xt);
-        consume((uint32_t)l, Xt, __popc(Xt ^ yt), (l < l_end) && comp, s_lpyx2[__popc(Xt ^ yt)]);
+        consume((uint32_t)l, Xt, popc_word((word_t)(Xt ^ yt)), (l < l_end) && comp, s_lpyx2[popc_word((word_t)(Xt ^ yt))]);
       }
     }
 
@@ -400,17 +402,21 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
       // natural-log scale of this record: true weights = exp(lscale) * relative weights
       out[4] = (mmax > (real)-1e29) ? (double)mmax * 0.693147180559945309417 + lscale_extra : -__longlong_as_double(0x7ff0000000000000LL) /* -inf */;
     }
-    double mine = 0.0;
+    double mine = 0.0, mine_hi = 0.0;  // lane k owns slots k and (p > 32) k + 32
 #pragma unroll
     for (int k = 0; k < PMAX; ++k) {
       if (k < p) {
         double v = (double)(acc[k] * s);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == (k & 31)) mine = v;
+        if (lane == (k & 31)) {
+          if (k < 32) mine = v;
+          else mine_hi = v;
+        }
       }
     }
     if (lane < p) out[kStatHdr + lane] = mine;
+    if (PMAX > 32 && lane + 32 < p) out[kStatHdr + 32 + lane] = mine_hi;
   }
 }
 

@@ -98,7 +98,7 @@ static Prog build_prog_t(const FlatPoset& f, int pmax, int elem_bytes) {
     g.xstart[k] = (unsigned short)x;
     if (k >= f.p) continue;
     g.ev[k] = (unsigned char)f.topo[k];
-    if constexpr (std::is_same<Prog, PosetProg>::value) g.parent_mask[k] = (unsigned)f.parent_pos[k];
+    g.parent_mask[k] = (decltype(g.parent_mask[k] + 0))f.parent_pos[k];
     int n = 0;
     for (uint64_t m = f.parent_pos[k]; m; m &= m - 1, ++n) {
       const unsigned row = (unsigned)ctz64(m);
@@ -264,13 +264,15 @@ struct mccbn_problem {
   }
 
   // the same policy for the conditional-proposal kernels (backward / bernoulli / OT-CBN / add-remove)
-  JitKernel* resolve_jit_cond(const FlatPoset& f, bool times_given, int mode, double samples_per_estep) {
+  JitKernel* resolve_jit_cond(const FlatPoset& f, bool times_given, int mode, double samples_per_estep,
+                              bool required = false) {
     int jm = ctx->jit_mode;
     if (jm < 0) {
       const char* e = std::getenv("MCCBN_JIT");
       if (e && std::strcmp(e, "0") == 0) jm = 0;
       else if (e && std::strcmp(e, "1") == 0) jm = 1;
     }
+    if (required) jm = 1;
     if (jm == 0) return nullptr;
     if (!ctx->jit) ctx->jit = new JitCache();
     const bool worth = samples_per_estep * (double)std::max(1, expected_esteps) >= 5e9;
