@@ -54,7 +54,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
   int L_eff = L;
 
   if (scheme == kForward) {
-    JitKernel* jk = (precision == 1 || p > kFastMaxP) ? nullptr : resolve_jit(flat[c], times_given, L);
+    JitKernel* jk = precision == 1 ? nullptr : resolve_jit(flat[c], times_given, L);
     choose_chunks(L, chunks, chunk_len, grid_x, jk ? jk->blocks_per_sm : 0);
     n_items = (long long)N * chunks;
     FwdArgs a;
@@ -1470,12 +1470,12 @@ int mccbn_set_jit(mccbn_ctx* c, int mode) {
 int mccbn_jit_compile_forward(const int* poset, int p, int times_given, size_t* cubin_bytes, double* compile_ms,
                               char* log, size_t loglen, char* source, size_t sourcelen, char* err, size_t errlen) {
   MCCBN_TRY
-  if (p > kFastMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 32");
+  if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");
   Poset P;
   FlatPoset f;
   flatten_or_throw(poset, p, P, f);
   static NvrtcApi rtc;
-  const std::string src = generate_forward_source(f, times_given != 0, jit_default_minb());
+  const std::string src = generate_forward_source(f, times_given != 0, p > kFastMaxP ? 2 : jit_default_minb());
   if (source && sourcelen) std::snprintf(source, sourcelen, "%s", src.c_str());
   JitCompiled cc;
   const bool ok = jit_compile(rtc, src, cc);

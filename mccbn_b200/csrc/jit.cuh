@@ -84,6 +84,9 @@ static std::string jit_key(const FlatPoset& f, bool times_given, int minb) {
 
 static std::string generate_forward_source(const FlatPoset& f, bool times_given, int minb) {
   const int p = f.p, pmax = jit_pmax(p);
+  // p > 32: 64-bit genotype words and the wide program
+  const char* prog = p > kFastMaxP ? "PosetProgWide" : "PosetProg";
+  const char* word_t = p > kFastMaxP ? "uint64_t" : "uint32_t";
   std::ostringstream s;
   if (const char* e = std::getenv("MCCBN_JIT_DIAG_ROUNDS"))  // profiling experiments only (see philox.cuh)
     s << "#define MCCBN_PHILOX_ROUNDS " << std::max(1, std::min(10, std::atoi(e))) << "\n";
@@ -92,13 +95,13 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
        "// generated for one poset: node k = topological position k, t<k> = event time, parents unrolled\n"
        "struct SpecSampler {\n"
        "  static constexpr bool kStagesT = false;\n"
-       "  __device__ __forceinline__ void operator()(const PosetProg& pg, const uint32_t tcol_s, const uint32_t zrow_s,\n"
+       "  __device__ __forceinline__ void operator()(const " << prog << "& pg, const uint32_t tcol_s, const uint32_t zrow_s,\n"
        "      const uint32_t l, const uint32_t gi, const uint32_t k0, const uint32_t k1, const uint32_t cw,\n"
        "      const float ts_given, const ScaleSrc<float, "
     << pmax
-    << "> scale, uint32_t& X, float& Ts_out) const {\n"
+    << "> scale, " << word_t << "& X, float& Ts_out) const {\n"
        "    float Ts = ts_given;\n"
-       "    uint32_t x = 0u;\n"
+       "    " << word_t << " x = 0;\n"
        "    const uint32_t one = pg.one_bits;\n";
   // Same stream layout as sample_forward (kernels_forward.cuh): field 0 = sampling time, field k + 1 = node k, 24-bit
   // fields packed back to back; stream word 4 b + i is state word i of Philox block b (variable a<i>_<b>).
@@ -115,6 +118,7 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
   // genotype bits: 0 = predicated integer add (ALU pipe), 1 = FSET + FFMA into two fp32 accumulators of 16 bits each
   int xmode = 0;
   if (const char* e = std::getenv("MCCBN_JIT_XMODE")) xmode = std::atoi(e);
+  if (p > kFastMaxP) xmode = 0;  // the experiments pack 32 bits
   if (xmode == 1) s << "    float xlo = 0.0f, xhi = 0.0f;\n";
   // 2 (experiment): not-X_k = sat(2^100 (T_k - T_s)) by FFMA.SAT, bits collected by Horner FFMAs (FP32 pipe only)
   if (xmode == 2) s << "    float xlo = 0.0f, xhi = 0.0f;\n";
@@ -158,7 +162,7 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
       o << (k < 16 ? "xlo" : "xhi") << " = fmaf(t" << k << " <= Ts ? 1.0f : 0.0f, " << (1u << (k & 15)) << ".0f, "
         << (k < 16 ? "xlo" : "xhi") << ");\n";
     else
-      o << "if (t" << k << " <= Ts) x |= 0x" << std::hex << (1u << k) << std::dec << "u;\n";
+      o << "if (t" << k << " <= Ts) x |= 0x" << std::hex << (1ull << k) << std::dec << "ull;\n";
     if (k % 4 == 3 || k == p - 1) {
       const int q = k / 4;
       o << "    sts128_f(zrow_s + " << q * 16 << "u";
@@ -231,7 +235,7 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
        "extern \"C\" __global__ void __launch_bounds__(mccbn::kFwdBlock, "
     << minb
     << ") mccbn_fwd_spec(const mccbn::FwdArgs a,\n"
-       "    const __grid_constant__ mccbn::PosetProg pg) {\n"
+       "    const __grid_constant__ mccbn::" << prog << " pg) {\n"
        "  mccbn::estep_forward_body<float, "
     << pmax << ", " << (times_given ? "true" : "false")
     << ">(a, pg, mccbn::SpecSampler{});\n"
@@ -418,7 +422,8 @@ struct JitCache {
 
   // `only_if_cached`: do not compile, return the kernel only if it is already in memory or on disk
   JitKernel* get(const FlatPoset& f, bool times_given, bool only_if_cached = false) {
-    return get_kernel(jit_key(f, times_given, minb), [&] { return generate_forward_source(f, times_given, minb); },
+    const int mb = f.p > kFastMaxP ? std::min(minb, 2) : minb;  // 64 event times + 64 sums per thread: 2 resident blocks
+    return get_kernel(jit_key(f, times_given, mb), [&] { return generate_forward_source(f, times_given, mb); },
                       "mccbn_fwd_spec", /*forward=*/true, f.p, only_if_cached);
   }
   // conditional-proposal kernels (mode = CondMode); they keep their scales in shared memory, no __constant__ symbol

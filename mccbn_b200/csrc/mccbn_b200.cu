@@ -282,10 +282,16 @@ struct mccbn_problem {
   void launch_forward_jit(JitKernel* jk, const FwdArgs& a, const FlatPoset& f, int c, int grid) {
     cudaStream_t s = ctx->stream;
     MCCBN_CUDA(cudaMemcpyAsync(jk->scale_sym, scales.ptr + c, sizeof(FwdScale), cudaMemcpyDeviceToDevice, s));
-    PosetProg pg = build_prog(f, jk->pmax, 4);
     FwdArgs args = a;
-    void* params[] = {(void*)&args, (void*)&pg};
-    MCCBN_CUDA(cudaLaunchKernel((const void*)jk->kern, dim3(grid), dim3(kFwdBlock), params, jk->smem, s));
+    if (f.p > kFastMaxP) {
+      PosetProgWide pg = build_prog_t<PosetProgWide>(f, jk->pmax, 4);
+      void* params[] = {(void*)&args, (void*)&pg};
+      MCCBN_CUDA(cudaLaunchKernel((const void*)jk->kern, dim3(grid), dim3(kFwdBlock), params, jk->smem, s));
+    } else {
+      PosetProg pg = build_prog(f, jk->pmax, 4);
+      void* params[] = {(void*)&args, (void*)&pg};
+      MCCBN_CUDA(cudaLaunchKernel((const void*)jk->kern, dim3(grid), dim3(kFwdBlock), params, jk->smem, s));
+    }
     ctx->launches++;
   }
 

@@ -8,9 +8,9 @@ from mccbn_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("p,times", [(5, False), (16, True), (23, False), (30, False), (32, True)])
+@pytest.mark.parametrize("p,times", [(5, False), (16, True), (23, False), (30, False), (32, True), (40, False), (64, True)])
 def test_specialised_equals_generic(p, times):
-    c = synth.make_config(p, 50, eps=0.07, seed=p, density=0.2)
+    c = synth.make_config(p, 50, eps=0.07, seed=p, density=0.2 if p <= 32 else 0.06)  # p > 32: the wide (64-bit) kernels
     t = c["times"] if times else None
     try:
         mc.set_jit(0)
