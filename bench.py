@@ -260,8 +260,9 @@ def run_ours(args):
                    "parallelism": (f"observations sharded over {world} rank(s); per iteration one exchange of p+5 doubles, " +
                                    ("fused into the reduction/M-step kernels over NVLink peer memory"
                                     if args.exchange == "peer" else "ncclAllReduce")),
-                   "kernel": ("generic estep_forward_kernel" if args.no_jit or sampling != "forward" else
-                              "NVRTC poset-specialised estep_forward_body (compiled during warm-up)")},
+                   "kernel": ({"forward": "estep_forward", "pool": "pool_generate + estep_pool"}.get(
+                       sampling, "estep_conditional") + (" (generic)" if args.no_jit or sampling == "pool" else
+                                                         " (NVRTC poset-specialised, compiled during warm-up)"))},
         "e2e": {"value": N * L_eff / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world, "call": "mccbn_obs_log_likelihood (host buffers, one E-step)"},
         "gpu_launches": int(launches),
@@ -287,11 +288,15 @@ def run_ours(args):
         except Exception:
             pass
         ach = value / world * words_per_sample
+        if sampling != "forward":
+            # nominal samples: the backward scheme skips the incompatible genotypes of the Hamming ball and the pool scheme
+            # counts (observation, pool entry) pairs, so a words-per-sample ceiling does not apply; see profiles/README.md
+            ach, peak = None, None
         hbm_bytes = (N / world) * (8 + (5 + p) * 8 * 2) + 0.0  # obs word read + partial record write/read per obs
         line["roofline"] = {
             "bound": "instruction issue (Philox INT32 + FP32/SFU); not hbm/tensor",
-            "achieved": ach / 1e9, "peak": (peak / 1e9) if peak else None, "unit": "Gword/s (32-bit Philox output)",
-            "frac": (ach / peak) if peak else None, "traffic": ncu_traffic_bytes(args.config),
+            "achieved": (ach / 1e9) if ach else None, "peak": (peak / 1e9) if peak else None,
+            "unit": "Gword/s (32-bit Philox output)", "frac": (ach / peak) if (ach and peak) else None, "traffic": ncu_traffic_bytes(args.config),
             "words_per_sample": words_per_sample,
             "peak_source": "pure Philox4x32-10 generator micro-kernel (IMAD.WIDE-bound) measured live on this GPU; "
                            "frac = share of the step the multiplier pipe alone would need (see profiles/README.md "
