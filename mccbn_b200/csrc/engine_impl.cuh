@@ -131,6 +131,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.key1 = key.k1;
     a.cw = eval_id[c];
     a.PS = PS();
+    a.next_item = item_counter.ensure(1);
+    MCCBN_CUDA(cudaMemsetAsync(a.next_item, 0, sizeof(unsigned long long), s));
     const int warps_per_block = kFwdBlock / 32;
     long long blocks = (n_items + warps_per_block - 1) / warps_per_block;
     // 32 < p <= 64 exists as a specialised kernel only: compile regardless of the work announced

@@ -40,6 +40,8 @@ struct CondArgs {
   uint32_t key0, key1;
   uint32_t cw;
   int PS;
+  unsigned long long* next_item;  // work counter (zeroed before the launch): items cost between nothing and reps x
+                                  // |ball| samples (incompatible genotypes are skipped), so warps claim them dynamically
 };
 
 template <typename real>
@@ -236,7 +238,13 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
   const uint32_t key1 = iter_key(a.key1, mdl);
   const uint32_t eps_thr = (MODE == kCondBernoulli) ? (uint32_t)fmin(mdl->eps * 4294967296.0, 4294967295.0) : 0u;
 
-  for (long long item = gw; item < a.n_items; item += nw) {
+  (void)gw;
+  (void)nw;
+  for (;;) {
+    long long item = 0;
+    if (lane == 0) item = (long long)atomicAdd(a.next_item, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= a.n_items) break;
     const int i = (int)(item / a.chunks);
     const int ch = (int)(item - (long long)i * a.chunks);
     const uint64_t yw = a.obs_bits[i];

@@ -452,6 +452,7 @@ struct mccbn_problem {
 
   // finalize + second-stage reduction + M-step; one fused launch on a single GPU (finalize_mstep_kernel)
   DevBuf<unsigned> fuse_counter;
+  DevBuf<unsigned long long> item_counter;  // dynamic work distribution of the conditional kernels
   void run_finalize_mstep(int c, int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out,
                           int update_params) {
     static const bool fuse = [] {
