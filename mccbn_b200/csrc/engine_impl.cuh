@@ -74,6 +74,16 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.key1 = key.k1;
     a.cw = eval_id[c];
     a.PS = PS();
+    // warps claim items from a counter instead of striding: all items cost the same, but SMs do not finish at the same
+    // time (cfg 3: 22.1 -> 20.9 ms); MCCBN_FWD_DYNAMIC=0 restores the static assignment
+    static const bool dynamic_items = [] {
+      const char* e = std::getenv("MCCBN_FWD_DYNAMIC");
+      return !(e && std::strcmp(e, "0") == 0);
+    }();
+    if (dynamic_items) {
+      a.next_item = item_counter.ensure(1);
+      MCCBN_CUDA(cudaMemsetAsync(a.next_item, 0, sizeof(unsigned long long), s));
+    }
     if (precision == 1)
       launch_forward<double>(a, flat[c], times_given, grid_x, c);
     else if (jk)

@@ -45,6 +45,7 @@ struct FwdArgs {
                              // can be replayed
   uint32_t cw;               // Philox counter word 3 (evaluation / candidate id)
   int PS;                    // record stride = kStatHdr + p
+  unsigned long long* next_item;  // optional work counter (zeroed before the launch): warps claim items dynamically
 };
 
 // key word 1 = (EM iteration << 4) | purpose (make_key, philox.cuh); the iteration is read from the model on the device
@@ -323,7 +324,12 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog&
   const int flip = mdl->flip;
   const uint32_t key1 = iter_key(a.key1, mdl);
 
-  for (long long item = gw; item < a.n_items; item += nw) {
+  for (long long item = gw;; item += nw) {
+    if (a.next_item) {  // warp-uniform
+      if (lane == 0) item = (long long)atomicAdd(a.next_item, 1ull);
+      item = __shfl_sync(0xffffffffu, item, 0);
+    }
+    if (item >= a.n_items) break;
     const int i = (int)(item / a.chunks);
     const int ch = (int)(item - (long long)i * a.chunks);
     const word_t yt = to_topo_bits<PMAX>(pg, a.obs_bits[i]);
