@@ -147,6 +147,29 @@ int mccbn_MCEM(mccbn_ctx* ctx, const double* ilambda, const int* poset, const in
                float max_lambda, float lambda_s, int sampling_time_available, int seed, int N, int p,
                double* lambda_out, double* llhood_out, char* err, size_t errlen);
 
+/* ---- callers of the OT-CBN conditional proposal -----------------------------------------------------
+ * replaces `drawHiddenVarsSamples` (src/mcem.cpp:214-248; .Call'ed by R/mcem_genotype_probabilities.r:17,65): N draws of
+ * the conditional proposal for ONE genotype O_vec at sampling time `time` (drawn ~ Exp(lambda_s) per sample when
+ * !sampling_time_available).  T is N x p column-major (waiting times by event id), densities[N] the log proposal
+ * density of each draw; time_out[N] (may be NULL; not in the reference's list) the sampling time each draw used.
+ * The reference consumes R's global generator; here the draws are Philox streams of `seed`. */
+int mccbn_drawHiddenVarsSamples(mccbn_ctx* ctx, int N, const int* O_vec, double time, const double* lambda,
+                                const int* poset, const int* topo_path, float lambda_s, int sampling_time_available,
+                                int seed, int p, double* T, double* densities, double* time_out, char* err,
+                                size_t errlen);
+/* replaces `expectedTimeDifference` (src/mcem.cpp:251-276): E[Z_j | genotype] by self-normalised importance sampling */
+int mccbn_expectedTimeDifference(mccbn_ctx* ctx, int nrOfSamples, const int* O_vec, double time, const double* lambda,
+                                 const int* poset, const int* topo_path, float lambda_s, int sampling_time_available,
+                                 int seed, int p, double* time_difference, char* err, size_t errlen);
+/* batched form of `loglike_importance_sampling` (R/mcem_genotype_probabilities.r:10-23), which loops over the
+ * observations with one .Call("drawHiddenVarsSamples") each: every (observation, sample) pair in ONE launch.
+ * probs[N] (may be NULL) = weights[i] * (logsumexp_l(log P(Z_il) - log q_il) - log nrOfSamples); approx_loglike = sum.
+ * All observations must be compatible with the poset (the R caller filters them, :86-91). */
+int mccbn_loglike_importance_sampling(mccbn_ctx* ctx, const int* poset, const double* lambda, const int* obs_events,
+                                      const double* sampling_times, int nrOfSamples, const double* weights,
+                                      float lambda_s, int sampling_times_available, int seed, int N, int p,
+                                      double* approx_loglike, double* probs, char* err, size_t errlen);
+
 /* ---- indexing seams (bit-exact tier) --------------------------------------------------------------------- */
 
 /* ---- forward simulators of the generative model (test / benchmark-data seams of the reference) -------------------

@@ -306,6 +306,75 @@ def estimate_mutation_rates(poset, genotypes, sampling_times=None, weights=None,
     return dict(lambda_=out_l, llhood=out_ll.value)
 
 
+# ---- OT-CBN callers of the conditional proposal (R/mcem_genotype_probabilities.r) ---------------------------------
+def _topo(poset):
+    """my.topological.sort(poset) - 1; the library derives its own order and reports cycles itself"""
+    from .synth import topological_sort
+    try:
+        return i32(np.array(topological_sort(poset)))
+    except ValueError:
+        return i32(np.arange(poset.shape[0]))
+
+
+def draw_hidden_vars_samples(N, genotype, time, lambda_, poset, lambda_s=1.0, sampling_time_available=True, seed=1,
+                             ctx=None):
+    """.Call("drawHiddenVarsSamples", ...) (src/mcem.cpp:214-248): dict(T=N x p, densities=N, time=N)."""
+    g, poset, lam = i32(genotype), i32(poset), f64(lambda_)
+    p = poset.shape[0]
+    T = np.zeros((int(N), p), order="F")
+    dens = np.zeros(int(N))
+    ts = np.zeros(int(N))
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_drawHiddenVarsSamples(_ctx(ctx), int(N), ptr(g), C.c_double(float(time)), ptr(lam),
+                                                   ptr(poset), ptr(_topo(poset)), C.c_float(lambda_s),
+                                                   int(bool(sampling_time_available)), int(seed), p, ptr(T), ptr(dens),
+                                                   ptr(ts), *e.args))
+    return dict(T=T, densities=dens, time=ts)
+
+
+def expected_time_difference(nrOfSamples, genotype, time, lambda_, poset, lambda_s=1.0, sampling_time_available=True,
+                             seed=1, ctx=None):
+    """.Call("expectedTimeDifference", ...) (src/mcem.cpp:251-276)."""
+    g, poset, lam = i32(genotype), i32(poset), f64(lambda_)
+    p = poset.shape[0]
+    out = np.zeros(p)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_expectedTimeDifference(_ctx(ctx), int(nrOfSamples), ptr(g), C.c_double(float(time)),
+                                                    ptr(lam), ptr(poset), ptr(_topo(poset)), C.c_float(lambda_s),
+                                                    int(bool(sampling_time_available)), int(seed), p, ptr(out),
+                                                    *e.args))
+    return out
+
+
+def loglike_importance_sampling(poset, lambda_, obs_events, sampling_times, nrOfSamples, weights=None, lambda_s=1.0,
+                                sampling_times_available=True, seed=1, ctx=None):
+    """loglike_importance_sampling (R/mcem_genotype_probabilities.r:10-23), all observations in one launch:
+    dict(approx_loglike, probs)."""
+    obs, poset, lam = i32(np.atleast_2d(obs_events)), i32(poset), f64(lambda_)
+    N, p = obs.shape
+    t = np.zeros(N) if sampling_times is None else f64(sampling_times)
+    wt = np.ones(N) if weights is None else f64(weights)
+    probs = np.zeros(N)
+    ll = C.c_double(0)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_loglike_importance_sampling(_ctx(ctx), ptr(poset), ptr(lam), ptr(obs), ptr(t),
+                                                         int(nrOfSamples), ptr(wt), C.c_float(lambda_s),
+                                                         int(bool(sampling_times_available)), int(seed), N, p,
+                                                         C.byref(ll), ptr(probs), *e.args))
+    return dict(approx_loglike=ll.value, probs=probs)
+
+
+def genotype_probability_fast(poset, lambda_, genotype, time, nrOfSamples=100, lambda_s=1.0,
+                              sampling_time_available=True, seed=1, ctx=None):
+    """genotype_probability_fast (R/mcem_genotype_probabilities.r:54-70): 0 for a genotype the poset excludes."""
+    g = i32(genotype)
+    if not compatible_observations(g[None, :], poset, ctx=ctx)["compatible"][0]:
+        return 0.0
+    r = loglike_importance_sampling(poset, lambda_, g[None, :], [time], nrOfSamples, None, lambda_s,
+                                    sampling_time_available, seed, ctx)
+    return float(np.exp(r["approx_loglike"]))
+
+
 # ---- indexing and supplied-randomness seams -----------------------------------------------------------------------
 def flatten_poset(poset):
     poset = i32(poset)

@@ -1195,7 +1195,8 @@ int mccbn_conditional_from_uniforms(mccbn_ctx* c, const int* X, int L, const int
   MCCBN_CUDA(cudaMemcpyAsync(dTs.ensure(L), T_sampling, sizeof(double) * L, cudaMemcpyHostToDevice, s));
   MCCBN_CUDA(cudaMemcpyAsync(dLam.ensure(p), lambda, sizeof(double) * p, cudaMemcpyHostToDevice, s));
   conditional_from_uniforms_kernel<<<std::min(2048, (L + 127) / 128), 128, 0, s>>>(
-      dX.ptr, dU.ptr, dTs.ptr, L, dpos.ptr, dLam.ptr, dT.ensure(LP), dq.ensure(L), dpz.ensure(L), dInc.ensure(L));
+      dX.ptr, dU.ptr, dTs.ptr, L, dpos.ptr, dLam.ptr, dT.ensure(LP), dq.ensure(L), dpz.ensure(L), dInc.ensure(L),
+      SeamRng{});
   c->launches++;
   MCCBN_CUDA(cudaGetLastError());
   if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, dT.ptr, sizeof(double) * LP, cudaMemcpyDeviceToHost, s));
@@ -1686,6 +1687,115 @@ int mccbn_MCEM(mccbn_ctx* c, const double* ilambda, const int* poset, const int*
   }
   for (int j = 0; j < p; ++j) lambda_out[j] = avg_lambda[j] / (max_iter - record_iter);  // :206-207
   *llhood_out = (double)(avg_llhood / (max_iter - record_iter));
+  MCCBN_CATCH
+}
+
+// ---- the OT-CBN callers of the conditional proposal ------------------------------------------------
+// `drawHiddenVarsSamples` (src/mcem.cpp:214-248): N draws of the conditional proposal for ONE genotype; returns the
+// waiting times T (N x p column-major) and the log proposal densities.  R's global generator (runif / rexp sugar)
+// cannot be mirrored outside R: the draws come from Philox (53-bit uniforms), the arithmetic is the fp64 seam kernel.
+int mccbn_drawHiddenVarsSamples(mccbn_ctx* c, int N, const int* O_vec, double time, const double* lambda,
+                                const int* poset, const int* topo_path, float lambda_s,
+                                int sampling_time_available, int seed, int p, double* T, double* densities,
+                                double* time_out, char* err, size_t errlen) {
+  (void)topo_path;  // any valid topological order gives the same distribution; we derive our own
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (N < 0) throw Error(MCCBN_ERR_ARG, "drawHiddenVarsSamples: N < 0");
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  if (N == 0) return MCCBN_OK;
+  cudaStream_t s = c->stream;
+  DevPoset dp;
+  fill_dev_poset(f, dp);
+  DevBuf<DevPoset> dpos;
+  DevBuf<double> dLam, dT, dq, dpz, dTs;
+  const size_t NP = (size_t)N * p;
+  MCCBN_CUDA(cudaMemcpyAsync(dpos.ensure(1), &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dLam.ensure(p), lambda, sizeof(double) * p, cudaMemcpyHostToDevice, s));
+  SeamRng rng;
+  std::memset(&rng, 0, sizeof(rng));
+  rng.enabled = 1;
+  rng.draw_ts = sampling_time_available ? 0 : 1;
+  const PhiloxKey key = make_key((uint32_t)seed, 0u, 7u);
+  rng.k0 = key.k0;
+  rng.k1 = key.k1;
+  rng.cw = 0u;
+  rng.x_word = pack_genotype(O_vec, p);
+  rng.time = time;
+  rng.lambda_s = (double)lambda_s;
+  rng.Ts_out = time_out ? dTs.ensure(N) : nullptr;
+  conditional_from_uniforms_kernel<<<std::min(2048, (N + 127) / 128), 128, 0, s>>>(
+      nullptr, nullptr, nullptr, N, dpos.ptr, dLam.ptr, dT.ensure(NP), dq.ensure(N), dpz.ensure(N), nullptr, rng);
+  c->launches++;
+  MCCBN_CUDA(cudaGetLastError());
+  if (T) MCCBN_CUDA(cudaMemcpyAsync(T, dT.ptr, sizeof(double) * NP, cudaMemcpyDeviceToHost, s));
+  if (densities) MCCBN_CUDA(cudaMemcpyAsync(densities, dq.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (time_out) MCCBN_CUDA(cudaMemcpyAsync(time_out, dTs.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  MCCBN_CATCH
+}
+
+// one OT-CBN E-step (noise-free model, conditional proposal) over N observations with per-observation outputs
+static void otcbn_estep(mccbn_ctx* c, mccbn_problem& pb, const int* obs, const double* times, const double* weights,
+                        const int* poset, const double* lambda, int nrOfSamples, float lambda_s,
+                        int sampling_time_available, int seed, int N, int p) {
+  if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");
+  if (nrOfSamples < 1) throw Error(MCCBN_ERR_ARG, "nrOfSamples must be >= 1");
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.upload(obs, times, weights);
+  pb.ensure_trace(1);
+  pb.set_model(0, f, lambda, 0.5, lambda_s, 1e6f);
+  pb.enqueue_iteration(0, kOtcbn, nrOfSamples, 0, sampling_time_available != 0, (uint32_t)seed, 0, true, 0);
+}
+
+// `expectedTimeDifference` (src/mcem.cpp:251-276 -> _expectedTimeDifference :105-146): self-normalised importance
+// estimate of E[Z_j | genotype] from nrOfSamples conditional draws.  Same kernel as one observation of `MCEM`.
+int mccbn_expectedTimeDifference(mccbn_ctx* c, int nrOfSamples, const int* O_vec, double time, const double* lambda,
+                                 const int* poset, const int* topo_path, float lambda_s, int sampling_time_available,
+                                 int seed, int p, double* time_difference, char* err, size_t errlen) {
+  (void)topo_path;
+  MCCBN_TRY
+  c = get_ctx(c);
+  mccbn_problem pb;
+  otcbn_estep(c, pb, O_vec, &time, nullptr, poset, lambda, nrOfSamples, lambda_s, sampling_time_available, seed, 1, p);
+  cudaStream_t s = c->stream;
+  MCCBN_CUDA(cudaMemcpyAsync(time_difference, pb.out_T.ptr, sizeof(double) * p, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  MCCBN_CATCH
+}
+
+// `loglike_importance_sampling` (R/mcem_genotype_probabilities.r:10-23) for ALL observations in one launch instead of
+// one .Call("drawHiddenVarsSamples") per observation from an R loop:
+//   probs[i] = weights[i] (logsumexp_l(log P(Z_l) - log q_l) - log nrOfSamples),  approx_loglike = sum_i probs[i]
+int mccbn_loglike_importance_sampling(mccbn_ctx* c, const int* poset, const double* lambda, const int* obs_events,
+                                      const double* sampling_times, int nrOfSamples, const double* weights,
+                                      float lambda_s, int sampling_times_available, int seed, int N, int p,
+                                      double* approx_loglike, double* probs, char* err, size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (N < 1) throw Error(MCCBN_ERR_ARG, "loglike_importance_sampling: no observations");
+  mccbn_problem pb;
+  otcbn_estep(c, pb, obs_events, sampling_times, weights, poset, lambda, nrOfSamples, lambda_s,
+              sampling_times_available, seed, N, p);
+  cudaStream_t s = c->stream;
+  std::vector<double> w(N);
+  MCCBN_CUDA(cudaMemcpyAsync(w.data(), pb.out_w.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  double total = 0.0;
+  const double logn = std::log((double)nrOfSamples);
+  for (int i = 0; i < N; ++i) {
+    const double v = (weights ? weights[i] : 1.0) * (std::log(w[i]) - logn);
+    if (probs) probs[i] = v;
+    total += v;
+  }
+  if (approx_loglike) *approx_loglike = total;
   MCCBN_CATCH
 }
 

@@ -10,6 +10,7 @@
 // They are HBM-bound test seams (8 (p+1) bytes read per sample), not the production path.
 #pragma once
 #include "device_types.cuh"
+#include "philox.cuh"
 
 namespace mccbn {
 
@@ -92,7 +93,19 @@ __global__ void __launch_bounds__(kF64Block) estep_from_times_kernel(
   }
 }
 
-// Conditional proposal from supplied uniforms (generate_mutation_times, src/add_remove.cpp:156-203):
+// Source of the randomness of the conditional seam kernel below.  enabled == 0: X, U and Ts are the caller's arrays
+// (supplied-randomness tier).  enabled == 1: one genotype `x_word` shared by all samples, 53-bit Philox uniforms
+// (counter = (sample l, 0, event >> 1, cw)) and, if draw_ts, T_s ~ Exp(lambda_s) per sample (block 64) -- the legacy
+// OT-CBN export `drawHiddenVarsSamples` (src/mcem.cpp:214-248), which returns the draws themselves.
+struct SeamRng {
+  int enabled, draw_ts;
+  uint32_t k0, k1, cw;
+  uint64_t x_word;
+  double time, lambda_s;
+  double* Ts_out;  // optional: the sampling time used by sample l
+};
+
+// Conditional proposal (generate_mutation_times, src/add_remove.cpp:156-203; drawHiddenVarsSample, src/mcem.cpp:52-92):
 //   m = max_pa T (0 without parents); c = X_j ? T_s - m : +inf; z = -log1p(u expm1(-c lambda))/lambda;
 //   T_j = (X_j ? m : max(m, T_s)) + z; Z_j = T_j - m; log q += (log lambda - lambda z) - log(1 - exp(-lambda c))
 // plus cbn_density_log (:206-216) and the incompatibility flag any_j Z_j < 0 (src/mcem_hcbn.cpp:524).
@@ -100,13 +113,22 @@ __global__ void conditional_from_uniforms_kernel(const int* __restrict__ X, cons
                                                  const double* __restrict__ Ts, int L, const DevPoset* pos,
                                                  const double* __restrict__ lambda, double* __restrict__ Tdiff,
                                                  double* __restrict__ log_q, double* __restrict__ log_pz,
-                                                 int* __restrict__ incompatible) {
+                                                 int* __restrict__ incompatible, const SeamRng rng) {
   const int p = pos->p;
   double sumlog = 0.0;
   for (int j = 0; j < p; ++j) sumlog += log(lambda[j]);  // event-id order, as lambda.array().log().sum()
   for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
     double T[64], Zev[64];
-    const double ts = Ts[l];
+    double ts;
+    if (!rng.enabled) {
+      ts = Ts[l];
+    } else if (rng.draw_ts) {
+      const uint4 r = philox4x32_10((uint32_t)l, 0u, 64u, rng.cw, rng.k0, rng.k1);
+      ts = -log(u01_open0_d(r.x, r.y)) / rng.lambda_s;
+    } else {
+      ts = rng.time;
+    }
+    if (rng.enabled && rng.Ts_out) rng.Ts_out[l] = ts;
     double dens = 0.0;
     int inc = 0;
     for (int k = 0; k < p; ++k) {
@@ -119,9 +141,17 @@ __global__ void conditional_from_uniforms_kernel(const int* __restrict__ X, cons
         m = first ? tu : fmax(m, tu);  // rowwise().maxCoeff() over the parents (not clamped at 0)
         first = false;
       }
-      const bool xj = X[(size_t)ev * L + l] != 0;
+      bool xj;
+      double u;
+      if (!rng.enabled) {
+        xj = X[(size_t)ev * L + l] != 0;
+        u = U[(size_t)ev * L + l];
+      } else {
+        xj = (rng.x_word >> ev) & 1ull;
+        const uint4 r = philox4x32_10((uint32_t)l, 0u, (uint32_t)(ev >> 1), rng.cw, rng.k0, rng.k1);
+        u = (ev & 1) ? u01_open0_d(r.z, r.w) : u01_open0_d(r.x, r.y);
+      }
       const double cutoff = xj ? ts - m : INFINITY;
-      const double u = U[(size_t)ev * L + l];
       const double z = -log1p(u * expm1(-cutoff * rate)) / rate;
       const double base = xj ? m : fmax(m, ts);
       const double tsum = base + z;
@@ -136,7 +166,7 @@ __global__ void conditional_from_uniforms_kernel(const int* __restrict__ X, cons
     for (int j = 0; j < p; ++j) dot += Zev[j] * lambda[j];
     log_q[l] = dens;
     log_pz[l] = sumlog - dot;
-    incompatible[l] = inc;
+    if (incompatible) incompatible[l] = inc;
   }
 }
 

@@ -1521,6 +1521,89 @@ extern "C" int ref_MCEM_otcbn(const double* ilambda, const int* poset, const int
   return 0;
 }
 
+static std::vector<std::vector<int>> ot_parents(const int* poset, int p) {  // src/mcem.cpp:232-240
+  std::vector<std::vector<int>> parents(p);
+  for (int k = 0; k < p; ++k)
+    for (int i = 0; i < p; ++i)
+      if (poset[(size_t)k * p + i] == 1) parents[k].push_back(i);
+  return parents;
+}
+
+// drawHiddenVarsSamples (src/mcem.cpp:214-248): T is N x p column-major, densities N
+extern "C" int ref_drawHiddenVarsSamples(int N, const int* O_vec, double time, const double* lambda, const int* poset,
+                                         const int* topo_path, float lambda_s, int time_available, int seed, int p,
+                                         double* T, double* densities) {
+  using namespace ref;
+  try {
+    StdRng rng((unsigned)seed);
+    const auto parents = ot_parents(poset, p);
+    const std::vector<int> O(O_vec, O_vec + p), topo(topo_path, topo_path + p);
+    const std::vector<double> lam(lambda, lambda + p);
+    for (int i = 0; i < N; ++i) {
+      const std::vector<double> t = drawHiddenVarsSample(O, time, lam, topo, parents, densities[i], lambda_s,
+                                                         time_available != 0, rng);
+      for (int j = 0; j < p; ++j) T[(size_t)j * N + i] = t[j];
+    }
+  } catch (const std::exception& e) {
+    return 9;
+  }
+  return 0;
+}
+
+// expectedTimeDifference (src/mcem.cpp:251-276)
+extern "C" int ref_expectedTimeDifference(int nrOfSamples, const int* O_vec, double time, const double* lambda,
+                                          const int* poset, const int* topo_path, float lambda_s, int time_available,
+                                          int seed, int p, double* out) {
+  using namespace ref;
+  try {
+    StdRng rng((unsigned)seed);
+    const auto parents = ot_parents(poset, p);
+    const std::vector<int> O(O_vec, O_vec + p), topo(topo_path, topo_path + p);
+    const std::vector<double> lam(lambda, lambda + p);
+    const std::vector<double> td = expectedTimeDifference(O, time, lam, topo, parents, nrOfSamples, lambda_s,
+                                                          time_available != 0, rng);
+    std::copy(td.begin(), td.end(), out);
+  } catch (const std::exception& e) {
+    return 9;
+  }
+  return 0;
+}
+
+// The proposal density of drawHiddenVarsSample as a function of its OUTPUT (src/mcem.cpp:64-90 with the draw `tmp`
+// recovered from T): for given waiting times T (N x p), genotype and per-sample sampling times, the log density the
+// sampler reports.  Lets a test check the (T, densities) pairs of another generator to fp64 accuracy.
+extern "C" int ref_otcbn_proposal_density(int N, const int* O_vec, const double* times, const double* lambda,
+                                          const int* poset, const int* topo_path, int p, const double* T,
+                                          double* densities) {
+  using namespace ref;
+  try {
+    const auto parents = ot_parents(poset, p);
+    std::vector<double> T_sum(p);
+    for (int i = 0; i < N; ++i) {
+      double dens = 0.0;
+      const double time = times[i];
+      for (int k = 0; k < p; ++k) {
+        const int e = topo_path[k];
+        double max_parents_t = 0.0;
+        for (int u : parents[e])
+          if (T_sum[u] > max_parents_t) max_parents_t = T_sum[u];
+        const double t = T[(size_t)e * N + i];
+        T_sum[e] = max_parents_t + t;
+        if (O_vec[e] == 1) {
+          dens += ot_dexp_log(t, lambda[e]) - ot_pexp_log(time - max_parents_t, lambda[e]);  // tmp = T[e]
+        } else {
+          const double tmp = T_sum[e] - std::max(time, max_parents_t);
+          dens += ot_dexp_log(tmp, lambda[e]);
+        }
+      }
+      densities[i] = dens;
+    }
+  } catch (const std::exception& e) {
+    return 9;
+  }
+  return 0;
+}
+
 // ================================================================================================
 // C interface (ctypes).  Return 0 = ok, 1 = not acyclic, 2 = zero weight, 9 = other error.
 // ================================================================================================

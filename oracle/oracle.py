@@ -360,6 +360,71 @@ def MCEM_otcbn(ilambda, poset, obs, times=None, max_iter=100, alpha=0.2, weights
     return dict(lambda_=out_l, llhood=out_ll.value)
 
 
+def _r_topo(poset):
+    """R's my.topological.sort order (Kahn, FIFO) - 1"""
+    p = poset.shape[0]
+    indeg = poset.sum(axis=0).astype(int)
+    order, ready = [], [j for j in range(p) if indeg[j] == 0]
+    while ready:
+        j = ready.pop(0)
+        order.append(j)
+        for c in np.nonzero(poset[j])[0]:
+            indeg[c] -= 1
+            if indeg[c] == 0:
+                ready.append(int(c))
+    return _i32(np.array(order))
+
+
+def draw_hidden_vars_samples(N, genotype, time, lambda_, poset, lambda_s=1.0, sampling_time_available=True, seed=1):
+    """drawHiddenVarsSamples (src/mcem.cpp:214-248): dict(T=N x p, densities=N)"""
+    g, poset, lam = _i32(genotype), _i32(poset), _f64(lambda_)
+    p = poset.shape[0]
+    T = np.zeros((N, p), order="F")
+    dens = np.zeros(N)
+    _chk(lib().ref_drawHiddenVarsSamples(int(N), _p(g), C.c_double(time), _p(lam), _p(poset), _p(_r_topo(poset)),
+                                         C.c_float(lambda_s), int(bool(sampling_time_available)), int(seed), p,
+                                         _p(T), _p(dens)))
+    return dict(T=T, densities=dens)
+
+
+def expected_time_difference(nrOfSamples, genotype, time, lambda_, poset, lambda_s=1.0, sampling_time_available=True,
+                             seed=1):
+    """expectedTimeDifference (src/mcem.cpp:251-276)"""
+    g, poset, lam = _i32(genotype), _i32(poset), _f64(lambda_)
+    p = poset.shape[0]
+    out = np.zeros(p)
+    _chk(lib().ref_expectedTimeDifference(int(nrOfSamples), _p(g), C.c_double(time), _p(lam), _p(poset),
+                                          _p(_r_topo(poset)), C.c_float(lambda_s), int(bool(sampling_time_available)),
+                                          int(seed), p, _p(out)))
+    return out
+
+
+def otcbn_proposal_density(genotype, times, lambda_, poset, T):
+    """log proposal density of drawHiddenVarsSample recomputed from its output T (N x p) and the sampling times"""
+    g, poset, lam, T, t = _i32(genotype), _i32(poset), _f64(lambda_), _f64(T), _f64(times)
+    N, p = T.shape
+    dens = np.zeros(N)
+    _chk(lib().ref_otcbn_proposal_density(N, _p(g), _p(t), _p(lam), _p(poset), _p(_r_topo(poset)), p, _p(T), _p(dens)))
+    return dens
+
+
+def loglike_importance_sampling(poset, lambda_, obs_events, sampling_times, nrOfSamples, weights=None, lambda_s=1.0,
+                                sampling_times_available=True, seed=1):
+    """loglike_importance_sampling (R/mcem_genotype_probabilities.r:3-23): one drawHiddenVarsSamples call per
+    observation (seed + i stands in for the advancing global R generator), cbn_density_ (:3-6), logsumexp."""
+    obs, lam = _i32(np.atleast_2d(obs_events)), _f64(lambda_)
+    N = obs.shape[0]
+    wt = np.ones(N) if weights is None else _f64(weights)
+    probs = np.zeros(N)
+    for i in range(N):
+        r = draw_hidden_vars_samples(nrOfSamples, obs[i], float(sampling_times[i]) if sampling_times is not None else 0.0,
+                                     lam, poset, lambda_s, sampling_times_available, seed + i)
+        values = (np.log(lam)[None, :] - r["T"] * lam[None, :]).sum(axis=1) - r["densities"]  # sum dexp(x, rates, log=TRUE)
+        m = values.max()
+        probs[i] = wt[i] * (m + np.log(np.exp(values - m).sum()) - np.log(nrOfSamples))
+    return dict(approx_loglike=float(probs.sum()), probs=probs)
+
+
 def adaptive_simulated_annealing(poset, obs, L, times=None, lambda_s=1.0, weights=None, sampling="forward", max_iter=100,
                                  update_step_size=20, tol=0.001, max_lambda=1e6, T0=50.0, adap_rate=0.3,
                                  acceptance_rate=None, step_size=None, max_iter_asa=10000, neighborhood_dist=1,

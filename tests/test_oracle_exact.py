@@ -269,3 +269,52 @@ def test_initialize_lambda_counts(oracle):
         expect = float(aux) * 1.0 / (1.0 - float(aux))
         assert lam[j] == pytest.approx(expect, rel=1e-12)
     assert eps0 == pytest.approx(oracle.num_incompatible_events(obs, poset) / (300 * 6))
+
+
+# ---- OT-CBN callers of the conditional proposal (src/mcem.cpp:214-276, R/mcem_genotype_probabilities.r) --------------
+def _otcbn_problem(seed=5, p=6):
+    cfg = synth.make_config(p, 30, eps=0.0, seed=seed, density=0.3)
+    comp = exact.compatible_states(cfg["poset"])
+    # a compatible genotype with about half of the events
+    x = sorted(comp, key=lambda s: abs(bin(s).count("1") - p // 2))[0]
+    g = np.array([(x >> j) & 1 for j in range(p)], np.int32)
+    return cfg, g, x
+
+
+@pytest.mark.parametrize("avail", [True, False])
+def test_otcbn_draw_hidden_vars_estimates_genotype_probability(oracle, avail):
+    """E_q[P(Z)/q(Z)] = P(X = genotype): the identity genotype_probability_fast relies on (K2 / K2')."""
+    cfg, g, x = _otcbn_problem()
+    lam, poset, t = cfg["lambdas"], cfg["poset"], 0.9
+    px = exact.genotype_probs_time(poset, lam, t) if avail else exact.genotype_probs_exp(poset, lam, 1.0)
+    est = []
+    for s in range(1, 13):
+        r = oracle.draw_hidden_vars_samples(4000, g, t, lam, poset, 1.0, avail, seed=s)
+        assert r["T"].shape == (4000, len(lam)) and (r["T"] >= 0).all()
+        logp = (np.log(lam)[None, :] - r["T"] * lam[None, :]).sum(axis=1)
+        est.append(np.exp(logp - r["densities"]).mean())
+    est = np.array(est)
+    se = est.std(ddof=1) / math.sqrt(est.size)
+    assert abs(est.mean() - px[x]) < 4 * se, (est.mean(), px[x], se)
+
+
+def test_otcbn_proposal_density_from_output(oracle):
+    """the density recomputed from the sampler's OUTPUT equals the density it reported (time given)"""
+    cfg, g, _ = _otcbn_problem(seed=8, p=7)
+    r = oracle.draw_hidden_vars_samples(500, g, 1.3, cfg["lambdas"], cfg["poset"], 1.0, True, seed=2)
+    d = oracle.otcbn_proposal_density(g, np.full(500, 1.3), cfg["lambdas"], cfg["poset"], r["T"])
+    np.testing.assert_allclose(d, r["densities"], rtol=1e-10, atol=1e-10)
+
+
+def test_otcbn_loglike_importance_sampling_exact(oracle):
+    """loglike_importance_sampling (R/mcem_genotype_probabilities.r:10-23) against the exact log-probabilities"""
+    cfg, _, _ = _otcbn_problem(seed=11)
+    poset, lam = cfg["poset"], cfg["lambdas"]
+    ok = oracle.compatible_observations(cfg["obs"], poset).astype(bool)
+    obs, times = cfg["obs"][ok][:8], cfg["times"][ok][:8]
+    wt = np.linspace(0.5, 2.0, obs.shape[0])
+    r = oracle.loglike_importance_sampling(poset, lam, obs, times, 20000, wt, 1.0, True, seed=3)
+    ex = np.array([wt[i] * math.log(exact.genotype_probs_time(poset, lam, times[i])[exact.mask_of(obs[i])])
+                   for i in range(obs.shape[0])])
+    np.testing.assert_allclose(r["probs"], ex, atol=0.05)
+    assert abs(r["approx_loglike"] - r["probs"].sum()) < 1e-12
