@@ -73,6 +73,19 @@ int mccbn_ctx_init_comm(mccbn_ctx* ctx, int rank, int world, const unsigned char
 int mccbn_ctx_peer_handle(mccbn_ctx* ctx, unsigned char handle[MCCBN_IPC_HANDLE_BYTES], char* err, size_t errlen);
 int mccbn_ctx_init_peers(mccbn_ctx* ctx, int rank, int world, const unsigned char* handles, char* err, size_t errlen);
 /* Counters for the bench contract: kernels launched by this library since the last reset. */
+/* In-process multi-GPU ("device team").  The reference's callers are a single process (an R session): with
+ * mccbn_set_gpus(G) -- or MCCBN_GPUS=G / MCCBN_GPUS=all in the environment -- the entries below that are called with
+ * ctx == NULL and without caller-side sharding (mccbn_em_options.obs_offset / N_global) split the observations over
+ * the first G devices themselves: one host thread and one context per device, the statistic vector exchanged through
+ * mailboxes inside the reduction / M-step kernels exactly as between the ranks of a multi-process job.  This is the
+ * role the reference's `thrds` argument plays for its OpenMP loop (src/mcem_hcbn.cpp:661-665).  Philox counters carry
+ * global observation indices: the result does not depend on G.
+ *   sharded by observation : mccbn_MCEM_hcbn, mccbn_obs_log_likelihood, mccbn_importance_weight
+ *   candidate-parallel     : mccbn_adaptive_simulated_annealing (every device holds all observations)
+ * n_gpus <= 1 turns it off; more devices than present are clamped.  mccbn_get_gpus() = devices a call would use. */
+int mccbn_set_gpus(int n_gpus, char* err, size_t errlen);
+int mccbn_get_gpus(void);
+
 uint64_t mccbn_kernel_launches(mccbn_ctx* ctx, int reset);
 
 /* ---- extended options shared by the EM entry points ------------------------------------------------------ */

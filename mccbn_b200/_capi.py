@@ -44,7 +44,7 @@ SYMBOLS = [
     "mccbn_poset_edit", "mccbn_set_jit", "mccbn_jit_compile_forward", "mccbn_jit_compile_conditional", "mccbn_sample_genotypes", "mccbn_sample_times",
     "mccbn_generate_genotypes", "mccbn_scale_path_to_mutation", "mccbn_cbn_density_log",
     "mccbn_complete_log_likelihood", "mccbn_draw_sample", "mccbn_coin_tossing", "mccbn_generate_mutation_times",
-    "mccbn_drawHiddenVarsSamples", "mccbn_expectedTimeDifference", "mccbn_loglike_importance_sampling",
+    "mccbn_set_gpus", "mccbn_get_gpus", "mccbn_drawHiddenVarsSamples", "mccbn_expectedTimeDifference", "mccbn_loglike_importance_sampling",
 ]
 
 

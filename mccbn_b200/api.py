@@ -81,6 +81,17 @@ def nccl_unique_id():
     return bytes(buf)
 
 
+def set_gpus(n):
+    """In-process multi-GPU: calls made without a context shard their observations over the first n devices
+    (mccbn_set_gpus; the role of the reference's `thrds`).  n <= 1 turns it off."""
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_set_gpus(int(n), *e.args))
+
+
+def get_gpus():
+    return int(capi.lib().mccbn_get_gpus())
+
+
 def device_count():
     return int(capi.lib().mccbn_device_count())
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -79,7 +80,12 @@ struct NcclApi {
 // cached block is never in use by in-flight work.  MCCBN_DEVICE_CACHE_MB caps the cache (default 4096, 0 = off).
 struct DeviceCache {
   std::mutex mu;
-  unsigned long long epoch = 0;  // bumped by every allocation: captured CUDA graphs hold raw pointers
+  std::atomic<unsigned long long> epoch[64] = {};  // per device, bumped by every allocation: captured CUDA graphs hold raw pointers
+  unsigned long long epoch_of_current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return epoch[dev & 63].load();
+  }
   std::multimap<std::pair<int, size_t>, void*> free_blocks;  // (device, bytes) -> block
   std::map<void*, std::pair<int, size_t>> live;               // block -> (device, bytes)
   size_t cached_bytes = 0, cap_bytes = (size_t)4096 << 20;
@@ -99,7 +105,7 @@ struct DeviceCache {
       auto it = free_blocks.lower_bound({dev, want});
       if (it != free_blocks.end() && it->first.first == dev && it->first.second <= 2 * want) {
         void* p = it->second;
-        ++epoch;
+        ++epoch[dev & 63];
         cached_bytes -= it->first.second;
         live[p] = it->first;
         free_blocks.erase(it);
@@ -107,7 +113,7 @@ struct DeviceCache {
       }
     }
     void* p = nullptr;
-    ++epoch;
+    ++epoch[dev & 63];
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
       cudaGetLastError();
@@ -194,6 +200,7 @@ struct mccbn_ctx {
   mccbn::Mailbox* mailbox = nullptr;
   mccbn::Mailbox* peer_box[mccbn::kMaxWorld] = {};
   bool peer_ready = false;
+  bool mailbox_host = false;  // member of an in-process team: the mailboxes are pinned host memory owned by the team
   unsigned long long xchg_seq = 0;
   mccbn::JitCache* jit = nullptr;  // poset-specialised kernels (jit.cuh)
   int jit_mode = -1;               // -1 auto (large problems only), 0 off, 1 always

@@ -422,6 +422,107 @@ static int report(const std::exception& e, char* err, size_t errlen) {
   return code;
 }
 
+// ---- in-process device team ---------------------------------------------------------------------------------------
+// The reference's callers are ONE process (an R session calling .Call): with MCCBN_GPUS=G (or mccbn_set_gpus) the
+// reference-facing entries that are given no context and no caller-side sharding split the observations over G
+// devices themselves -- one host thread and one context per device, the very code path a rank of a multi-process job
+// runs (global observation indices in the Philox counters => the result does not depend on G).  The statistic
+// exchange uses the same mailbox protocol as the multi-process path; the mailboxes of a team live in pinned, portable
+// host memory, which every device of the process can address without enabling peer access (p + 5 doubles per
+// iteration: the few microseconds of PCIe latency are irrelevant next to a millisecond E-step, and no later
+// cudaMalloc has to be mapped into the peers).
+struct Team {
+  std::vector<mccbn_ctx*> ctx;
+  Mailbox* boxes = nullptr;  // cudaHostAlloc(portable | mapped), one per member
+};
+static Team* g_team = nullptr;
+static int g_team_want = -1;  // -1: read MCCBN_GPUS on first use
+static int g_team_jit_mode = -1;  // mccbn_set_jit(NULL, mode) applies to the team members too
+
+static int team_want_locked() {
+  if (g_team_want < 0) {
+    g_team_want = 1;
+    if (const char* e = std::getenv("MCCBN_GPUS")) {
+      int n = 0;
+      cudaGetDeviceCount(&n);
+      cudaGetLastError();
+      g_team_want = std::strcmp(e, "all") == 0 ? std::max(1, n) : std::max(1, std::atoi(e));
+    }
+  }
+  return g_team_want;
+}
+
+// the team to shard over, or nullptr (single device).  N = number of observations of the call.
+static Team* team_for(int N) {
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  int G = std::min(team_want_locked(), kMaxWorld);
+  if (G > 1) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+    cudaGetLastError();
+    G = std::min(G, n);
+  }
+  if (G <= 1 || N < G) return nullptr;
+  if (g_team && (int)g_team->ctx.size() == G) return g_team;
+  if (g_team) {  // size changed: contexts of the old team are kept alive (a handful of streams), mailboxes reused
+    for (mccbn_ctx* c : g_team->ctx) c->peer_ready = false;
+  }
+  Team* t = new Team();
+  MCCBN_CUDA(cudaHostAlloc((void**)&t->boxes, sizeof(Mailbox) * G, cudaHostAllocPortable | cudaHostAllocMapped));
+  std::memset(t->boxes, 0, sizeof(Mailbox) * G);
+  for (int r = 0; r < G; ++r) {
+    mccbn_ctx* c = new mccbn_ctx();
+    ctx_init(c, r);
+    c->rank = r;
+    c->world = G;
+    c->mailbox = &t->boxes[r];
+    c->mailbox_host = true;
+    for (int q = 0; q < G; ++q) c->peer_box[q] = &t->boxes[q];
+    c->peer_ready = true;
+    c->jit_mode = g_team_jit_mode;
+    t->ctx.push_back(c);
+  }
+  g_team = t;
+  return t;
+}
+
+// f(rank, ctx, err, errlen) -> return code, on one host thread per member; the first failing rank's code and message
+// are reported (a rank that fails alone leaves the others waiting for its statistics until the peer timeout).
+template <class F>
+static void team_run(Team& t, F&& f) {
+  const int G = (int)t.ctx.size();
+  // every member starts the call from the same exchange number
+  unsigned long long base = 0;
+  for (mccbn_ctx* c : t.ctx) base = std::max(base, c->xchg_seq);
+  for (mccbn_ctx* c : t.ctx) c->xchg_seq = base;
+  std::vector<int> rc(G, MCCBN_OK);
+  std::vector<std::array<char, 512>> msg(G);
+  std::vector<std::thread> th;
+  for (int r = 0; r < G; ++r) {
+    msg[r][0] = 0;
+    th.emplace_back([&, r] { rc[r] = f(r, t.ctx[r], msg[r].data(), msg[r].size()); });
+  }
+  for (auto& x : th) x.join();
+  int bad = -1;
+  for (int r = 0; r < G; ++r)
+    if (rc[r] != MCCBN_OK && (bad < 0 || (std::strstr(msg[bad].data(), "timed out") && !std::strstr(msg[r].data(), "timed out"))))
+      bad = r;
+  if (bad >= 0) throw Error(rc[bad], msg[bad].data());
+}
+
+// rows [lo, hi) of a column-major N x p matrix as a column-major (hi - lo) x p matrix
+static std::vector<int> shard_rows(const int* obs, int N, int p, int lo, int hi) {
+  std::vector<int> out((size_t)(hi - lo) * p);
+  for (int j = 0; j < p; ++j)
+    std::memcpy(out.data() + (size_t)j * (hi - lo), obs + (size_t)j * N + lo, sizeof(int) * (size_t)(hi - lo));
+  return out;
+}
+static inline int shard_begin(int N, int G, int r) { return (int)((long long)N * r / G); }
+// a call shards itself only when the caller passed no context and does not shard on its own
+static inline bool caller_shards(const mccbn_em_options* opt, int N) {
+  return opt && (opt->obs_offset != 0 || (opt->N_global > 0 && opt->N_global != N));
+}
+
 // host-built weight table, same libm expression as the reference (src/mcem_hcbn.cpp:387-388)
 static std::vector<double> host_wtab(double eps, int p) {
   std::vector<double> w(65, 0.0);
@@ -465,8 +566,10 @@ static void lambda_from_counts(const FlatPoset& f, const unsigned long long* cnt
 }
 }  // namespace mccbn
 
+#include <array>
 #include <chrono>
 #include <functional>
+#include <thread>
 #include "engine_asa.cuh"
 
 // ================================================================================================================
@@ -500,8 +603,8 @@ void mccbn_ctx_destroy(mccbn_ctx* c) {
   cudaSetDevice(c->device);
   delete c->jit;
   for (int q = 0; q < kMaxWorld; ++q)
-    if (c->peer_box[q] && c->peer_box[q] != c->mailbox) cudaIpcCloseMemHandle(c->peer_box[q]);
-  if (c->mailbox) cudaFree(c->mailbox);
+    if (!c->mailbox_host && c->peer_box[q] && c->peer_box[q] != c->mailbox) cudaIpcCloseMemHandle(c->peer_box[q]);
+  if (c->mailbox && !c->mailbox_host) cudaFree(c->mailbox);
   if (c->comm) c->nccl.CommDestroy(c->comm);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -581,6 +684,23 @@ int mccbn_ctx_init_peers(mccbn_ctx* c, int rank, int world, const unsigned char*
   c->xchg_seq = 0;
   c->peer_ready = world > 1;
   MCCBN_CATCH
+}
+
+int mccbn_set_gpus(int n_gpus, char* err, size_t errlen) {
+  MCCBN_TRY
+  if (n_gpus < 0 || n_gpus > kMaxWorld) throw Error(MCCBN_ERR_ARG, "mccbn_set_gpus: between 0 and 16 devices");
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  g_team_want = std::max(1, n_gpus);
+  MCCBN_CATCH
+}
+
+int mccbn_get_gpus(void) {
+  try {
+    Team* t = team_for(1 << 30);
+    return t ? (int)t->ctx.size() : 1;
+  } catch (...) {
+    return 0;
+  }
 }
 
 uint64_t mccbn_kernel_launches(mccbn_ctx* c, int reset) {
@@ -670,6 +790,30 @@ int mccbn_MCEM_hcbn(mccbn_ctx* c, const double* ilambda, const int* poset, const
                     char* err, size_t errlen) {
   (void)thrds;
   MCCBN_TRY
+  if (!c && !caller_shards(opt, N)) {
+    if (Team* team = team_for(N)) {  // in-process multi-GPU: one thread per device, each running this entry on its shard
+      const int G = (int)team->ctx.size();
+      std::vector<std::vector<double>> lam_r(G, std::vector<double>(p));
+      std::vector<double> eps_r(G), ll_r(G);
+      team_run(*team, [&](int r, mccbn_ctx* cr, char* e, size_t el) {
+        const int lo = shard_begin(N, G, r), hi = shard_begin(N, G, r + 1);
+        const std::vector<int> sh = shard_rows(obs, N, p, lo, hi);
+        mccbn_em_options o;
+        if (opt) o = *opt; else std::memset(&o, 0, sizeof(o));
+        o.obs_offset = lo;
+        o.N_global = N;
+        if (r != 0) o.trace = nullptr, o.n_iter = nullptr;
+        return mccbn_MCEM_hcbn(cr, ilambda, poset, sh.data(), times ? times + lo : nullptr, lambda_s, eps,
+                               weights ? weights + lo : nullptr, L, sampling, max_iter, update_step_size, tol,
+                               max_lambda, neighborhood_dist, sampling_times_available, thrds, r == 0 ? verbose : 0,
+                               seed, hi - lo, p, lam_r[r].data(), &eps_r[r], &ll_r[r], &o, e, el);
+      });
+      std::copy(lam_r[0].begin(), lam_r[0].end(), lambda_out);  // the M-step is replicated: all ranks hold the same fit
+      *eps_out = eps_r[0];
+      *llhood_out = ll_r[0];
+      return MCCBN_OK;
+    }
+  }
   c = get_ctx(c);
   const Scheme sc = parse_scheme(sampling);
   Poset P;
@@ -742,6 +886,25 @@ int mccbn_obs_log_likelihood(mccbn_ctx* c, const int* obs, const int* poset, con
                              size_t errlen) {
   (void)thrds;
   MCCBN_TRY
+  if (!c && !caller_shards(opt, N)) {
+    if (Team* team = team_for(N)) {
+      const int G = (int)team->ctx.size();
+      std::vector<double> ll_r(G);
+      team_run(*team, [&](int r, mccbn_ctx* cr, char* e, size_t el) {
+        const int lo = shard_begin(N, G, r), hi = shard_begin(N, G, r + 1);
+        const std::vector<int> sh = shard_rows(obs, N, p, lo, hi);
+        mccbn_em_options o;
+        if (opt) o = *opt; else std::memset(&o, 0, sizeof(o));
+        o.obs_offset = lo;
+        o.N_global = N;
+        return mccbn_obs_log_likelihood(cr, sh.data(), poset, lambda, eps, weights ? weights + lo : nullptr,
+                                        times ? times + lo : nullptr, L, sampling, neighborhood_dist, lambda_s,
+                                        sampling_times_available, thrds, seed, hi - lo, p, &ll_r[r], &o, e, el);
+      });
+      *llhood_out = ll_r[0];  // summed over the ranks inside the reduction kernels
+      return MCCBN_OK;
+    }
+  }
   c = get_ctx(c);
   mccbn_problem pb;
   single_estep(c, pb, obs, poset, lambda, eps, weights, times, L, sampling, neighborhood_dist, lambda_s,
@@ -761,6 +924,30 @@ int mccbn_importance_weight(mccbn_ctx* c, const int* obs, unsigned L, const int*
                             const mccbn_em_options* opt, char* err, size_t errlen) {
   (void)thrds;
   MCCBN_TRY
+  if (!c && !caller_shards(opt, N)) {
+    if (Team* team = team_for(N)) {  // per-observation outputs: every rank fills the rows of its shard
+      const int G = (int)team->ctx.size();
+      team_run(*team, [&](int r, mccbn_ctx* cr, char* e, size_t el) {
+        const int lo = shard_begin(N, G, r), hi = shard_begin(N, G, r + 1), n = hi - lo;
+        const std::vector<int> sh = shard_rows(obs, N, p, lo, hi);
+        mccbn_em_options o;
+        if (opt) o = *opt; else std::memset(&o, 0, sizeof(o));
+        o.obs_offset = lo;
+        o.N_global = N;
+        std::vector<double> td(Tdiff ? (size_t)n * p : 0);
+        const int rc = mccbn_importance_weight(cr, sh.data(), L, poset, lambda, eps, times ? times + lo : nullptr,
+                                               sampling, neighborhood_dist, lambda_s, sampling_times_available, thrds,
+                                               seed, n, p, w_sum ? w_sum + lo : nullptr,
+                                               w_sum_sq ? w_sum_sq + lo : nullptr, L_eff ? L_eff + lo : nullptr,
+                                               dist ? dist + lo : nullptr, Tdiff ? td.data() : nullptr, &o, e, el);
+        if (rc == MCCBN_OK && Tdiff)
+          for (int j = 0; j < p; ++j)
+            std::memcpy(Tdiff + (size_t)j * N + lo, td.data() + (size_t)j * n, sizeof(double) * (size_t)n);
+        return rc;
+      });
+      return MCCBN_OK;
+    }
+  }
   c = get_ctx(c);
   mccbn_problem pb;
   single_estep(c, pb, obs, poset, lambda, eps, nullptr, times, L, sampling, neighborhood_dist, lambda_s,
@@ -1473,8 +1660,15 @@ int mccbn_set_jit(mccbn_ctx* c, int mode) {
   char* err = nullptr;
   size_t errlen = 0;
   MCCBN_TRY
+  const int m = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  if (!c) {  // the default context and the in-process team behind it
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    g_team_jit_mode = m;
+    if (g_team)
+      for (mccbn_ctx* t : g_team->ctx) t->jit_mode = m;
+  }
   c = get_ctx(c);
-  c->jit_mode = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  c->jit_mode = m;
   MCCBN_CATCH
 }
 
@@ -1556,6 +1750,26 @@ int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int
                                        double* llhood_out, char* err, size_t errlen) {
   (void)thrds;
   MCCBN_TRY
+  if (!c) {
+    if (Team* team = team_for(N)) {  // candidate-parallel annealing: every member is given ALL observations
+      const int G = (int)team->ctx.size();
+      std::vector<std::vector<double>> lam_r(G, std::vector<double>(p));
+      std::vector<std::vector<int>> pos_r(G, std::vector<int>((size_t)p * p));
+      std::vector<double> eps_r(G), ll_r(G);
+      team_run(*team, [&](int r, mccbn_ctx* cr, char* e, size_t el) {
+        return mccbn_adaptive_simulated_annealing(cr, poset, obs, times, lambda_s, weights, L, sampling, max_iter_EM,
+                                                  update_step_size, tol, max_lambda, T0, adap_rate, acceptance_rate,
+                                                  step_size, max_iter_ASA, neighborhood_dist, adaptive, outdir,
+                                                  sampling_times_available, thrds, r == 0 ? verbose : 0, seed, N, p,
+                                                  lam_r[r].data(), &eps_r[r], pos_r[r].data(), &ll_r[r], e, el);
+      });
+      std::copy(lam_r[0].begin(), lam_r[0].end(), lambda_out);
+      std::copy(pos_r[0].begin(), pos_r[0].end(), poset_out);
+      *eps_out = eps_r[0];
+      *llhood_out = ll_r[0];
+      return MCCBN_OK;
+    }
+  }
   c = get_ctx(c);
   const Scheme sc = parse_scheme(sampling);
   if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");

@@ -13,6 +13,8 @@
 // NVRTC (libnvrtc.so.12) and the loaded module are reached through dlopen / the CUDA runtime library-management API;
 // if NVRTC is unavailable or compilation fails the generic kernel is used (still the device path, never the CPU).
 #pragma once
+#include <mutex>
+#include <thread>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <sys/stat.h>
@@ -395,6 +397,8 @@ static std::string jit_cache_path(const std::string& src) {
   else if (const char* h = std::getenv("HOME")) dir = std::string(h) + "/.cache/mccbn_b200";
   if (dir.empty() || dir == "off") return "";
   static std::string made;  // create the directory once per process, not once per lookup
+  static std::mutex made_mu;  // several device threads of one process (in-process team) look kernels up concurrently
+  std::lock_guard<std::mutex> made_lk(made_mu);
   if (made != dir) {  // mkdir -p
     for (size_t i = 1; i <= dir.size(); ++i)
       if (i == dir.size() || dir[i] == '/') ::mkdir(dir.substr(0, i).c_str(), 0755);
@@ -476,7 +480,8 @@ struct JitCache {
     if (!have && jit_compile(rtc, src, cc)) {
       have = true;
       if (!path.empty()) {  // write-then-rename: safe with several ranks compiling the same kernel
-        const std::string tmp = path + "." + std::to_string((long)getpid());
+        const std::string tmp = path + "." + std::to_string((long)getpid()) + "." +
+                                std::to_string(std::hash<std::thread::id>()(std::this_thread::get_id()));
         if (FILE* fp = std::fopen(tmp.c_str(), "wb")) {
           const bool okw = std::fwrite(cc.cubin.data(), 1, cc.cubin.size(), fp) == cc.cubin.size();
           std::fclose(fp);

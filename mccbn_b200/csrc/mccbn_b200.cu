@@ -11,6 +11,9 @@
 //   the host synchronises once per `update_step_size` iterations to apply the reference's batch-average /
 //   convergence rule on the trace rows.
 #include <algorithm>
+#include <array>
+#include <atomic>
+#include <thread>
 #include <cfloat>
 #include <mutex>
 #include <sstream>
@@ -135,6 +138,16 @@ static void optin_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024)
     MCCBN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
+// cudaFuncSetAttribute is per device: opt in once per (kernel, device), not once per process
+#define MCCBN_OPTIN_ONCE(bytes, ...)                                        \
+  do {                                                                      \
+    static std::atomic<unsigned long long> done__{0};                       \
+    const unsigned long long bit__ = 1ull << (ctx->device & 63);            \
+    if (!(done__.load() & bit__)) {                                         \
+      optin_smem(__VA_ARGS__, bytes);                                       \
+      done__.fetch_or(bit__);                                               \
+    }                                                                       \
+  } while (0)
 }  // namespace mccbn
 
 struct mccbn_problem {
@@ -303,12 +316,10 @@ struct mccbn_problem {
     const PosetProg pg = build_prog(f, PM, (int)sizeof(real));                                          \
     constexpr size_t sm = fwd_smem_bytes<real, PM>();                                                   \
     if (times_given) {                                                                                  \
-      static bool once = (optin_smem(estep_forward_kernel<real, PM, true>, sm), true);                  \
-      (void)once;                                                                                       \
+      MCCBN_OPTIN_ONCE(sm, estep_forward_kernel<real, PM, true>);                  \
       estep_forward_kernel<real, PM, true><<<grid, kFwdBlock, sm, s>>>(a, pg);                          \
     } else {                                                                                            \
-      static bool once = (optin_smem(estep_forward_kernel<real, PM, false>, sm), true);                 \
-      (void)once;                                                                                       \
+      MCCBN_OPTIN_ONCE(sm, estep_forward_kernel<real, PM, false>);                 \
       estep_forward_kernel<real, PM, false><<<grid, kFwdBlock, sm, s>>>(a, pg);                         \
     }                                                                                                   \
   } while (0)
@@ -322,12 +333,10 @@ struct mccbn_problem {
     const PosetProgWide pg = build_prog_t<PosetProgWide>(f, PM, 4);                                         \
     constexpr size_t sm = fwd_smem_bytes<float, PM>();                                                      \
     if (times_given) {                                                                                      \
-      static bool once = (optin_smem(estep_forward_wide_kernel<PM, true>, sm), true);                       \
-      (void)once;                                                                                           \
+      MCCBN_OPTIN_ONCE(sm, estep_forward_wide_kernel<PM, true>);                       \
       estep_forward_wide_kernel<PM, true><<<grid, kFwdBlock, sm, s>>>(a, pg);                               \
     } else {                                                                                                \
-      static bool once = (optin_smem(estep_forward_wide_kernel<PM, false>, sm), true);                      \
-      (void)once;                                                                                           \
+      MCCBN_OPTIN_ONCE(sm, estep_forward_wide_kernel<PM, false>);                      \
       estep_forward_wide_kernel<PM, false><<<grid, kFwdBlock, sm, s>>>(a, pg);                              \
     }                                                                                                       \
   } while (0)
@@ -401,7 +410,7 @@ struct mccbn_problem {
       std::ostringstream k;
       k << (int)scheme << ':' << L << ':' << neighborhood_dist << ':' << times_given << ':' << seed << ':' << update_params
         << ':' << precision << ':' << N << ':' << p << ':' << model_version[c] << ':' << eval_id[c] << ':' << trace_rows << ':'
-        << device_cache().epoch << ':' << (void*)s << ':' << ctx->jit_mode;
+        << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode;
       IterGraph& g = iter_graph[c];
       if (!g.exec || g.key != k.str()) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -434,7 +443,7 @@ struct mccbn_problem {
           std::ostringstream k2;
           k2 << (int)scheme << ':' << L << ':' << neighborhood_dist << ':' << times_given << ':' << seed << ':'
              << update_params << ':' << precision << ':' << N << ':' << p << ':' << model_version[c] << ':' << eval_id[c]
-             << ':' << trace_rows << ':' << device_cache().epoch << ':' << (void*)s << ':' << ctx->jit_mode;
+             << ':' << trace_rows << ':' << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode;
           g.key = k2.str();
         }
       }

@@ -35,3 +35,23 @@ def test_sharded_em_matches_single_gpu(world):
         assert v["identical_across_ranks"], key
         # same samples (Philox counters carry the global observation index); only the fp64 summation order differs
         assert v["max_rel_vs_single_gpu"] < 1e-9 and v["eps_abs"] < 1e-11 and v["ll_rel"] < 1e-10, (key, v)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_in_process_team(world):
+    """mccbn_set_gpus: ONE process (the reference's callers are an R session) shards over `world` devices itself."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, MCCBN_PEER_TIMEOUT_S="60")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_team_worker.py"), str(world)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("TEAM_RESULT ")][-1]
+    res = json.loads(line[len("TEAM_RESULT "):])
+    for sampling in ("forward", "backward"):
+        v = res[sampling]
+        assert v["lambda_rel"] < 1e-9 and v["eps_abs"] < 1e-11 and v["ll_rel"] < 1e-10 and v["obs_ll_rel"] < 1e-10, v
+        assert v["iw_w_rel"] < 1e-10 and v["iw_dist_abs"] < 1e-10 and v["iw_Tdiff_rel"] < 1e-9, v
+    assert res["weights_times_ll_rel"] < 1e-10 and res["after_error_ll_rel"] < 1e-10, res
+    assert res["zero_weight_error"][0] == 2 and "weight 0" in res["zero_weight_error"][1], res
+    assert res["asa_identical"], res
