@@ -82,6 +82,27 @@ def test_no_cpu_fallback():
         mc.compatible_observations(c["obs"], c["poset"])
 
 
+def test_device_team_arguments():
+    """mccbn_set_gpus: argument range; without devices a team request degrades to "one device" and the compute entries
+    still fail loudly (no CPU fallback behind the team path either)."""
+    with pytest.raises(mc.MccbnError) as e:
+        mc.set_gpus(-1)
+    assert e.value.code == 4
+    with pytest.raises(mc.MccbnError):
+        mc.set_gpus(17)
+    if mc.device_count() > 0:
+        pytest.skip("CUDA device present")
+    mc.set_gpus(8)
+    try:
+        assert mc.get_gpus() == 1
+        c = synth.make_config(5, 10, seed=1)
+        with pytest.raises(mc.MccbnError) as e:
+            mc.obs_loglikelihood(c["obs"], c["poset"], c["lambdas"], 0.1, L=8, seed=1)
+        assert e.value.code == 3 and "no CPU fallback" in str(e.value)
+    finally:
+        mc.set_gpus(1)
+
+
 def test_r_wrapper_argument_rules():
     with pytest.raises(ValueError):
         mc.obs_loglikelihood(np.zeros((2, 3), np.int32), np.zeros((3, 3), np.int32), np.ones(3), 0.1, L=4,
