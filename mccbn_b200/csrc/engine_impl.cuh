@@ -452,9 +452,8 @@ static int team_want_locked() {
   return g_team_want;
 }
 
-// the team to shard over, or nullptr (single device).  N = number of observations of the call.
-static Team* team_for(int N) {
-  std::lock_guard<std::mutex> lk(g_default_mu);
+// devices a call with N observations would be sharded over (1 = no team); g_default_mu held
+static int team_size_locked(int N) {
   int G = std::min(team_want_locked(), kMaxWorld);
   if (G > 1) {
     int n = 0;
@@ -462,11 +461,20 @@ static Team* team_for(int N) {
     cudaGetLastError();
     G = std::min(G, n);
   }
-  if (G <= 1 || N < G) return nullptr;
+  return (G <= 1 || N < G) ? 1 : G;
+}
+
+// the team to shard over, or nullptr (single device).  N = number of observations of the call.
+static Team* team_for(int N) {
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  const int G = team_size_locked(N);
+  if (G <= 1) return nullptr;
   if (g_team && (int)g_team->ctx.size() == G) return g_team;
-  if (g_team) {  // size changed: contexts of the old team are kept alive (a handful of streams), mailboxes reused
+  if (g_team) {  // size changed: the old team's contexts stay alive (a handful of streams) but are no longer used
     for (mccbn_ctx* c : g_team->ctx) c->peer_ready = false;
   }
+  int caller_device = 0;  // creating the contexts must not move the calling thread to another device
+  cudaGetDevice(&caller_device);
   Team* t = new Team();
   MCCBN_CUDA(cudaHostAlloc((void**)&t->boxes, sizeof(Mailbox) * G, cudaHostAllocPortable | cudaHostAllocMapped));
   std::memset(t->boxes, 0, sizeof(Mailbox) * G);
@@ -482,6 +490,7 @@ static Team* team_for(int N) {
     c->jit_mode = g_team_jit_mode;
     t->ctx.push_back(c);
   }
+  cudaSetDevice(caller_device);
   g_team = t;
   return t;
 }
@@ -490,6 +499,8 @@ static Team* team_for(int N) {
 // are reported (a rank that fails alone leaves the others waiting for its statistics until the peer timeout).
 template <class F>
 static void team_run(Team& t, F&& f) {
+  static std::mutex run_mu;  // one team call at a time: the members' streams, mailboxes and exchange numbers are shared
+  std::lock_guard<std::mutex> run_lk(run_mu);
   const int G = (int)t.ctx.size();
   // every member starts the call from the same exchange number
   unsigned long long base = 0;
@@ -695,12 +706,8 @@ int mccbn_set_gpus(int n_gpus, char* err, size_t errlen) {
 }
 
 int mccbn_get_gpus(void) {
-  try {
-    Team* t = team_for(1 << 30);
-    return t ? (int)t->ctx.size() : 1;
-  } catch (...) {
-    return 0;
-  }
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  return team_size_locked(1 << 30);
 }
 
 uint64_t mccbn_kernel_launches(mccbn_ctx* c, int reset) {
