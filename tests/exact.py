@@ -114,3 +114,16 @@ def k1_empty_poset(y, lambdas, eps, t):
 
 def all_genotypes(p):
     return np.array(list(itertools.product([0, 1], repeat=p)), dtype=np.int32)
+
+
+def forward_weight_moments(px, y_mask, eps, p):
+    """E[w] and E[w^2] of the forward scheme's importance weight w = eps^d (1-eps)^(p-d), d = d(X, Y), X ~ px.
+    The reference's diagnostic (utils/hcbn_test.r:415-590) is the effective sample size (sum w)^2 / sum w^2, whose
+    large-L limit is L E[w]^2 / E[w^2]."""
+    m1 = m2 = 0.0
+    for x, q in px.items():
+        d = bin(x ^ y_mask).count("1")
+        w = eps ** d * (1 - eps) ** (p - d)
+        m1 += q * w
+        m2 += q * w * w
+    return m1, m2

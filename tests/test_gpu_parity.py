@@ -373,6 +373,28 @@ def test_pool_given_times_matches_forward_exact():
     assert np.abs((mean - np.concatenate([ex[:, 0], ex[:, 0] * ex[:, 1]])) / se).max() < 4.0
 
 
+@pytest.mark.parametrize("times_given", [False, True])
+def test_effective_sample_size_forward(oracle, times_given):
+    """The reference's own diagnostic (utils/hcbn_test.r T4-T6): ESS = (sum w)^2 / sum w^2 per genotype from the
+    `_importance_weight` outputs (w, w_sqrt), against its exact large-L limit L E[w]^2 / E[w^2] (K2 / K2') and the
+    oracle's independent stream."""
+    c = _cfg(p=7, N=16, eps=0.1, seed=4)
+    L, eps = 100000, 0.1
+    times = c["times"] if times_given else None
+    r = mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], eps, time=times, seed=5)
+    o = oracle.importance_weight(c["obs"], L, c["poset"], c["lambdas"], eps, times=times, thrds=oracle.num_threads(),
+                                 seed=6)
+    ess, ess_o = r["w"] ** 2 / r["w_sqrt"], o["w"] ** 2 / o["w_sqrt"]
+    px = None if times_given else exact.genotype_probs_exp(c["poset"], c["lambdas"], 1.0)
+    for i in range(c["obs"].shape[0]):
+        if times_given:
+            px = exact.genotype_probs_time(c["poset"], c["lambdas"], times[i])
+        m1, m2 = exact.forward_weight_moments(px, exact.mask_of(c["obs"][i]), eps, 7)
+        lim = L * m1 * m1 / m2
+        assert abs(ess[i] / lim - 1) < 0.05 and abs(ess[i] / ess_o[i] - 1) < 0.07, (i, ess[i], ess_o[i], lim)
+        assert abs(r["w"][i] / (L * m1) - 1) < 0.03  # sum w -> L P(Y)
+
+
 def test_otcbn_mcem_matches_oracle(oracle):
     """Legacy OT-CBN entry (`MCEM`, src/mcem.cpp:307-335): noise-free model, conditional proposal with X == Y."""
     c = synth.make_config(7, 300, eps=0.0, seed=41, density=0.3)

@@ -318,3 +318,17 @@ def test_otcbn_loglike_importance_sampling_exact(oracle):
                    for i in range(obs.shape[0])])
     np.testing.assert_allclose(r["probs"], ex, atol=0.05)
     assert abs(r["approx_loglike"] - r["probs"].sum()) < 1e-12
+
+
+def test_effective_sample_size_forward(oracle):
+    """The reference's own diagnostic (utils/hcbn_test.r T4-T6): ESS = (sum w)^2 / sum w^2 per genotype, against its
+    exact large-L limit L E[w]^2 / E[w^2] from the genotype distribution (K2)."""
+    cfg = _small_problem(p=6, N=12, eps=0.1, seed=4)
+    L = 60000
+    r = oracle.importance_weight(cfg["obs"], L, cfg["poset"], cfg["lambdas"], 0.1, thrds=oracle.num_threads(), seed=5)
+    px = exact.genotype_probs_exp(cfg["poset"], cfg["lambdas"], 1.0)
+    ess = r["w"] ** 2 / r["w_sqrt"]
+    for i in range(cfg["obs"].shape[0]):
+        m1, m2 = exact.forward_weight_moments(px, exact.mask_of(cfg["obs"][i]), 0.1, 6)
+        assert abs(ess[i] / (L * m1 * m1 / m2) - 1) < 0.05, (i, ess[i], L * m1 * m1 / m2)
+        assert 1.0 <= ess[i] <= L
