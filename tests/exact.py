@@ -127,3 +127,43 @@ def forward_weight_moments(px, y_mask, eps, p):
         m1 += q * w
         m2 += q * w * w
     return m1, m2
+
+
+def brute_force_posterior(poset, lambdas, eps, M, seed=0, lambda_s=1.0):
+    """The reference's validation method T1 (utils/hcbn_test.r:101-193, hcbn_functions.r:163-203): simulate M draws of
+    the generative model with noise (R/cbn_sampler.r:93-135) in plain numpy and tabulate, per observed genotype y,
+    the frequency P(Y = y) and the conditional means E[Z_j | Y = y], E[d(X, Y) | Y = y] with their standard errors.
+    Independent of the oracle and of the device code.  Returns {y_mask: dict(n, prob, Z, Z_se, d, d_se)}."""
+    poset = np.asarray(poset)
+    lam = np.asarray(lambdas, float)
+    p = lam.size
+    rng = np.random.default_rng(seed)
+    Z = rng.exponential(1.0, (M, p)) / lam
+    Ts = rng.exponential(1.0 / lambda_s, M)
+    # topological order by repeated relaxation (p is small)
+    indeg = poset.sum(axis=0).astype(int)
+    order, ready = [], [j for j in range(p) if indeg[j] == 0]
+    while ready:
+        j = ready.pop(0)
+        order.append(j)
+        for c in np.nonzero(poset[j])[0]:
+            indeg[c] -= 1
+            if indeg[c] == 0:
+                ready.append(int(c))
+    T = np.zeros((M, p))
+    for j in order:
+        par = np.nonzero(poset[:, j])[0]
+        T[:, j] = Z[:, j] + (T[:, par].max(axis=1) if par.size else 0.0)
+    X = T <= Ts[:, None]
+    Y = X ^ (rng.random((M, p)) < eps)
+    d = (X ^ Y).sum(axis=1)
+    key = (Y * (1 << np.arange(p))).sum(axis=1)
+    out = {}
+    for y in np.unique(key):
+        sel = key == y
+        n = int(sel.sum())
+        if n < 2:
+            continue
+        out[int(y)] = dict(n=n, prob=n / M, Z=Z[sel].mean(axis=0), Z_se=Z[sel].std(axis=0, ddof=1) / math.sqrt(n),
+                           d=float(d[sel].mean()), d_se=float(d[sel].std(ddof=1) / math.sqrt(n)))
+    return out

@@ -395,6 +395,43 @@ def test_effective_sample_size_forward(oracle, times_given):
         assert abs(r["w"][i] / (L * m1) - 1) < 0.03  # sum w -> L P(Y)
 
 
+_T1_CACHE = {}
+
+
+def _t1_table():
+    if not _T1_CACHE:
+        c = _cfg(p=5, N=4, eps=0.1, seed=6)
+        bf = exact.brute_force_posterior(c["poset"], c["lambdas"], 0.1, 1500000, seed=1)
+        ys = sorted(bf, key=lambda y: -bf[y]["n"])[:6]
+        _T1_CACHE.update(c=c, bf=bf, ys=ys)
+    return _T1_CACHE["c"], _T1_CACHE["bf"], _T1_CACHE["ys"]
+
+
+@pytest.mark.parametrize("sampling,L,kw", [("forward", 100000, {}), ("bernoulli", 100000, {}),
+                                           ("backward", 32 * 2000, dict(neighborhood_dist=5)), ("pool", 4000, {})])
+def test_t1_brute_force_posterior_means(sampling, L, kw):
+    """The reference's validation method T1 (utils/hcbn_test.r:101-193): importance-sampling estimates of P(Y),
+    E[Z_j | Y] and E[d | Y] against frequencies / conditional means over 1.5e6 simulated noisy genotypes (plain numpy,
+    independent of the oracle and of the device code).  Every scheme with full support is consistent for them:
+    forward, bernoulli, backward with the whole cube as its ball, pool."""
+    c, bf, ys = _t1_table()
+    p, eps = 5, 0.1
+    obs = np.array([[(y >> j) & 1 for j in range(p)] for y in ys], np.int32)
+    reps = [mc.importance_weight(obs, L, c["poset"], c["lambdas"], eps, sampling=sampling, seed=s, **kw)
+            for s in range(1, 9)]
+    for i, y in enumerate(ys):
+        b = bf[y]
+        Zs = np.array([r["Tdiff"][i] for r in reps])
+        ds = np.array([r["dist"][i] for r in reps])
+        Leff = np.array([(r["L_eff"][i] if sampling == "backward" else L) for r in reps], float)
+        ps = np.array([r["w"][i] for r in reps]) / Leff
+        se_Z = np.sqrt(Zs.var(axis=0, ddof=1) / len(reps) + b["Z_se"] ** 2)
+        assert np.abs((Zs.mean(axis=0) - b["Z"]) / se_Z).max() < 4.5, (sampling, y, Zs.mean(axis=0), b["Z"])
+        assert abs(ds.mean() - b["d"]) < 4.5 * math.sqrt(ds.var(ddof=1) / len(reps) + b["d_se"] ** 2), (sampling, y)
+        se_p = math.sqrt(ps.var(ddof=1) / len(reps) + b["prob"] * (1 - b["prob"]) / 1500000)
+        assert abs(ps.mean() - b["prob"]) < 4.5 * se_p, (sampling, y, ps.mean(), b["prob"])
+
+
 def test_otcbn_mcem_matches_oracle(oracle):
     """Legacy OT-CBN entry (`MCEM`, src/mcem.cpp:307-335): noise-free model, conditional proposal with X == Y."""
     c = synth.make_config(7, 300, eps=0.0, seed=41, density=0.3)

@@ -332,3 +332,30 @@ def test_effective_sample_size_forward(oracle):
         m1, m2 = exact.forward_weight_moments(px, exact.mask_of(cfg["obs"][i]), 0.1, 6)
         assert abs(ess[i] / (L * m1 * m1 / m2) - 1) < 0.05, (i, ess[i], L * m1 * m1 / m2)
         assert 1.0 <= ess[i] <= L
+
+
+def _t1_targets(bf, k=6):
+    """the k most frequent observed genotypes of a brute-force table"""
+    return sorted(bf, key=lambda y: -bf[y]["n"])[:k]
+
+
+def test_t1_brute_force_posterior_means(oracle):
+    """Reference validation T1: importance-sampling estimates of P(Y), E[Z_j | Y] and E[d | Y] against brute-force
+    frequencies / conditional means over simulated noisy genotypes (an estimator-independent answer for E[Z | Y])."""
+    cfg = _small_problem(p=5, N=4, eps=0.1, seed=6)
+    poset, lam, eps, p = cfg["poset"], cfg["lambdas"], 0.1, 5
+    bf = exact.brute_force_posterior(poset, lam, eps, 1500000, seed=1)
+    ys = _t1_targets(bf)
+    obs = np.array([[(y >> j) & 1 for j in range(p)] for y in ys], np.int32)
+    L = 40000
+    reps = [oracle.importance_weight(obs, L, poset, lam, eps, thrds=oracle.num_threads(), seed=s) for s in range(1, 9)]
+    for i, y in enumerate(ys):
+        b = bf[y]
+        Zs = np.array([r["Tdiff"][i] for r in reps])
+        ds = np.array([r["dist"][i] for r in reps])
+        ps = np.array([r["w"][i] / L for r in reps])
+        se_Z = np.sqrt(Zs.var(axis=0, ddof=1) / len(reps) + b["Z_se"] ** 2)
+        assert np.abs((Zs.mean(axis=0) - b["Z"]) / se_Z).max() < 4.5, (y, Zs.mean(axis=0), b["Z"])
+        assert abs(ds.mean() - b["d"]) < 4.5 * math.sqrt(ds.var(ddof=1) / len(reps) + b["d_se"] ** 2)
+        se_p = math.sqrt(ps.var(ddof=1) / len(reps) + b["prob"] * (1 - b["prob"]) / 1500000)
+        assert abs(ps.mean() - b["prob"]) < 4.5 * se_p
