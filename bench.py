@@ -96,6 +96,17 @@ def philox_peak_words_per_s(torch):
     return float(lib.mccbn_microbench_philox(None, 5))
 
 
+def host_cores(orc):
+    """Threads for the CPU arms: every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers, so
+    omp_get_max_threads() would make the reference arm single-threaded in the N > 1 runs; the oracle takes the count as
+    an argument (`thrds`, like the reference) and calls omp_set_num_threads itself."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    return max(int(n), int(orc.num_threads()), 1)
+
+
 def run_reference(args):
     """Reference arm: the CPU oracle (the reference's OpenMP loop restated) on all host cores, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -105,7 +116,7 @@ def run_reference(args):
     import oracle as orc
     orc.build()
     cfg, p, N, L, sampling, desc = make_problem(args.config)
-    cores = orc.num_threads()
+    cores = host_cores(orc)
     kw = dict(L=L, sampling=sampling, thrds=cores)
     # calibrate a bounded slice: ~args.ref_seconds of CPU work per step
     n0 = min(N, 4 * cores)
@@ -325,7 +336,7 @@ def cpu_baseline(cfg, p, N, L, sampling, args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as orc
     orc.build()
-    cores = orc.num_threads()
+    cores = host_cores(orc)
     kw = dict(L=L, sampling=sampling, thrds=cores)
     n0 = min(N, 4 * cores)
     t0 = time.perf_counter()
