@@ -237,6 +237,16 @@ def run_ours(args):
 
     # ---- end-to-end through the C ABI with host buffers (one E-step per call) ----
     e2e_steps = max(2, min(args.steps, 5))
+    # the observations of the timed calls live in pinned host memory (column-major N x p int32, R's layout)
+    host_kind, pinned_keepalive = "pageable", None
+    try:
+        pinned_keepalive = torch.empty((obs.shape[1], obs.shape[0]), dtype=torch.int32).pin_memory()
+        view = pinned_keepalive.numpy().T  # F-contiguous (N, p) view of the pinned block: passed through without a copy
+        view[...] = obs
+        if view.flags["F_CONTIGUOUS"] and view.dtype == np.int32:
+            obs, host_kind = view, "pinned"
+    except Exception:
+        pinned_keepalive = None
 
     def e2e_call(seed):
         try:
@@ -275,7 +285,8 @@ def run_ours(args):
                        sampling, "estep_conditional") + (" (generic)" if args.no_jit or sampling == "pool" else
                                                          " (NVRTC poset-specialised, compiled during warm-up)"))},
         "e2e": {"value": N * L_eff / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
-                "d2h_bytes_per_step": d2h * world, "call": "mccbn_obs_log_likelihood (host buffers, one E-step)"},
+                "d2h_bytes_per_step": d2h * world,
+                "call": f"mccbn_obs_log_likelihood ({host_kind} host buffers, one E-step)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
