@@ -173,8 +173,10 @@ def run_ours(args):
     ctx = mc.Context(local)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    # forward scheme: NVRTC poset-specialised kernel (csrc/jit.cuh); compiled once during warm-up
-    mc.set_jit(0 if args.no_jit else 1, ctx=ctx)
+    # NVRTC poset-specialised kernels (csrc/jit.cuh) under the library's DEFAULT policy: the device-resident problem
+    # announces its work, the kernel is compiled during warm-up and the one-call e2e path finds it in the context's cache
+    if args.no_jit:
+        mc.set_jit(0, ctx=ctx)
     if world > 1:
         from mccbn_b200 import dist as mdist
         if args.exchange == "peer":  # statistic exchange fused into the reduction / M-step kernels over NVLink peer memory
@@ -214,12 +216,18 @@ def run_ours(args):
             evs.append((e0, e1))
         barrier()
         launches = ctx.kernel_launches()
+        jit_launches = ctx.jit_launches(reset=True)
         clocks = sampler.stop() if rank == 0 else None
         ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     run_note = None
+    check = None
     try:
         out = pb.read()
         assert np.all(np.isfinite(out["lambda_"])), "E-step produced non-finite parameters"
+        # result checksum: the parameters after the W + K EM iterations of this run.  The Philox counters carry global
+        # observation indices, so every --gpus N must print the same numbers (up to fp64 summation order, ~1e-12)
+        check = {"llhood": float(out["llhood"]), "eps": float(out["eps"]), "sum_lambda": float(np.sum(out["lambda_"])),
+                 "em_iterations": args.warmup + args.steps}
     except mc.MccbnError as e:
         if e.code != 2:
             raise
@@ -264,6 +272,7 @@ def run_ours(args):
             e2e_call(8 + k)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_jit = ctx.jit_launches()
     if dist is not None:
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -282,56 +291,175 @@ def run_ours(args):
                                    ("fused into the reduction/M-step kernels over NVLink peer memory"
                                     if args.exchange == "peer" else "ncclAllReduce")),
                    "kernel": ({"forward": "estep_forward", "pool": "pool_generate + estep_pool"}.get(
-                       sampling, "estep_conditional") + (" (generic)" if args.no_jit or sampling == "pool" else
-                                                         " (NVRTC poset-specialised, compiled during warm-up)"))},
+                       sampling, "estep_conditional") + (" (NVRTC poset-specialised, default JIT policy)"
+                                                         if jit_launches else " (generic)"))},
         "e2e": {"value": N * L_eff / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world,
-                "call": f"mccbn_obs_log_likelihood ({host_kind} host buffers, one E-step)"},
+                "call": f"mccbn_obs_log_likelihood ({host_kind} host buffers, one E-step, default JIT policy: "
+                        f"{'specialised kernel from the context cache' if e2e_jit else 'generic kernel'})"},
         "gpu_launches": int(launches),
+        "gpu_launches_specialised": int(jit_launches),
+        "check": check,
         "clocks": clocks,
     }
     if run_note:
         line["config"]["note"] = run_note
     if rank == 0:
-        # roofline of the dominant kernel (estep_forward / estep_conditional): see module docstring
-        pmax = ((p + 3) // 4) * 4
-        # forward: p + 1 uniforms of 24 bits packed back to back in the Philox stream (kernels_forward.cuh)
-        fwd_blocks = ((24 * p + 23) // 32) // 4 + 1
-        words_per_sample = 4 * fwd_blocks if sampling == "forward" else pmax + 4
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
         peak = None
         try:
             with torch.cuda.stream(stream):
                 peak = philox_peak_words_per_s(torch)
         except Exception:
             peak = None
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        ach = value / world * words_per_sample
-        if sampling != "forward":
-            # nominal samples: the backward scheme skips the incompatible genotypes of the Hamming ball and the pool scheme
-            # counts (observation, pool entry) pairs, so a words-per-sample ceiling does not apply; see profiles/README.md
-            ach, peak = None, None
-        hbm_bytes = (N / world) * (8 + (5 + p) * 8 * 2) + 0.0  # obs word read + partial record write/read per obs
-        line["roofline"] = {
-            "bound": "instruction issue (Philox INT32 + FP32/SFU); not hbm/tensor",
-            "achieved": (ach / 1e9) if ach else None, "peak": (peak / 1e9) if peak else None,
-            "unit": "Gword/s (32-bit Philox output)", "frac": (ach / peak) if (ach and peak) else None, "traffic": ncu_traffic_bytes(args.config),
-            "words_per_sample": words_per_sample,
-            "peak_source": "pure Philox4x32-10 generator micro-kernel (IMAD.WIDE-bound) measured live on this GPU; "
-                           "frac = share of the step the multiplier pipe alone would need (see profiles/README.md "
-                           "for the measured issue-cost model that accounts for the rest)",
-            "hbm": {"achieved_GBs": hbm_bytes / (ms * 1e-3) / 1e9, "peak_GBs": peaks.get("hbm_gbs"),
-                    "note": "algorithmic HBM bytes per E-step / step time: memory is not the limiter"},
-        }
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        line["roofline"] = workload_roofline(args.config, cfg, p, N // world, L, sampling, ms, peak, sm_hz, n_sm, peaks)
+        if world == 1 and not args.no_other:
+            other = {}
+            for name in ("cfg2", "cfg4", "cfg5", "cfg5pool"):
+                if name == args.config:
+                    continue
+                try:
+                    other[name] = time_other_workload(torch, mc, ctx, stream, flush, name, peak, sm_hz, n_sm, peaks)
+                except Exception as e:  # a side measurement must never take the headline down
+                    other[name] = {"error": str(e)[:200]}
+            line["config"]["other_workloads"] = other
+            if sampling == "forward":
+                try:
+                    line["config"]["fp64_mode"] = time_fp64_mode(torch, mc, ctx, stream, cfg, obs, p, N, L)
+                except Exception as e:
+                    line["config"]["fp64_mode"] = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, p, N, L, sampling, args)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def fwd_words_per_sample(p):
+    """p + 1 uniforms of 24 bits packed back to back in the Philox stream (kernels_forward.cuh): 32-bit words drawn"""
+    return 4 * (((24 * p + 23) // 32) // 4 + 1)
+
+
+def executed_backward_samples(cfg, p, L):
+    """backward scheme, k = 1: the kernel draws `reps` samples for every genotype of the Hamming ball that is compatible
+    with the poset and skips the others (their weight is 0 in the reference, src/mcem_hcbn.cpp:524-532)."""
+    obs = np.asarray(cfg["obs"]) != 0
+    poset = np.asarray(cfg["poset"]) != 0
+    reps = L // (p + 1)
+    par = [np.nonzero(poset[:, j])[0] for j in range(p)]
+
+    def n_incompatible(X):  # rows of X that violate some cover relation
+        bad = np.zeros(X.shape[0], bool)
+        for j in range(p):
+            if par[j].size:
+                bad |= X[:, j] & ~X[:, par[j]].all(axis=1)
+        return bad
+
+    total = (~n_incompatible(obs)).sum()
+    for j in range(p):
+        X = obs.copy()
+        X[:, j] = ~X[:, j]
+        total += (~n_incompatible(X)).sum()
+    return int(total) * reps
+
+
+def workload_roofline(name, cfg, p, N_local, L, sampling, ms, philox_peak, sm_hz, n_sm, peaks):
+    """Roofline of the dominant kernel of one workload.  None of these kernels is HBM- or tensor-bound (no contraction;
+    the observation stream is ~1e-3 B per sample): the binding resource is instruction issue.  Ceilings, all per GPU:
+      philox  32-bit random words/s of a pure Philox4x32-10 generator kernel measured live (IMAD.WIDE-bound)
+      mufu    16 MUFU results / clk / SM (XU pipe, tools/pipe_microbench.cu: MUFU.LG2 = 8 cycles per warp per scheduler)
+      fp32    128 FFMA / clk / SM
+    `achieved` counts ALGORITHMIC work per launch / the E-step time."""
+    t = ms * 1e-3
+    mufu_peak = 16.0 * n_sm * sm_hz
+    fp32_peak = 128.0 * n_sm * sm_hz
+    hbm_bytes = N_local * (8 + (5 + p) * 8 * 2)  # observation word read + partial record write/read per observation
+    out = {"bound": "instruction issue (Philox INT32 + FP32/SFU); not hbm/tensor", "traffic": ncu_traffic_bytes(name),
+           "hbm": {"achieved_GBs": hbm_bytes / t / 1e9, "peak_GBs": peaks.get("hbm_gbs"),
+                   "note": "algorithmic HBM bytes per E-step / step time: memory is not the limiter"}}
+    if sampling == "forward":
+        wps = fwd_words_per_sample(p)
+        ach = N_local * L * wps / t
+        out.update({"achieved": ach / 1e9, "peak": philox_peak / 1e9 if philox_peak else None,
+                    "unit": "Gword/s (32-bit Philox output)", "frac": ach / philox_peak if philox_peak else None,
+                    "words_per_sample": wps,
+                    "also": {"mufu_frac": N_local * L * (p + 1) / t / mufu_peak,
+                             "fp32_frac": N_local * L * (2 * p + 3) / t / fp32_peak},
+                    "peak_source": "pure Philox4x32-10 generator micro-kernel (IMAD.WIDE-bound) measured live on this GPU; "
+                                   "frac = share of the step the multiplier pipe alone would need (see profiles/README.md "
+                                   "for the measured issue-cost model that accounts for the rest)"})
+    elif sampling == "pool":
+        PM = 8 if p <= 8 else (16 if p <= 16 else 32)
+        pairs = float(N_local) * p * L  # (observation, pool entry) pairs, K = p L entries
+        ach = pairs * (PM + 3) / t     # weighted sums: PMAX + 3 FFMA per pair
+        out.update({"achieved": ach / 1e12, "peak": fp32_peak / 1e12, "unit": "TFFMA/s (fp32, PMAX + 3 per pair)",
+                    "frac": ach / fp32_peak, "pairs_per_s": pairs / t,
+                    "also": {"philox_frac": (pairs / t / philox_peak) if philox_peak else None,  # one word per pair (T_s)
+                             "mufu_frac": pairs / t / mufu_peak},
+                    "peak_source": "128 FFMA/clk/SM x SMs x SM clock; per pair the kernel also does a 5-step binary search "
+                                   "in shared memory, one popc and one 32-bit uniform + MUFU.LG2 for the sampling time"})
+    else:
+        nblk = ((24 * p + 23) // 32) // 4 + 1
+        executed = executed_backward_samples(cfg, p, L) * (N_local / cfg["obs"].shape[0]) if sampling == "backward" \
+            else float(N_local) * L
+        mufu = executed * (3 * p + 2)  # per node EX2 (F), LG2 (z), LG2 (log F); + T_s + the final EX2 of the weight
+        ach = mufu / t
+        out.update({"achieved": ach / 1e12, "peak": mufu_peak / 1e12, "unit": "TMUFU/s (3p + 2 per executed sample)",
+                    "frac": ach / mufu_peak, "executed_samples": executed,
+                    "also": {"philox_frac": (executed * 4 * nblk / t / philox_peak) if philox_peak else None},
+                    "peak_source": "16 MUFU/clk/SM x SMs x SM clock (XU pipe); executed samples = compatible genotypes of "
+                                   "the Hamming balls x reps (incompatible ones are skipped: their weight is 0)"})
+    return out
+
+
+def time_other_workload(torch, mc, ctx, stream, flush, name, philox_peak, sm_hz, n_sm, peaks, steps=5, warmup=3):
+    """One EM iteration of another BASELINE configuration, inputs resident, CUDA events on the launching stream."""
+    cfg, p, N, L, sampling, desc = make_problem(name)
+    pb = mc.Problem(np.asfortranarray(cfg["obs"]), ctx=ctx)
+    pb.set_model(cfg["poset"], cfg["lambda0"], 0.1)
+    ctx.jit_launches(reset=True)
+    with torch.cuda.stream(stream):
+        for w in range(warmup):
+            pb.em_iterations(L, n_iter=1, sampling=sampling, seed=50 + w, update_params=False)
+        torch.cuda.synchronize()
+        evs = []
+        for k in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            pb.em_iterations(L, n_iter=1, sampling=sampling, seed=60 + k, update_params=False)
+            e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    L_eff = L if sampling != "backward" else (L // (p + 1)) * (p + 1)
+    r = {"workload": f"{name}: {desc}", "ms_per_step": ms, "value": N * L_eff / (ms * 1e-3), "unit": "samples/s",
+         "specialised_kernel": bool(ctx.jit_launches()),
+         "roofline": workload_roofline(name, cfg, p, N, L, sampling, ms, philox_peak, sm_hz, n_sm, peaks)}
+    pb.close()
+    return r
+
+
+def time_fp64_mode(torch, mc, ctx, stream, cfg, obs, p, N, L, steps=2):
+    """The headline workload in the library's fp64 mode (precision = 1: 53-bit uniforms, log, fp64 event times and sums --
+    the reference's arithmetic), through the one-call entry with host buffers."""
+    with torch.cuda.stream(stream):
+        mc.obs_loglikelihood(obs, cfg["poset"], cfg["lambda0"], 0.1, L=L, seed=3, ctx=ctx, precision=1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            mc.obs_loglikelihood(obs, cfg["poset"], cfg["lambda0"], 0.1, L=L, seed=4 + k, ctx=ctx, precision=1)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+    return {"value": N * L / dt, "unit": "samples/s", "ms_per_step": dt * 1e3,
+            "call": "mccbn_obs_log_likelihood, precision = 1 (fp64 sampling), host buffers"}
 
 
 def ncu_traffic_bytes(config):
@@ -373,6 +501,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the side measurements (other configs, fp64 mode)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU statistic exchange: fused peer-memory kernels (default) or ncclAllReduce")
     ap.add_argument("--no-jit", action="store_true", help="time the generic (poset-interpreting) forward kernel")

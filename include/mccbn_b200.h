@@ -54,7 +54,9 @@ int mccbn_device_count(void);
  * process-wide context on device 0 (or $LOCAL_RANK if set). */
 int mccbn_ctx_create(mccbn_ctx** out, int device, char* err, size_t errlen);
 void mccbn_ctx_destroy(mccbn_ctx* ctx);
-/* Run on a caller-owned CUDA stream (cudaStream_t); NULL = the context's own non-blocking stream. */
+/* Run on a caller-owned CUDA stream (cudaStream_t); NULL = the context's own non-blocking stream.  The work of one
+ * context is ordered by one stream at a time: switching waits for the old stream to drain.  Contexts are independent of
+ * each other, also on the same device. */
 int mccbn_ctx_set_stream(mccbn_ctx* ctx, void* cuda_stream);
 /* Multi-GPU, one process per GPU: observations are sharded over `world` ranks; each EM iteration one
  * sum-allreduce of p+3 doubles (NCCL over NVLink) combines the expected sufficient statistics
@@ -87,6 +89,9 @@ int mccbn_set_gpus(int n_gpus, char* err, size_t errlen);
 int mccbn_get_gpus(void);
 
 uint64_t mccbn_kernel_launches(mccbn_ctx* ctx, int reset);
+/* of those, launches of NVRTC poset-specialised kernels (mccbn_fwd_spec / mccbn_cond_spec, csrc/jit.cuh): lets a caller
+ * (tests, bench.py) state which kernel actually ran */
+uint64_t mccbn_jit_launches(mccbn_ctx* ctx, int reset);
 
 /* ---- extended options shared by the EM entry points ------------------------------------------------------ */
 typedef struct mccbn_em_options {
@@ -152,6 +157,19 @@ int mccbn_adaptive_simulated_annealing(mccbn_ctx* ctx, const int* poset, const i
                                        const char* outdir, int sampling_times_available, int thrds, int verbose,
                                        int seed, int N, int p, double* lambda_out, double* eps_out, int* poset_out,
                                        double* llhood_out, char* err, size_t errlen);
+
+/* TEST-ONLY seam, not a reference export: the annealer with every MCEM score replaced by the deterministic structural
+ * score -1000 - num_incompatible_events + 3 |cover relations|, so that tests can compare the host logic of src/asa.cpp
+ * (move generator, memo tables, Metropolis rule, temperature schedule, files) with the oracle without Monte-Carlo noise.
+ * Same arguments as mccbn_adaptive_simulated_annealing; always runs on one device. */
+int mccbn_test_asa_structural_score(mccbn_ctx* ctx, const int* poset, const int* obs, const double* times,
+                                    float lambda_s, const double* weights, unsigned L, const char* sampling,
+                                    unsigned max_iter_EM, unsigned update_step_size, double tol, float max_lambda,
+                                    float T0, float adap_rate, float acceptance_rate, int step_size,
+                                    unsigned max_iter_ASA, unsigned neighborhood_dist, int adaptive,
+                                    const char* outdir, int sampling_times_available, int thrds, int verbose,
+                                    int seed, int N, int p, double* lambda_out, double* eps_out, int* poset_out,
+                                    double* llhood_out, char* err, size_t errlen);
 
 /* replaces `MCEM` (legacy OT-CBN, src/mcem.cpp:307-335, called by estimate_mutation_rates): noise-free model,
  * X == Y, conditional (truncated-exponential) proposal; returns list(lambda, llhood) */
@@ -282,9 +300,13 @@ int mccbn_problem_read(mccbn_problem* pb, double* lambda, double* eps, double* l
 /* the CUDA stream the problem's work is enqueued on (for event timing by the caller) */
 void* mccbn_problem_stream(mccbn_problem* pb);
 
-/* Poset-specialised forward kernels (NVRTC, csrc/jit.cuh).  mode: -1 auto (only when N*L >= 2e8 samples per
- * E-step, default; env MCCBN_JIT=0/1 overrides), 0 never, 1 always.  The specialised and the generic kernel draw the
- * same random stream and produce the same records. */
+/* Poset-specialised kernels (NVRTC, csrc/jit.cuh).  mode: -1 automatic (default; env MCCBN_JIT=0/1 overrides), 0 never,
+ * 1 always (compile on first use).  Automatic: a kernel found in the context's memory cache or in the on-disk cache
+ * ($MCCBN_CACHE_DIR, default ~/.cache/mccbn_b200) is always used; otherwise it is compiled at once when the announced
+ * sampling work (samples per E-step x expected E-steps) is >= 5e9 samples, compiled on a background host thread when one
+ * E-step has >= 5e7 samples (the generic kernel runs until it is ready), and not at all for smaller problems.  The
+ * specialised and the generic kernel draw the same random stream and write identical records, so results do not depend
+ * on the mode. */
 int mccbn_set_jit(mccbn_ctx* ctx, int mode);
 /* host-only: generate and compile (no device needed) the specialised kernel of `poset`; log = NVRTC / ptxas -v
  * output, source = generated CUDA text (either may be NULL) */

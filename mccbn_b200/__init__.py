@@ -9,7 +9,7 @@ from .api import (Context, Problem, MCEM_hcbn, adaptive_simulated_annealing, com
                   conditional_from_uniforms, device_count, estep_forward_from_times, estimate_mutation_rates,
                   flatten_poset,
                   forward_from_times, importance_weight, initialize_lambda, neighbors, nccl_unique_id,
-                  obs_loglikelihood, poset_edit, set_jit, jit_compile_forward, jit_compile_conditional, sample_genotypes, sample_times,
+                  obs_loglikelihood, poset_edit, set_jit, jit_launches, kernel_launches, jit_compile_forward, jit_compile_conditional, sample_genotypes, sample_times,
                   generate_genotypes, scale_path_to_mutation, cbn_density_log, complete_log_likelihood,
                   draw_sample, coin_tossing, generate_mutation_times, draw_hidden_vars_samples,
                   expected_time_difference, loglike_importance_sampling, genotype_probability_fast, set_gpus, get_gpus)

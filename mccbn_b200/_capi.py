@@ -35,7 +35,7 @@ _lib = None
 SYMBOLS = [
     "mccbn_version", "mccbn_device_count", "mccbn_ctx_create", "mccbn_ctx_destroy", "mccbn_ctx_set_stream",
     "mccbn_nccl_unique_id", "mccbn_ctx_init_comm", "mccbn_ctx_peer_handle", "mccbn_ctx_init_peers",
-    "mccbn_kernel_launches", "mccbn_MCEM_hcbn",
+    "mccbn_kernel_launches", "mccbn_jit_launches", "mccbn_test_asa_structural_score", "mccbn_MCEM_hcbn",
     "mccbn_obs_log_likelihood", "mccbn_importance_weight", "mccbn_importance_weight_genotype",
     "mccbn_adaptive_simulated_annealing", "mccbn_MCEM", "mccbn_flatten_poset", "mccbn_compatible_observations",
     "mccbn_neighbors", "mccbn_initialize_lambda", "mccbn_forward_from_times", "mccbn_estep_forward_from_times",
@@ -57,6 +57,8 @@ def lib():
         _lib.mccbn_version.restype = C.c_char_p
         _lib.mccbn_kernel_launches.restype = C.c_uint64
         _lib.mccbn_kernel_launches.argtypes = [C.c_void_p, C.c_int]
+        _lib.mccbn_jit_launches.restype = C.c_uint64
+        _lib.mccbn_jit_launches.argtypes = [C.c_void_p, C.c_int]
         _lib.mccbn_problem_stream.restype = C.c_void_p
         _lib.mccbn_problem_stream.argtypes = [C.c_void_p]
         _lib.mccbn_problem_destroy.argtypes = [C.c_void_p]

@@ -62,6 +62,10 @@ class Context:
     def kernel_launches(self, reset=False):
         return int(capi.lib().mccbn_kernel_launches(self._h, int(reset)))
 
+    def jit_launches(self, reset=False):
+        """launches of NVRTC poset-specialised kernels among kernel_launches()"""
+        return int(capi.lib().mccbn_jit_launches(self._h, int(reset)))
+
     def close(self):
         if self._h:
             capi.lib().mccbn_ctx_destroy(self._h)
@@ -234,7 +238,7 @@ def adaptive_simulated_annealing(poset, obs, times=None, lambda_s=1.0, weights=N
                                  max_iter=100, update_step_size=20, tol=0.001, max_lambda_val=1e6, T0=50.0,
                                  adap_rate=0.3, acceptance_rate=None, step_size=None, max_iter_asa=10000,
                                  neighborhood_dist=1, adaptive=True, outdir=None, thrds=1, verbose=False, seed=None,
-                                 ctx=None):
+                                 ctx=None, _test_structural_score=False):
     """adaptive.simulated.annealing (R/adaptive_simulated_annealing.R:62-113) -> `_adaptive_simulated_annealing`
     (src/asa.cpp:596-665).  Returns dict(lambda_, eps, poset, llhood)."""
     import os
@@ -260,7 +264,9 @@ def adaptive_simulated_annealing(poset, obs, times=None, lambda_s=1.0, weights=N
     out_e, out_ll = C.c_double(0), C.c_double(0)
     out_p = np.zeros((p, p), np.int32, order="F")
     e = ErrBuf()
-    e.check(capi.lib().mccbn_adaptive_simulated_annealing(
+    entry = (capi.lib().mccbn_test_asa_structural_score if _test_structural_score  # test-only seam, see the header
+             else capi.lib().mccbn_adaptive_simulated_annealing)
+    e.check(entry(
         _ctx(ctx), ptr(poset), ptr(obs), ptr(t), C.c_float(lambda_s), ptr(wt), C.c_uint(int(L)), sampling.encode(),
         C.c_uint(int(max_iter)), C.c_uint(int(update_step_size)), C.c_double(tol), C.c_float(max_lambda_val),
         C.c_float(T0), C.c_float(adap_rate), C.c_float(acceptance_rate), int(step_size), C.c_uint(int(max_iter_asa)),
@@ -417,6 +423,15 @@ def neighbors(p, k, genotype):
     ring = np.zeros(n.value, np.int32)
     e.check(capi.lib().mccbn_neighbors(p, k, ptr(g), ptr(out), ptr(ring), C.byref(n), *e.args))
     return out, ring
+
+
+def jit_launches(ctx=None, reset=False):
+    """Launches of NVRTC poset-specialised kernels by `ctx` (None: the default context) since the last reset."""
+    return int(capi.lib().mccbn_jit_launches(_ctx(ctx), int(reset)))
+
+
+def kernel_launches(ctx=None, reset=False):
+    return int(capi.lib().mccbn_kernel_launches(_ctx(ctx), int(reset)))
 
 
 def set_jit(mode, ctx=None):

@@ -196,6 +196,7 @@ struct mccbn_ctx {
   mccbn::NcclApi::comm_t comm = nullptr;
   int rank = 0, world = 1;
   uint64_t launches = 0;
+  uint64_t jit_launches = 0;  // launches of NVRTC poset-specialised kernels (mccbn_jit_launches)
   // peer-memory statistic exchange (device_types.cuh: Mailbox); preferred over NCCL when initialised
   mccbn::Mailbox* mailbox = nullptr;
   mccbn::Mailbox* peer_box[mccbn::kMaxWorld] = {};

@@ -55,18 +55,16 @@ static void initialize_candidate(mccbn_problem& pb, Candidate& c, float lambda_s
 static void score_candidates(mccbn_problem& pb, std::vector<Candidate*>& cands, const std::vector<uint32_t>& eval_ids,
                              Scheme scheme, unsigned L, const EmControl& ctl, bool times_given, uint32_t seed,
                              float lambda_s, int precision) {
-  // test seam (tests/test_gpu_asa.py, mirrored by the oracle's score_mode 1): a deterministic score of the poset
-  // instead of the MCEM fit, so that the move generator and the annealing bookkeeping can be compared without
-  // Monte-Carlo noise.  Not part of the reference.
-  if (const char* e = std::getenv("MCCBN_ASA_TEST_SCORE")) {
-    if (std::atoi(e) == 1) {
-      for (Candidate* c : cands) {
-        int n_inc = 0;
-        count_compatible(pb, c->poset, &n_inc);
-        c->llhood = -1000.0 - (double)n_inc + 3.0 * (double)c->poset.num_edges();
-      }
-      return;
+  // test seam (reachable only through the test-only entry point mccbn_test_asa_structural_score; mirrored by the
+  // oracle's score_mode 1): a deterministic score of the poset instead of the MCEM fit, so that the move generator and
+  // the annealing bookkeeping can be compared without Monte-Carlo noise.  Not part of the reference.
+  if (pb.test_structural_score) {
+    for (Candidate* c : cands) {
+      int n_inc = 0;
+      count_compatible(pb, c->poset, &n_inc);
+      c->llhood = -1000.0 - (double)n_inc + 3.0 * (double)c->poset.num_edges();
     }
+    return;
   }
   // Several GPUs (candidate-parallel annealing, pb.local_only): rank r fits the candidates q with q % world == r; the
   // fitted (llhood, eps, lambda) of all candidates are then shared by one sum-exchange (each entry is non-zero on exactly

@@ -48,7 +48,6 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     throw Error(MCCBN_ERR_ARG, "32 < p <= 64 is supported by the forward, backward and bernoulli schemes (fp32 path)");
   cudaStream_t s = ctx->stream;
   const int iter = iter_host[c];
-  bind_scales(c);
   int chunks = 1, chunk_len = L, grid_x = 1;
   long long n_items = 0;
   int L_eff = L;
@@ -62,6 +61,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.obs_bits = bits.ptr;
     a.times = times.ptr;
     a.model = models.ptr + c;
+    a.scale = scales.ptr + c;
     a.part = part.ensure((size_t)n_items * PS());
     a.N = N;
     a.L = L;
@@ -173,6 +173,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
       CondLauncher::go<float, 32>(a, flat[c], times_given, mode, grid_x, s);
     }
     ctx->launches++;
+    if (jkc) ctx->jit_launches++;
     MCCBN_CUDA(cudaGetLastError());
   } else if (scheme == kPool) {
     // pool of K = p * L prior draws shared by all observations, regenerated every EM iteration (:606, :650-654)
@@ -195,6 +196,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.obs_bits = bits.ptr;
     a.times = times.ptr;
     a.model = models.ptr + c;
+    a.scale = scales.ptr + c;
     a.Tp = Tp;
     a.Mp = Mp;
     a.Zp = Zp;
@@ -214,7 +216,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     const PosetProg pg = build_prog(flat[c], PMX, 4);                                                           \
     pool_generate_kernel<PMX><<<ggen, kFwdBlock, fwd_smem_bytes<float, PMX>(), s>>>(Tp, Mp, Zp, K, kgen.k0,     \
                                                                                     kgen.k1, eval_id[c],       \
-                                                                                    models.ptr + c, pg);        \
+                                                                                    models.ptr + c,            \
+                                                                                    scales.ptr + c, pg);        \
     if (times_given)                                                                                            \
       estep_pool_kernel<PMX, true><<<grid, kPoolBlock, 0, s>>>(a, pg);                                          \
     else                                                                                                        \
@@ -626,6 +629,9 @@ int mccbn_ctx_set_stream(mccbn_ctx* c, void* stream) {
   size_t errlen = 0;
   MCCBN_TRY
   c = get_ctx(c);
+  // work of one context is ordered by ONE stream at a time (its specialised kernels read the context's __constant__
+  // scales, its buffers are reused from call to call): drain the old stream before switching
+  MCCBN_CUDA(cudaStreamSynchronize(c->stream));
   c->stream = stream ? (cudaStream_t)stream : c->own_stream;
   MCCBN_CATCH
 }
@@ -721,6 +727,17 @@ uint64_t mccbn_kernel_launches(mccbn_ctx* c, int reset) {
   return v;
 }
 
+uint64_t mccbn_jit_launches(mccbn_ctx* c, int reset) {
+  try {
+    c = get_ctx(c);
+  } catch (...) {
+    return 0;
+  }
+  uint64_t v = c->jit_launches;
+  if (reset) c->jit_launches = 0;
+  return v;
+}
+
 // ---- device-resident problem ------------------------------------------------------------------------------------
 int mccbn_problem_create(mccbn_ctx* c, const int* obs, const double* times, const double* weights, int N, int p,
                          int64_t obs_offset, int64_t N_global, mccbn_problem** out, char* err, size_t errlen) {
@@ -768,6 +785,8 @@ int mccbn_problem_em_iterations(mccbn_problem* pb, unsigned L, const char* sampl
   MCCBN_TRY
   get_ctx(pb->ctx);
   const Scheme sc = parse_scheme(sampling);
+  // a device-resident problem exists to run many E-steps on the same poset: announce that to the JIT policy
+  pb->expected_esteps = std::max(pb->expected_esteps, std::max(n_iter, 64));
   pb->enqueue_iterations(0, n_iter, sc, (int)L, neighborhood_dist, sampling_times_available != 0, (uint32_t)seed,
                          update_params, 0);
   MCCBN_CATCH
@@ -999,7 +1018,6 @@ int mccbn_importance_weight_genotype(mccbn_ctx* c, const int* genotype, unsigned
   pb.p = p;
   pb.upload(one_obs, &time, nullptr);
   pb.set_model(0, f, lambda, eps, lambda_s, 1e6f);
-  pb.bind_scales(0);
   cudaStream_t s = c->stream;
   DevBuf<double> dZ, dTs;
   DevBuf<int> dD;
@@ -1009,6 +1027,7 @@ int mccbn_importance_weight_genotype(mccbn_ctx* c, const int* genotype, unsigned
   a.obs_word = pack_genotype(genotype, p);
   a.time = time;
   a.model = pb.models.ptr;
+  a.scale = pb.scales.ptr;
   a.Z_out = dZ.ensure((size_t)L * p);
   a.dist_out = dD.ensure(L);
   a.X_out = dX.ensure(L);
@@ -1077,6 +1096,7 @@ static void simulate_forward(mccbn_ctx* c, unsigned N, const int* poset, const d
   FwdDumpArgs a;
   std::memset(&a, 0, sizeof(a));
   a.model = pb.models.ptr;
+  a.scale = pb.scales.ptr;
   a.Z_out = dZ.ensure((size_t)N * p);
   a.T_out = (T_sum || given_times) ? dT.ensure((size_t)N * p) : nullptr;
   a.dist_out = dD.ensure(N);
@@ -1747,17 +1767,21 @@ int mccbn_poset_edit(const int* poset, int p, int op, int u, int v, int* poset_o
 }
 
 // ---- adaptive simulated annealing --------------------------------------------------------------------------------
-int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int* obs, const double* times,
-                                       float lambda_s, const double* weights, unsigned L, const char* sampling,
-                                       unsigned max_iter_EM, unsigned update_step_size, double tol, float max_lambda,
-                                       float T0, float adap_rate, float acceptance_rate, int step_size,
-                                       unsigned max_iter_ASA, unsigned neighborhood_dist, int adaptive,
-                                       const char* outdir, int sampling_times_available, int thrds, int verbose,
-                                       int seed, int N, int p, double* lambda_out, double* eps_out, int* poset_out,
-                                       double* llhood_out, char* err, size_t errlen) {
+}  // extern "C"
+extern "C" int mccbn_adaptive_simulated_annealing(mccbn_ctx*, const int*, const int*, const double*, float, const double*,
+                                                  unsigned, const char*, unsigned, unsigned, double, float, float, float,
+                                                  float, int, unsigned, unsigned, int, const char*, int, int, int, int,
+                                                  int, int, double*, double*, int*, double*, char*, size_t);
+static int asa_entry(mccbn_ctx* c, const int* poset, const int* obs, const double* times, float lambda_s,
+                     const double* weights, unsigned L, const char* sampling, unsigned max_iter_EM,
+                     unsigned update_step_size, double tol, float max_lambda, float T0, float adap_rate,
+                     float acceptance_rate, int step_size, unsigned max_iter_ASA, unsigned neighborhood_dist,
+                     int adaptive, const char* outdir, int sampling_times_available, int thrds, int verbose, int seed,
+                     int N, int p, double* lambda_out, double* eps_out, int* poset_out, double* llhood_out, char* err,
+                     size_t errlen, bool structural_score) {
   (void)thrds;
   MCCBN_TRY
-  if (!c) {
+  if (!c && !structural_score) {
     if (Team* team = team_for(N)) {  // candidate-parallel annealing: every member is given ALL observations
       const int G = (int)team->ctx.size();
       std::vector<std::vector<double>> lam_r(G, std::vector<double>(p));
@@ -1790,6 +1814,7 @@ int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int
   pb.N = N;
   pb.p = p;
   pb.upload(obs, times, weights);
+  pb.test_structural_score = structural_score;
   // several GPUs: candidate-parallel -- every rank is given ALL observations and fits its share of each speculative batch
   pb.local_only = c->world > 1;
   initialize_candidate(pb, M, lambda_s, max_lambda);  // src/asa.cpp:640-642
@@ -1825,6 +1850,37 @@ int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int
   M.poset.to_adjacency(poset_out);
   *llhood_out = ll;
   MCCBN_CATCH
+}
+extern "C" {
+int mccbn_adaptive_simulated_annealing(mccbn_ctx* c, const int* poset, const int* obs, const double* times,
+                                       float lambda_s, const double* weights, unsigned L, const char* sampling,
+                                       unsigned max_iter_EM, unsigned update_step_size, double tol, float max_lambda,
+                                       float T0, float adap_rate, float acceptance_rate, int step_size,
+                                       unsigned max_iter_ASA, unsigned neighborhood_dist, int adaptive,
+                                       const char* outdir, int sampling_times_available, int thrds, int verbose,
+                                       int seed, int N, int p, double* lambda_out, double* eps_out, int* poset_out,
+                                       double* llhood_out, char* err, size_t errlen) {
+  return asa_entry(c, poset, obs, times, lambda_s, weights, L, sampling, max_iter_EM, update_step_size, tol, max_lambda,
+                   T0, adap_rate, acceptance_rate, step_size, max_iter_ASA, neighborhood_dist, adaptive, outdir,
+                   sampling_times_available, thrds, verbose, seed, N, p, lambda_out, eps_out, poset_out, llhood_out, err,
+                   errlen, false);
+}
+
+// TEST-ONLY seam (tests/test_gpu_asa.py): the annealer with every MCEM score replaced by the deterministic structural
+// score  -1000 - num_incompatible_events + 3 |cover relations|  (the oracle's score_mode 1), so that the move generator,
+// memo tables, Metropolis rule and temperature schedule can be compared with the oracle without Monte-Carlo noise.
+int mccbn_test_asa_structural_score(mccbn_ctx* c, const int* poset, const int* obs, const double* times,
+                                    float lambda_s, const double* weights, unsigned L, const char* sampling,
+                                    unsigned max_iter_EM, unsigned update_step_size, double tol, float max_lambda,
+                                    float T0, float adap_rate, float acceptance_rate, int step_size,
+                                    unsigned max_iter_ASA, unsigned neighborhood_dist, int adaptive,
+                                    const char* outdir, int sampling_times_available, int thrds, int verbose,
+                                    int seed, int N, int p, double* lambda_out, double* eps_out, int* poset_out,
+                                    double* llhood_out, char* err, size_t errlen) {
+  return asa_entry(c, poset, obs, times, lambda_s, weights, L, sampling, max_iter_EM, update_step_size, tol, max_lambda,
+                   T0, adap_rate, acceptance_rate, step_size, max_iter_ASA, neighborhood_dist, adaptive, outdir,
+                   sampling_times_available, thrds, verbose, seed, N, p, lambda_out, eps_out, poset_out, llhood_out, err,
+                   errlen, true);
 }
 
 // ---- legacy OT-CBN MCEM (src/mcem.cpp:149-210, :307-335) ---------------------------------------------------------

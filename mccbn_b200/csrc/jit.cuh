@@ -21,6 +21,7 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <future>
 #include <map>
 #include <set>
 #include <sstream>
@@ -45,6 +46,7 @@ struct NvrtcApi {
   int (*GetProgramLog)(program_t, char*) = nullptr;
   int (*DestroyProgram)(program_t*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*Version)(int*, int*) = nullptr;
   bool tried = false;
 
   bool load() {
@@ -70,6 +72,7 @@ struct NvrtcApi {
     DestroyProgram = (decltype(DestroyProgram))sym("nvrtcDestroyProgram");
     GetErrorString = (decltype(GetErrorString))sym("nvrtcGetErrorString");
     if (!ok) lib = nullptr;
+    else Version = (decltype(Version))dlsym(lib, "nvrtcVersion");
     return ok;
   }
 };
@@ -84,32 +87,38 @@ static std::string jit_key(const FlatPoset& f, bool times_given, int minb) {
   return k.str();
 }
 
+// Same arithmetic and random stream as sample_forward (kernels_forward.cuh, fp32 path), poset unrolled:
+//   - 24-bit fields packed back to back: field 0 = sampling time, field k + 1 = node k; stream word 4 b + i is state
+//     word i of Philox block b (variable a<i>_<b>); blocks are generated two at a time in lock-step (independent
+//     multiplies of a round hide the IMAD.WIDE -> LOP3 latency), right before the first node that needs them
+//   - event times relative to the sampling time, in registers: t<k> = e<k> c_k + max(parents) (roots: - T_s), the
+//     genotype bit is the sign bit of t<k>, shifted into x with one funnel shift (node k -> bit p - 1 - k)
+//   - e<k> = log2(u_k) stays in registers (E[k]) for the weighted sums: no shared-memory round trip
 static std::string generate_forward_source(const FlatPoset& f, bool times_given, int minb) {
   const int p = f.p, pmax = jit_pmax(p);
   // p > 32: 64-bit genotype words and the wide program
   const char* prog = p > kFastMaxP ? "PosetProgWide" : "PosetProg";
   const char* word_t = p > kFastMaxP ? "uint64_t" : "uint32_t";
   std::ostringstream s;
-  if (const char* e = std::getenv("MCCBN_JIT_DIAG_ROUNDS"))  // profiling experiments only (see philox.cuh)
+#ifdef MCCBN_DIAG_BUILD  // tools/ profiling builds only (./build.sh -DMCCBN_DIAG_BUILD): never in the shipped library
+  if (const char* e = std::getenv("MCCBN_JIT_DIAG_ROUNDS"))
     s << "#define MCCBN_PHILOX_ROUNDS " << std::max(1, std::min(10, std::atoi(e))) << "\n";
+#endif
   s << "#include \"kernels_forward.cuh\"\n"
        "namespace mccbn {\n"
-       "// generated for one poset: node k = topological position k, t<k> = event time, parents unrolled\n"
+       "// generated for one poset: node k = topological position k, t<k> = event time - sampling time\n"
        "struct SpecSampler {\n"
        "  static constexpr bool kStagesT = false;\n"
+       "  static constexpr bool kStagesE = false;\n"
        "  __device__ __forceinline__ void operator()(const " << prog << "& pg, const uint32_t tcol_s, const uint32_t zrow_s,\n"
        "      const uint32_t l, const uint32_t gi, const uint32_t k0, const uint32_t k1, const uint32_t cw,\n"
-       "      const float ts_given, const ScaleSrc<float, "
-    << pmax
-    << "> scale, " << word_t << "& X, float& Ts_out) const {\n"
-       "    float Ts = ts_given;\n"
+       "      const float ts_given, const ScaleSrc<float, " << pmax << "> scale, " << word_t << "& X, float& Ts_out,\n"
+       "      float (&E)[" << pmax << "]) const {\n"
        "    " << word_t << " x = 0;\n"
        "    const uint32_t one = pg.one_bits;\n";
-  // Same stream layout as sample_forward (kernels_forward.cuh): field 0 = sampling time, field k + 1 = node k, 24-bit
-  // fields packed back to back; stream word 4 b + i is state word i of Philox block b (variable a<i>_<b>).
   const int nblocks = fwd_blocks_for_fields(p + 1);
   auto word = [&](int wi) { return "a" + std::to_string(wi % 4) + "_" + std::to_string(wi / 4); };
-  auto field = [&](int f) {  // the expression field_u01 folds to
+  auto field = [&](int f) {  // the expression fast_lg2(field_u01(W, f, one)) folds to
     const int st = 24 * f, wi = st / 32, o = st % 32;
     std::string m;
     if (o == 0) m = "((" + word(wi) + " & 0x7fffffu) | one)";
@@ -117,23 +126,12 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
     else m = "((__funnelshift_r(" + word(wi) + ", " + word(wi + 1) + ", " + std::to_string(o) + ") & 0x7fffffu) | one)";
     return "fast_lg2(2.0f - __uint_as_float(" + m + "))";
   };
-  // genotype bits: 0 = predicated integer add (ALU pipe), 1 = FSET + FFMA into two fp32 accumulators of 16 bits each
-  int xmode = 0;
-  if (const char* e = std::getenv("MCCBN_JIT_XMODE")) xmode = std::atoi(e);
-  if (p > kFastMaxP) xmode = 0;  // the experiments pack 32 bits
-  if (xmode == 1) s << "    float xlo = 0.0f, xhi = 0.0f;\n";
-  // 2 (experiment): not-X_k = sat(2^100 (T_k - T_s)) by FFMA.SAT, bits collected by Horner FFMAs (FP32 pipe only)
-  if (xmode == 2) s << "    float xlo = 0.0f, xhi = 0.0f;\n";
-
-  // ---- statements -------------------------------------------------------------------------------------------------
-  // Philox4x32-10 block b, written out round by round (same arithmetic as philox4x32_10) so that the rounds of one
-  // block can be interleaved with the node code that consumes the previous block
   auto philox_init = [&](int b) {
     std::ostringstream o;
     o << "    uint32_t a0_" << b << " = l, a1_" << b << " = gi, a2_" << b << " = " << b << "u, a3_" << b << " = cw;\n";
     return o.str();
   };
-  auto philox_round = [&](int b, int r) {
+  auto philox_round = [&](int b, int r) {  // same arithmetic as philox4x32_10, written out round by round
     std::ostringstream o;
     o << "    { const uint64_t p0 = (uint64_t)0xD2511F53u * a0_" << b << ", p1 = (uint64_t)0xCD9E8D57u * a2_" << b << ";"
       << " a0_" << b << " = (uint32_t)(p1 >> 32) ^ a1_" << b << " ^ (k0 + " << (uint32_t)(0x9E3779B9u * (uint32_t)r) << "u);"
@@ -142,7 +140,6 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
     return o.str();
   };
   const int rounds = MCCBN_PHILOX_ROUNDS;
-  // node k: waiting time, event time, genotype bit, staged e_k (one 16-byte store per four nodes)
   auto node_stmt = [&](int k) {
     std::ostringstream o;
     o << "    const float e" << k << " = " << field(k + 1) << ";";
@@ -155,82 +152,32 @@ static std::string generate_forward_source(const FlatPoset& f, bool times_given,
       if (terms.size() & 1) nxt.push_back(terms.back());
       terms.swap(nxt);
     }
-    o << "  const float t" << k << " = fmaf(e" << k << ", c_scale.c[" << k << "], " << (terms.empty() ? "0.0f" : terms[0])
-      << ");  ";
-    if (xmode == 2)
-      o << (k < 16 ? "xlo" : "xhi") << " = fmaf(" << (k < 16 ? "xlo" : "xhi") << ", 2.0f, __saturatef(fmaf(t" << k
-        << ", 1.2676506e30f, nbts)));\n";
-    else if (xmode == 1)
-      o << (k < 16 ? "xlo" : "xhi") << " = fmaf(t" << k << " <= Ts ? 1.0f : 0.0f, " << (1u << (k & 15)) << ".0f, "
-        << (k < 16 ? "xlo" : "xhi") << ");\n";
-    else
-      o << "if (t" << k << " <= Ts) x |= 0x" << std::hex << (1ull << k) << std::dec << "ull;\n";
-    if (k % 4 == 3 || k == p - 1) {
-      const int q = k / 4;
-      o << "    sts128_f(zrow_s + " << q * 16 << "u";
-      for (int j = 4 * q; j < 4 * q + 4; ++j) o << ", " << (j <= k ? "e" + std::to_string(j) : std::string("0.0f"));
-      o << ");\n";
-    }
+    o << "  const float t" << k << " = fmaf(e" << k << ", c_scale.c[" << k << "], " << (terms.empty() ? "nts" : terms[0])
+      << ");  E[" << k << "] = e" << k << ";  ";
+    if (p > kFastMaxP) o << "x = (x << 1) | (uint64_t)(__float_as_uint(t" << k << ") >> 31);\n";
+    else o << "x = __funnelshift_l(__float_as_uint(t" << k << "), x, 1);\n";
     return o.str();
   };
-  std::string ts_stmt = times_given ? std::string() : "    Ts = " + field(0) + " * c_scale.cs;\n";
-  if (xmode == 2) ts_stmt += "    const float nbts = -1.2676506e30f * Ts;\n";
-
-  // ---- schedule ---------------------------------------------------------------------------------------------------
-  // 0: G blocks in lock-step, then the nodes they complete (phases alternate between the multiplier pipe and the rest)
-  // 1: software pipeline -- the rounds of block b + 1 are interleaved with the nodes completed by block b, so that every
-  //    warp always offers the schedulers IMAD.WIDE work and ALU / FP32 / SFU work at the same time
-  int sched = 0;  // measured on B200: 0 = 22.8 ms, 1 (with ptxas -O1, which keeps the order) = 24.7 ms per cfg-3 E-step
-  if (const char* e = std::getenv("MCCBN_JIT_SCHED")) sched = std::atoi(e);
-  int G = 2;
+  // nts = -T_s: the scale c_scale.cs = -ln2/lambda_s is negative, T_s = log2(u) cs >= 0
+  const std::string ts_stmt = times_given ? std::string("    const float nts = -ts_given;\n")
+                                          : "    const float nts = -(" + field(0) + " * c_scale.cs);\n";
+  int G = 2;  // Philox blocks advanced in lock-step
   if (const char* e = std::getenv("MCCBN_JIT_PHILOX_ILP")) G = std::max(1, std::min(8, std::atoi(e)));
-  if (sched == 0) {
-    int generated = 0;  // blocks generated so far
-    for (int k = 0; k < p; ++k) {
-      while (generated <= fwd_field_block(k + 1)) {
-        const int b0 = generated, g = std::min(G, nblocks - b0);
-        for (int b = b0; b < b0 + g; ++b) s << philox_init(b);
-        for (int r = 0; r < rounds; ++r)
-          for (int b = b0; b < b0 + g; ++b) s << philox_round(b, r);
-        if (b0 == 0) s << ts_stmt;
-        generated += g;
-      }
-      s << node_stmt(k);
+  int generated = 0;  // blocks generated so far
+  for (int k = 0; k < p; ++k) {
+    while (generated <= fwd_field_block(k + 1)) {
+      const int b0 = generated, g = std::min(G, nblocks - b0);
+      for (int b = b0; b < b0 + g; ++b) s << philox_init(b);
+      for (int r = 0; r < rounds; ++r)
+        for (int b = b0; b < b0 + g; ++b) s << philox_round(b, r);
+      if (b0 == 0) s << ts_stmt;
+      generated += g;
     }
-  } else {
-    s << philox_init(0);
-    for (int r = 0; r < rounds; ++r) s << philox_round(0, r);
-    for (int b = 0; b < nblocks; ++b) {
-      // statements that become ready with block b
-      std::vector<std::string> ready;
-      if (b == 0 && !ts_stmt.empty()) ready.push_back(ts_stmt);
-      for (int k = 0; k < p; ++k)
-        if (fwd_field_block(k + 1) == b) ready.push_back(node_stmt(k));
-      // sched 2: an opaque never-taken branch closes the basic block, ptxas schedules each phase on its own
-      if (sched == 2 && b > 0) s << "    if (l == 0xfffffff7u) asm volatile(\"trap;\");\n";
-      if (b + 1 < nblocks) {
-        s << philox_init(b + 1);
-        size_t done = 0;
-        for (int r = 0; r < rounds; ++r) {
-          s << philox_round(b + 1, r);
-          const size_t upto = ready.size() * (size_t)(r + 1) / (size_t)rounds;
-          for (; done < upto; ++done) s << ready[done];
-        }
-        for (; done < ready.size(); ++done) s << ready[done];
-      } else {
-        for (const std::string& st : ready) s << st;
-      }
-    }
+    s << node_stmt(k);
   }
-  if (xmode == 1) s << "    x = __float2uint_rz(xlo) | (__float2uint_rz(xhi) << 16);\n";
-  if (xmode == 2) {  // Horner collected not-X, most significant bit first: reverse and complement
-    const int nlo = std::min(p, 16), nhi = p - nlo;
-    s << "    x = ~((__brev(__float2uint_rz(xlo)) >> " << (32 - nlo) << ")";
-    if (nhi > 0) s << " | ((__brev(__float2uint_rz(xhi)) >> " << (32 - nhi) << ") << 16)";
-    s << ") & 0x" << std::hex << (p >= 32 ? 0xffffffffu : ((1u << p) - 1u)) << std::dec << "u;\n";
-  }
+  for (int k = p; k < pmax; ++k) s << "    E[" << k << "] = 0.0f;\n";
   s << "    X = x;\n"
-       "    Ts_out = Ts;\n"
+       "    Ts_out = -nts;\n"
        "  }\n"
        "};\n"
        "}  // namespace mccbn\n"
@@ -379,19 +326,29 @@ struct JitKernel {
   int blocks_per_sm = 0;  // resident 128-thread blocks per SM (occupancy query at load time)
   bool ok = false;
   double compile_ms = 0;
+  uint64_t last_use = 0;  // LRU stamp (JitCache::tick)
 };
 
-static uint64_t fnv1a64(const std::string& s) {
-  uint64_t h = 1469598103934665603ull;
-  for (unsigned char c : s) {
-    h ^= c;
+static uint64_t fnv1a64(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+  const unsigned char* c = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) {
+    h ^= c[i];
     h *= 1099511628211ull;
   }
   return h;
 }
+static uint64_t fnv1a64(const std::string& s) { return fnv1a64(s.data(), s.size()); }
 
-// optional on-disk cubin cache ($MCCBN_CACHE_DIR, default ~/.cache/mccbn_b200): makes the compilation a one-time cost
-static std::string jit_cache_path(const std::string& src) {
+// On-disk cubin cache ($MCCBN_CACHE_DIR, default ~/.cache/mccbn_b200, "off" disables it): makes the compilation a
+// one-time cost per poset.  File name = hash of (generated source, embedded device headers, target architecture, NVRTC
+// version, ptxas options); file = 24-byte header {magic, payload size, FNV-1a of the payload} + cubin.  A file whose
+// header or checksum does not match is ignored (and recompiled), the directory is created with mode 0700.
+struct JitDiskHeader {
+  uint64_t magic, size, hash;
+};
+static constexpr uint64_t kJitDiskMagic = 0x324e4942554343ull;  // "CCUBIN2"
+
+static std::string jit_cache_path(NvrtcApi& rtc, const std::string& src) {
   std::string dir;
   if (const char* e = std::getenv("MCCBN_CACHE_DIR")) dir = e;
   else if (const char* h = std::getenv("HOME")) dir = std::string(h) + "/.cache/mccbn_b200";
@@ -399,17 +356,47 @@ static std::string jit_cache_path(const std::string& src) {
   static std::string made;  // create the directory once per process, not once per lookup
   static std::mutex made_mu;  // several device threads of one process (in-process team) look kernels up concurrently
   std::lock_guard<std::mutex> made_lk(made_mu);
-  if (made != dir) {  // mkdir -p
+  if (made != dir) {  // mkdir -p, private to the user
     for (size_t i = 1; i <= dir.size(); ++i)
-      if (i == dir.size() || dir[i] == '/') ::mkdir(dir.substr(0, i).c_str(), 0755);
+      if (i == dir.size() || dir[i] == '/') ::mkdir(dir.substr(0, i).c_str(), 0700);
     made = dir;
   }
+  int vmaj = 0, vmin = 0;
+  if (rtc.load() && rtc.Version) rtc.Version(&vmaj, &vmin);
+  std::ostringstream k;
+  k << src << kSrc_kernels_forward_cuh << kSrc_kernels_cond_cuh << kSrc_philox_cuh << kSrc_device_types_cuh
+    << "|sm_100a|nvrtc" << vmaj << "." << vmin << "|O" << (std::getenv("MCCBN_JIT_PTXAS_O") ? std::getenv("MCCBN_JIT_PTXAS_O") : "3");
   char name[64];
-  std::snprintf(name, sizeof name, "/spec_%016llx.cubin",
-                (unsigned long long)fnv1a64(src + kSrc_kernels_forward_cuh + kSrc_kernels_cond_cuh + kSrc_philox_cuh +
-                                            kSrc_device_types_cuh +
-                                            (std::getenv("MCCBN_JIT_PTXAS_O") ? std::getenv("MCCBN_JIT_PTXAS_O") : "")));
+  std::snprintf(name, sizeof name, "/spec_%016llx.cubin", (unsigned long long)fnv1a64(k.str()));
   return dir + name;
+}
+
+static bool jit_disk_read(const std::string& path, std::vector<char>& cubin) {
+  FILE* fp = path.empty() ? nullptr : std::fopen(path.c_str(), "rb");
+  if (!fp) return false;
+  JitDiskHeader h;
+  bool ok = std::fread(&h, sizeof h, 1, fp) == 1 && h.magic == kJitDiskMagic && h.size > 0 && h.size < (1ull << 28);
+  if (ok) {
+    cubin.resize((size_t)h.size);
+    ok = std::fread(cubin.data(), 1, cubin.size(), fp) == cubin.size() && fnv1a64(cubin.data(), cubin.size()) == h.hash;
+  }
+  std::fclose(fp);
+  if (!ok) cubin.clear();
+  return ok;
+}
+
+static void jit_disk_write(const std::string& path, const std::vector<char>& cubin) {
+  if (path.empty() || cubin.empty()) return;
+  // write-then-rename: safe with several ranks / threads compiling the same kernel
+  const std::string tmp = path + "." + std::to_string((long)getpid()) + "." +
+                          std::to_string(std::hash<std::thread::id>()(std::this_thread::get_id()));
+  if (FILE* fp = std::fopen(tmp.c_str(), "wb")) {
+    const JitDiskHeader h{kJitDiskMagic, (uint64_t)cubin.size(), fnv1a64(cubin.data(), cubin.size())};
+    const bool okw = std::fwrite(&h, sizeof h, 1, fp) == 1 && std::fwrite(cubin.data(), 1, cubin.size(), fp) == cubin.size();
+    std::fclose(fp);
+    if (okw) std::rename(tmp.c_str(), path.c_str());
+    else std::remove(tmp.c_str());
+  }
 }
 
 // resident blocks per SM the specialised kernel is compiled for (register cap = 65536 / (128 * minb))
@@ -418,78 +405,100 @@ static int jit_default_minb() {
   return 3;  // best of {3,4,5,6} on B200 (profiles/README.md): fewer, fatter warps win on this pipe-bound kernel
 }
 
+// Specialised kernels of ONE context.  Lookup order: memory, disk, then -- depending on the caller's policy -- a
+// synchronous compilation, a compilation on a background host thread (the generic kernel runs until it is ready; both
+// kernels produce identical records, so the switch-over does not change results), or nothing.
 struct JitCache {
+  enum Policy { kCachedOnly = 0, kBackground = 1, kCompileNow = 2 };
   NvrtcApi rtc;
   std::map<std::string, JitKernel> kernels;
-  std::set<std::string> disk_misses;  // posets looked up with only_if_cached and not found on disk
+  std::set<std::string> disk_misses;  // keys looked up without compiling and not found on disk
+  struct Pending {
+    std::future<JitCompiled> fut;
+    std::string path;
+  };
+  std::map<std::string, Pending> pending;  // compilations running on background threads
   int minb = jit_default_minb();
+  uint64_t tick = 0;
+  uint64_t tick_loaded = 0;  // modules loaded so far (captured CUDA graphs are re-captured when it changes)
+  size_t max_loaded = 256;  // LRU bound on loaded modules (an annealing run visits thousands of posets)
 
-  // `only_if_cached`: do not compile, return the kernel only if it is already in memory or on disk
-  JitKernel* get(const FlatPoset& f, bool times_given, bool only_if_cached = false) {
+  JitCache() {
+    if (const char* e = std::getenv("MCCBN_JIT_MAX_LOADED")) max_loaded = (size_t)std::max(2, std::atoi(e));
+  }
+  ~JitCache() {
+    for (auto& kv : pending)
+      if (kv.second.fut.valid()) kv.second.fut.wait();
+    for (auto& kv : kernels)
+      if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+  }
+
+  JitKernel* get(const FlatPoset& f, bool times_given, Policy pol = kCompileNow) {
     const int mb = f.p > kFastMaxP ? std::min(minb, 2) : minb;  // 64 event times + 64 sums per thread: 2 resident blocks
     return get_kernel(jit_key(f, times_given, mb), [&] { return generate_forward_source(f, times_given, mb); },
-                      "mccbn_fwd_spec", /*forward=*/true, f.p, only_if_cached);
+                      "mccbn_fwd_spec", /*forward=*/true, f.p, pol);
   }
   // conditional-proposal kernels (mode = CondMode); they keep their scales in shared memory, no __constant__ symbol
-  JitKernel* get_cond(const FlatPoset& f, bool times_given, int mode, bool only_if_cached = false) {
+  JitKernel* get_cond(const FlatPoset& f, bool times_given, int mode, Policy pol = kCompileNow) {
     const int mb = cond_minb();
     return get_kernel("c" + std::to_string(mode) + jit_key(f, times_given, mb),
                       [&] { return generate_cond_source(f, times_given, mode, mb); }, "mccbn_cond_spec",
-                      /*forward=*/false, f.p, only_if_cached);
+                      /*forward=*/false, f.p, pol);
   }
   static int cond_minb() {
     if (const char* e = std::getenv("MCCBN_JIT_COND_MINB")) return std::max(1, std::min(8, std::atoi(e)));
     return 2;  // cfg 5 backward: 2 / 3 / 4 resident blocks = 3.18 / 3.67 / 15.1 ms (4 blocks: 128 registers, spills in the loop)
   }
 
+  // start compiling on a background thread without waiting (the annealer announces the posets it is about to score)
+  void prefetch(const FlatPoset& f, bool times_given) { get(f, times_given, kBackground); }
+
   template <typename SrcFn>
-  JitKernel* get_kernel(const std::string& key, SrcFn make_src, const char* kname, bool forward, int p,
-                        bool only_if_cached) {
+  JitKernel* get_kernel(const std::string& key, SrcFn make_src, const char* kname, bool forward, int p, Policy pol) {
     auto it = kernels.find(key);
-    if (it != kernels.end()) return it->second.ok ? &it->second : nullptr;
-    if (only_if_cached) {
-      // this lookup sits on the per-iteration path of small problems: remember that the disk cache has no kernel for
-      // this poset instead of regenerating and hashing the source every time
-      if (disk_misses.count(key)) return nullptr;
-      const std::string p0 = jit_cache_path(make_src());
-      FILE* fp = p0.empty() ? nullptr : std::fopen(p0.c_str(), "rb");
-      if (!fp) {
+    if (it != kernels.end()) {
+      it->second.last_use = ++tick;
+      return it->second.ok ? &it->second : nullptr;
+    }
+    JitCompiled cc;
+    bool have = false;
+    auto pit = pending.find(key);
+    if (pit != pending.end()) {  // a background compilation of this kernel is under way
+      if (pol != kCompileNow && pit->second.fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready)
+        return nullptr;
+      cc = pit->second.fut.get();  // kCompileNow: wait for it instead of compiling twice
+      pending.erase(pit);
+      have = !cc.cubin.empty();
+    } else {
+      if (pol != kCompileNow && disk_misses.count(key)) return nullptr;  // per-iteration path of small problems
+      const std::string src = make_src();
+      const std::string path = jit_cache_path(rtc, src);
+      have = jit_disk_read(path, cc.cubin);
+      if (!have && pol == kCachedOnly) {
         if (disk_misses.size() > 4096) disk_misses.clear();
         disk_misses.insert(key);
         return nullptr;
       }
-      std::fclose(fp);
+      if (!have && pol == kBackground) {
+        if (!rtc.load() || pending.size() >= 64) return nullptr;
+        NvrtcApi* api = &rtc;  // the cache outlives its futures (~JitCache waits for them)
+        Pending pd;
+        pd.path = path;
+        pd.fut = std::async(std::launch::async, [api, src, path] {
+          JitCompiled out;
+          if (jit_compile(*api, src, out)) jit_disk_write(path, out.cubin);
+          else out.cubin.clear();
+          return out;
+        });
+        pending.emplace(key, std::move(pd));
+        return nullptr;
+      }
+      if (!have) {
+        have = jit_compile(rtc, src, cc);
+        if (have) jit_disk_write(path, cc.cubin);
+      }
     }
     JitKernel jk;
-    JitCompiled cc;
-    const std::string src = make_src();
-    const std::string path = jit_cache_path(src);
-    bool have = false;
-    if (!path.empty()) {
-      if (FILE* fp = std::fopen(path.c_str(), "rb")) {
-        std::fseek(fp, 0, SEEK_END);
-        const long n = std::ftell(fp);
-        std::fseek(fp, 0, SEEK_SET);
-        if (n > 0) {
-          cc.cubin.resize((size_t)n);
-          have = std::fread(cc.cubin.data(), 1, (size_t)n, fp) == (size_t)n;
-        }
-        std::fclose(fp);
-      }
-    }
-    if (!have && jit_compile(rtc, src, cc)) {
-      have = true;
-      if (!path.empty()) {  // write-then-rename: safe with several ranks compiling the same kernel
-        const std::string tmp = path + "." + std::to_string((long)getpid()) + "." +
-                                std::to_string(std::hash<std::thread::id>()(std::this_thread::get_id()));
-        if (FILE* fp = std::fopen(tmp.c_str(), "wb")) {
-          const bool okw = std::fwrite(cc.cubin.data(), 1, cc.cubin.size(), fp) == cc.cubin.size();
-          std::fclose(fp);
-          if (okw) std::rename(tmp.c_str(), path.c_str());
-          else std::remove(tmp.c_str());
-        }
-      }
-    }
     if (have) {
       cudaError_t e = cudaLibraryLoadData(&jk.lib, cc.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
       if (e == cudaSuccess) e = cudaLibraryGetKernel(&jk.kern, jk.lib, kname);
@@ -498,8 +507,7 @@ struct JitCache {
       if (e == cudaSuccess && bytes == sizeof(FwdScale)) {
         jk.ok = true;
         jk.pmax = jit_pmax(p);
-        // forward: ZStage<float, pmax>::kRowBytes per thread of dynamic shared memory; conditional: static only
-        jk.smem = forward ? (size_t)(((jk.pmax / 4) | 1) * 16) * kFwdBlock : 0;
+        jk.smem = 0;  // neither kernel stages anything in dynamic shared memory (event times and log-uniforms in registers)
         jk.compile_ms = cc.compile_ms;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)jk.kern, kFwdBlock, jk.smem) != cudaSuccess ||
@@ -507,21 +515,46 @@ struct JitCache {
           cudaGetLastError();
           nb = forward ? minb : cond_minb();  // the launch bound the kernel was compiled for
         }
-        if (const char* e = std::getenv("MCCBN_JIT_RESIDENT")) nb = std::max(1, std::min(nb, std::atoi(e)));
+        if (const char* e2 = std::getenv("MCCBN_JIT_RESIDENT")) nb = std::max(1, std::min(nb, std::atoi(e2)));
         jk.blocks_per_sm = nb;
       } else {
         std::fprintf(stderr, "mccbn_b200: loading the specialised kernel failed (%s); using the generic kernel\n",
                      cudaGetErrorString(e));
         cudaGetLastError();
+        if (jk.lib) cudaLibraryUnload(jk.lib);
+        jk.lib = nullptr;
       }
     } else {
       std::fprintf(stderr, "mccbn_b200: NVRTC specialisation failed, using the generic kernel\n%s\n", cc.log.c_str());
     }
     if (std::getenv("MCCBN_JIT_VERBOSE"))
       std::fprintf(stderr, "mccbn_b200: specialised kernel %s p=%d: %s in %.0f ms\n%s\n", kname, p,
-                   jk.ok ? "compiled" : "FAILED", cc.compile_ms, cc.log.c_str());
+                   jk.ok ? "ready" : "FAILED", cc.compile_ms, cc.log.c_str());
+    evict_lru();
+    ++tick_loaded;
+    jk.last_use = ++tick;
     auto res = kernels.emplace(key, jk);
     return res.first->second.ok ? &res.first->second : nullptr;
+  }
+
+  // unload the least recently used modules beyond the bound.  Callers hold a JitKernel* only for the launch they are
+  // about to enqueue, and a module is unloaded only after the context's stream has drained (cudaLibraryUnload of a
+  // module with kernels in flight is undefined), so eviction synchronises the device first -- it is rare by design.
+  void evict_lru() {
+    if (kernels.size() < max_loaded) return;
+    cudaDeviceSynchronize();
+    {  // captured CUDA graphs may hold kernels of the modules about to be unloaded: invalidate them
+      int dev = 0;
+      cudaGetDevice(&dev);
+      ++device_cache().epoch[dev & 63];
+    }
+    while (kernels.size() >= max_loaded) {
+      auto victim = kernels.begin();
+      for (auto it = kernels.begin(); it != kernels.end(); ++it)
+        if (it->second.last_use < victim->second.last_use) victim = it;
+      if (victim->second.lib) cudaLibraryUnload(victim->second.lib);
+      kernels.erase(victim);
+    }
   }
 };
 

@@ -27,12 +27,17 @@
 
 namespace mccbn {
 
+// lambda-derived scales as immediate constant-bank operands: used ONLY by the NVRTC-specialised kernels (jit.cuh), whose
+// module -- and therefore whose copy of this symbol -- belongs to one context.  The kernels compiled into the library
+// read the scales of their candidate from FwdArgs::scale (device memory -> shared memory): contexts that share a device
+// share the library's module, so a module-wide symbol would be raced by their streams.
 __constant__ FwdScale c_scale;
 
 struct FwdArgs {
   const uint64_t* obs_bits;  // N
   const double* times;       // N (TIMES_GIVEN only)
   const DevModel* model;     // this candidate's parameters (weight tables; fp64 mode: lambda)
+  const FwdScale* scale;     // this candidate's exponential scales (fp32 path)
   double* part;              // n_items x PS
   int N;
   int L;
@@ -109,18 +114,12 @@ struct ZStage {
   static constexpr uint32_t kRowBytes = (uint32_t)(kStride * sizeof(real));
 };
 
-// per-node exponential scale: fp32 -> constant-bank operand, fp64 -> shared memory (validation mode)
+// per-node exponential scale, by topological position; element PMAX = the sampling time's scale.  A shared-memory array
+// filled at kernel start (fp32: from FwdArgs::scale; fp64 validation mode: -1/lambda from the model).
 template <typename real, int PMAX>
-struct ScaleSrc;
-template <int PMAX>
-struct ScaleSrc<float, PMAX> {
-  const float* unused;
-  __device__ __forceinline__ float operator()(int k) const { return k < 0 ? c_scale.cs : c_scale.c[k]; }
-};
-template <int PMAX>
-struct ScaleSrc<double, PMAX> {
-  const double* s;  // [PMAX + 1], last = sampling
-  __device__ __forceinline__ double operator()(int k) const { return s[k < 0 ? PMAX : k]; }
+struct ScaleSrc {
+  const real* s;  // [PMAX + 1]
+  __device__ __forceinline__ real operator()(int k) const { return s[k < 0 ? PMAX : k]; }
 };
 
 // shared-memory load through a 32-bit shared-space address (keeps LDS even where the compiler loses track of the
@@ -180,11 +179,18 @@ __device__ __forceinline__ real parents_max(const Prog& pg, const typename Prog:
   return m;
 }
 
-// One forward draw for sample l of (global) observation gi.  The event time T_k of the node at topological
-// position k is staged in this thread's shared-memory column (element k at tcol_s + k * kFwdBlock * sizeof(real));
-// e_k = log(u_k) (log2 in fp32, ln in fp64) is staged in this thread's row at zrow_s (ZStage layout); X = hidden
-// genotype in topological-position space.  All PMAX slots run unconditionally (no per-node branch): slots k >= p
-// have scale 0 and no parents, so their T is 0 and the caller's valid_mask removes them from X.
+// One forward draw for sample l of (global) observation gi.  e_k = log(u_k) (log2 in fp32, ln in fp64) is staged in this
+// thread's row at zrow_s (ZStage layout).  All PMAX slots run unconditionally (no per-node branch): slots k >= p have
+// scale 0 and no parents; the final shift / valid_mask removes them from X.
+//
+// fp32 path -- event times RELATIVE to the sampling time: T'_k = T_k - T_s = e_k c_k + max(-T_s, max_parents T'), staged
+// in this thread's shared-memory column (element k at tcol_s + k * kFwdBlock * 4; the dummy row PMAX, which absent
+// parents read, holds -T_s of the current sample).  The hidden genotype bit X_k = [T_k <= T_s] is then the SIGN BIT of
+// T'_k, shifted into X with one funnel shift per node (no compare, no predicated add): the node at topological
+// position k ends up at bit p - 1 - k of X (to_topo_bits_rev gives the observed genotype in the same order).
+// T'_k == 0 exactly (an fp32 tie, probability ~1e-8 per node) counts as "not yet mutated"; the specialised sampler of
+// jit.cuh performs the identical arithmetic, so both kernels produce the same X bit for bit.
+// fp64 path (validation mode) -- absolute times and the reference's comparison T_k <= T_s, X_k at bit p - 1 - k too.
 // Random stream of a sample (fp32): field 0 = sampling time, field k + 1 = node k (field_u01); Philox block b is
 // generated right before the first field that touches it, and only if that field belongs to a real node.
 template <typename real, int PMAX, bool TIMES_GIVEN, typename Prog>
@@ -197,7 +203,7 @@ __device__ __forceinline__ void sample_forward(const Prog& pg, const uint32_t tc
   constexpr uint32_t kRow = kFwdBlock * sizeof(real);
   const word_t multi_mask = pg.multi_mask;
   real Ts = ts_given;
-  X = 0;
+  word_t x = 0;
   if constexpr (sizeof(real) == 4) {
     constexpr int NB = fwd_blocks_for_fields(PMAX + 1);
     uint32_t W[4 * NB];
@@ -214,14 +220,18 @@ __device__ __forceinline__ void sample_forward(const Prog& pg, const uint32_t tc
         } else {
           W[4 * b + 0] = W[4 * b + 1] = W[4 * b + 2] = W[4 * b + 3] = 0u;
         }
-        if (k == 0 && !TIMES_GIVEN) Ts = fast_lg2(field_u01(W, 0, one)) * scale(-1);
+        if (k == 0) {
+          if (!TIMES_GIVEN) Ts = fast_lg2(field_u01(W, 0, one)) * scale(-1);
+          sts_at_f(tcol_s + PMAX * kRow, -Ts);  // dummy parent row: max(-T_s, ...) is the reference's T_max = 0
+        }
       }
       const float e = fast_lg2(field_u01(W, k + 1, one));  // log2(u) <= 0;  Z = e * c,  c = -ln2/lambda
-      const float t = fmaf(e, scale(k), parents_max<real>(pg, multi_mask, k, tcol_s));
+      const float t = fmaf(e, scale(k), parents_max<real>(pg, multi_mask, k, tcol_s));  // T_k - T_s
       sts_at_f(tcol_s + k * kRow, t);
       zq[k & 3] = e;
       if ((k & 3) == 3) sts128_f(zrow_s + (uint32_t)(k - 3) * 4u, zq[0], zq[1], zq[2], zq[3]);
-      if (t <= Ts) X |= ((word_t)1 << k);
+      if constexpr (sizeof(word_t) == 4) x = __funnelshift_l(__float_as_uint(t), x, 1);
+      else x = (x << 1) | (word_t)(__float_as_uint(t) >> 31);
     }
   } else {
     constexpr int UPB = RealTraits<double>::kUniPerBlock;
@@ -237,10 +247,10 @@ __device__ __forceinline__ void sample_forward(const Prog& pg, const uint32_t tc
       const double t = fma(e, scale(k), parents_max<real>(pg, multi_mask, k, tcol_s));
       sts_at_d(tcol_s + k * kRow, t);
       sts_at_d(zrow_s + (uint32_t)k * 8u, e);
-      if (t <= Ts) X |= ((word_t)1 << k);
+      x = (x << 1) | (word_t)(t <= Ts ? 1u : 0u);
     }
   }
-  X &= pg.valid_mask;
+  X = (x >> (PMAX - pg.p)) & pg.valid_mask;  // drop the padding slots: node k -> bit p - 1 - k
   Ts_out = Ts;
 }
 
@@ -254,11 +264,25 @@ __device__ __forceinline__ typename Prog::word_t to_topo_bits(const Prog& pg, co
   return yt;
 }
 
+// the same in the bit order of the forward samplers' X: node k (topological position) -> bit p - 1 - k
+template <int PMAX, typename Prog>
+__device__ __forceinline__ typename Prog::word_t to_topo_bits_rev(const Prog& pg, const uint64_t yw) {
+  typename Prog::word_t yt = 0;
+#pragma unroll
+  for (int k = 0; k < PMAX; ++k)
+    if (k < pg.p) yt |= (typename Prog::word_t)((yw >> pg.ev[k]) & 1ull) << (pg.p - 1 - k);
+  return yt;
+}
+
+// fill the block's scale array (ScaleSrc): fp32 from the candidate's FwdScale, fp64 (validation mode) from the model
 template <typename real, int PMAX, typename Prog>
-__device__ __forceinline__ void load_scales_fp64(const Prog& pg, const DevModel* __restrict__ mdl, real* s_scale) {
-  if (sizeof(real) == 8) {
-    for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock)
+__device__ __forceinline__ void load_scales(const Prog& pg, const DevModel* __restrict__ mdl,
+                                            const FwdScale* __restrict__ sc, real* s_scale) {
+  for (int t = threadIdx.x; t <= PMAX; t += kFwdBlock) {
+    if (sizeof(real) == 8)
       s_scale[t] = t < pg.p ? (real)(-1.0 / mdl->lambda[pg.ev[t]]) : (t == PMAX ? (real)(-1.0 / mdl->lambda_s) : (real)0);
+    else
+      s_scale[t] = t < pg.p ? (real)sc->c[t] : (t == PMAX ? (real)sc->cs : (real)0);
   }
 }
 
@@ -280,12 +304,14 @@ __host__ __device__ constexpr size_t fwd_smem_bytes(bool stages_t = true) {
 template <typename real, int PMAX, bool TIMES_GIVEN>
 struct GenericSampler {
   static constexpr bool kStagesT = true;
+  static constexpr bool kStagesE = true;  // e_k goes through the thread's shared-memory row; E is left untouched
   template <typename Prog>
   __device__ __forceinline__ void operator()(const Prog& pg, const uint32_t tcol_s, const uint32_t zrow_s,
                                              const uint32_t l, const uint32_t gi, const uint32_t k0,
                                              const uint32_t k1, const uint32_t cw, const real ts_given,
                                              const ScaleSrc<real, PMAX> scale, typename Prog::word_t& X,
-                                             real& Ts_out) const {
+                                             real& Ts_out, real (&E)[PMAX]) const {
+    (void)E;
     sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zrow_s, l, gi, k0, k1, cw, ts_given, scale, X, Ts_out);
   }
 };
@@ -293,31 +319,31 @@ struct GenericSampler {
 template <typename real, int PMAX, bool TIMES_GIVEN, typename Sampler, typename Prog>
 __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog& pg, const Sampler sampler) {
   typedef typename Prog::word_t word_t;
-  // dynamic shared memory (fwd_smem_bytes): [rows 0..PMAX-1 staged T_k, row PMAX the dummy row (0),] then one row
-  // per thread of staged e_k = log(u_k) (ZStage; frees PMAX registers per thread)
+  // dynamic shared memory (fwd_smem_bytes): [rows 0..PMAX-1 staged T_k, row PMAX the dummy row,] then -- samplers that
+  // stage e_k = log(u_k) -- one row per thread (ZStage; frees PMAX registers per thread)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using ZS = ZStage<real, PMAX>;
   real* s_T = reinterpret_cast<real*>(smem_raw);
   real* s_Z = s_T + (Sampler::kStagesT ? (PMAX + 1) * kFwdBlock : 0);
   __shared__ real s_rtab[kRtabN];
-  __shared__ real s_scale[PMAX + 1];  // fp64 mode only
+  __shared__ real s_scale[PMAX + 1];
 
   const DevModel* __restrict__ mdl = a.model;
   const int p = pg.p;
   const int lane = threadIdx.x & 31;
   constexpr int kWarps = kFwdBlock / 32;
   if (Sampler::kStagesT) s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;
-  for (int k = 0; k < ZS::kStride; ++k) s_Z[threadIdx.x * ZS::kStride + k] = (real)0;  // unused node slots stay 0
+  if (Sampler::kStagesE)
+    for (int k = 0; k < ZS::kStride; ++k) s_Z[threadIdx.x * ZS::kStride + k] = (real)0;  // unused node slots stay 0
   const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
   const uint32_t zrow_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x * ZS::kStride);
 
   for (int t = threadIdx.x; t < kRtabN; t += kFwdBlock)
     s_rtab[t] = sizeof(real) == 4 ? (real)mdl->rtab[t] : (real)mdl->rtab_d[t];
-  load_scales_fp64<real, PMAX>(pg, mdl, s_scale);
+  load_scales<real, PMAX>(pg, mdl, a.scale, s_scale);
   __syncthreads();
 
-  ScaleSrc<real, PMAX> scale;
-  scale = ScaleSrc<real, PMAX>{reinterpret_cast<const real*>(s_scale)};
+  const ScaleSrc<real, PMAX> scale{reinterpret_cast<const real*>(s_scale)};
 
   const long long gw = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * kWarps;
@@ -332,27 +358,30 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog&
     if (item >= a.n_items) break;
     const int i = (int)(item / a.chunks);
     const int ch = (int)(item - (long long)i * a.chunks);
-    const word_t yt = to_topo_bits<PMAX>(pg, a.obs_bits[i]);
+    // observed genotype in the samplers' bit order.  Weights decrease in de = flip ? p - d : d (flip: eps > 1/2), and
+    // p - d = popc(X ^ ~Y): complementing Y once per item makes popc return de directly.
+    const word_t yt = to_topo_bits_rev<PMAX>(pg, a.obs_bits[i]);
+    const word_t ye = flip ? (word_t)(~yt & pg.valid_mask) : yt;
     const real ts_given = TIMES_GIVEN ? (real)a.times[i] : (real)0;
     const uint32_t gi = (uint32_t)(a.obs_offset + i);
 
     real acc[PMAX];
 #pragma unroll
     for (int k = 0; k < PMAX; ++k) acc[k] = (real)0;
-    real aw = (real)0, aw2 = (real)0, awd = (real)0;
+    real aw = (real)0, aw2 = (real)0, awd = (real)0;  // awd = sum w' de
     int dref = 1 << 20;
 
     const int l_begin = ch * a.chunk_len;
     const int l_end = min(a.L, l_begin + a.chunk_len);
     for (int l0 = l_begin; l0 < l_end; l0 += 32) {
       const int l = l0 + lane;
-      const bool valid = l < l_end;
       word_t X;
       real Ts;
-      sampler(pg, tcol_s, zrow_s, (uint32_t)l, gi, a.key0, key1, a.cw, ts_given, scale, X, Ts);
-      const int d = popc_word((word_t)(X ^ yt));
-      const int de = flip ? p - d : d;  // weights decrease in `de`
-      const int dmin = __reduce_min_sync(0xffffffffu, valid ? de : (1 << 19));
+      real E[PMAX];
+      sampler(pg, tcol_s, zrow_s, (uint32_t)l, gi, a.key0, key1, a.cw, ts_given, scale, X, Ts, E);
+      // lanes beyond the chunk get a distance that maps to the zero tail of the weight table
+      const int de = l < l_end ? popc_word((word_t)(X ^ ye)) : (1 << 19);
+      const int dmin = __reduce_min_sync(0xffffffffu, de);
       if (dmin < dref) {  // warp-uniform: a better sample arrived, rescale the running sums
         const real s = s_rtab[min(dref - dmin, kRtabN - 1)];
         aw *= s;
@@ -362,11 +391,14 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog&
         for (int k = 0; k < PMAX; ++k) acc[k] *= s;
         dref = dmin;
       }
-      const real wr = valid ? s_rtab[min(de - dref, kRtabN - 1)] : (real)0;
+      const real wr = s_rtab[min(de - dref, kRtabN - 1)];
       aw += wr;
       aw2 = fma(wr, wr, aw2);
-      awd = fma(wr, (real)d, awd);
-      if constexpr (sizeof(real) == 4) {
+      awd = fma(wr, (real)de, awd);  // lanes beyond the chunk: wr == 0
+      if constexpr (!Sampler::kStagesE) {
+#pragma unroll
+        for (int k = 0; k < PMAX; ++k) acc[k] = fma(wr, E[k], acc[k]);
+      } else if constexpr (sizeof(real) == 4) {
 #pragma unroll
         for (int q = 0; q < PMAX / 4; ++q) {
           const float4 e = lds128_f(zrow_s + (uint32_t)q * 16u);
@@ -393,7 +425,7 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog&
     if (lane == 0) {
       out[0] = v0;
       out[1] = v1;
-      out[2] = v2;
+      out[2] = flip ? (double)p * v0 - v2 : v2;  // sum w' d from sum w' de
       out[3] = (double)(l_end - l_begin);  // every forward sample has a positive weight (unless eps == 0)
       // natural-log scale of the record: true w = exp(scale) * w', scale = log(base) + dref * log(r)
       out[4] = mdl->log_base + (dref > 0 ? (double)dref * mdl->log_r : 0.0);
@@ -437,6 +469,7 @@ struct FwdDumpArgs {
   uint64_t obs_word;
   double time;
   const DevModel* model;
+  const FwdScale* scale;
   double* Z_out;    // L x p column-major by EVENT id
   double* T_out;    // L x p event times (sample_times, src/mcem_hcbn.cpp:184-213), or nullptr
   int* dist_out;    // L
@@ -459,11 +492,10 @@ __global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpAr
   s_T[PMAX * kFwdBlock + threadIdx.x] = (real)0;
   const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
   const uint32_t zrow_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x * ZS::kStride);
-  load_scales_fp64<real, PMAX>(pg, a.model, s_scale);
+  load_scales<real, PMAX>(pg, a.model, a.scale, s_scale);
   __syncthreads();
-  ScaleSrc<real, PMAX> scale;
-  scale = ScaleSrc<real, PMAX>{reinterpret_cast<const real*>(s_scale)};
-  const uint32_t yt = to_topo_bits<PMAX>(pg, a.obs_word);
+  const ScaleSrc<real, PMAX> scale{reinterpret_cast<const real*>(s_scale)};
+  const uint32_t yt = to_topo_bits_rev<PMAX>(pg, a.obs_word);
   for (int l = blockIdx.x * kFwdBlock + threadIdx.x; l < a.L; l += gridDim.x * kFwdBlock) {
     uint32_t X;
     real Ts;
@@ -475,8 +507,11 @@ __global__ void __launch_bounds__(kFwdBlock) forward_dump_kernel(const FwdDumpAr
     for (int k = 0; k < PMAX; ++k)
       if (k < p) {
         a.Z_out[(size_t)pg.ev[k] * a.L + l] = (double)s_Z[threadIdx.x * ZS::kStride + k] * (double)scale(k);
-        if (a.T_out) a.T_out[(size_t)pg.ev[k] * a.L + l] = (double)s_T[k * kFwdBlock + threadIdx.x];
-        xe |= ((X >> k) & 1u) << pg.ev[k];
+        // the fp32 sampler stages T_k - T_s
+        if (a.T_out)
+          a.T_out[(size_t)pg.ev[k] * a.L + l] =
+              (double)s_T[k * kFwdBlock + threadIdx.x] + (sizeof(real) == 4 ? (double)Ts : 0.0);
+        xe |= ((X >> (p - 1 - k)) & 1u) << pg.ev[k];
       }
     a.X_out[l] = xe;
     a.Ts_out[l] = (double)Ts;

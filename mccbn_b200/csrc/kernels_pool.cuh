@@ -40,8 +40,11 @@ __global__ void __launch_bounds__(kFwdBlock) pool_generate_kernel(float* __restr
                                                                   float* __restrict__ Zp, int K, uint32_t key0,
                                                                   uint32_t key1_purpose, uint32_t cw,
                                                                   const DevModel* __restrict__ mdl,
+                                                                  const FwdScale* __restrict__ sc,
                                                                   const __grid_constant__ PosetProg pg) {
   const uint32_t key1 = iter_key(key1_purpose, mdl);
+  __shared__ float s_scale[PMAX + 1];
+  load_scales<float, PMAX>(pg, mdl, sc, s_scale);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_T = reinterpret_cast<float*>(smem_raw);
   using ZS = ZStage<float, PMAX>;
@@ -49,8 +52,8 @@ __global__ void __launch_bounds__(kFwdBlock) pool_generate_kernel(float* __restr
   s_T[PMAX * kFwdBlock + threadIdx.x] = 0.f;
   const uint32_t tcol_s = (uint32_t)__cvta_generic_to_shared(s_T + threadIdx.x);
   const uint32_t zrow_s = (uint32_t)__cvta_generic_to_shared(s_Z + threadIdx.x * ZS::kStride);
-  ScaleSrc<float, PMAX> scale;
-  scale = ScaleSrc<float, PMAX>{nullptr};
+  __syncthreads();
+  const ScaleSrc<float, PMAX> scale{s_scale};
   const int p = pg.p;
   for (int k = blockIdx.x * kFwdBlock + threadIdx.x; k < K; k += gridDim.x * kFwdBlock) {
     uint32_t X;
@@ -85,6 +88,7 @@ struct PoolArgs {
   const uint64_t* obs_bits;
   const double* times;
   const DevModel* model;
+  const FwdScale* scale;
   const float* Tp;     // K x PMAX sorted event times
   const uint32_t* Mp;  // K x (PMAX + 1) prefix genotypes
   const float* Zp;     // K x PMAX
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a
   const uint32_t yt = live ? to_topo_bits<PMAX>(pg, a.obs_bits[i]) : 0u;
   const float ts_given = (TIMES_GIVEN && live) ? (float)a.times[i] : 0.f;
   const uint32_t gi = (uint32_t)(a.obs_offset + i);
-  const float cs = c_scale.cs;
+  const float cs = a.scale->cs;
 
   float acc[PMAX];
 #pragma unroll

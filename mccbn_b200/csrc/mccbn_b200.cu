@@ -177,6 +177,7 @@ struct mccbn_problem {
   // candidate-parallel annealing: every rank holds ALL observations and scores its share of the candidate posets, so the
   // EM iterations of this problem must not exchange statistics with the other ranks
   bool local_only = false;
+  bool test_structural_score = false;  // set by mccbn_test_asa_structural_score only (engine_asa.cuh)
   bool sharded() const { return ctx->world > 1 && !local_only; }
   unsigned long long xchg_seq[kMaxCand] = {};  // exchange number of the candidate's pending reduce_push
   // timeout: sharded EM iterations run in lock-step (30 s covers a first-call NVRTC compile on one rank); the annealer's score exchange waits for the
@@ -260,36 +261,44 @@ struct mccbn_problem {
     }
   }
 
-  // poset-specialised kernel (jit.cuh) when the sampling work amortises a compilation; nullptr = generic kernel
-  JitKernel* resolve_jit(const FlatPoset& f, bool times_given, int L) {
+  // Poset-specialised kernel (jit.cuh) or nullptr = generic kernel.  Policy of the automatic mode (jit_mode < 0 and no
+  // MCCBN_JIT in the environment), by the sampling work the caller announces (samples per E-step x expected E-steps):
+  //   kernel already in this context's memory cache or in the on-disk cache      -> use it
+  //   announced work >= 5e9 samples (a compilation, ~0.3 s, costs < 10 % of it)  -> compile now
+  //   >= 5e7 samples per E-step                                                  -> compile on a background thread, run the
+  //                                                                                 generic kernel until it is ready
+  //   smaller                                                                    -> generic kernel
+  // Both kernels draw the same stream and write identical records (the chunking does not depend on the kernel), so
+  // the result of a run does not depend on when -- or whether -- the specialised kernel becomes available.
+  int jit_mode_effective() const {
     int mode = ctx->jit_mode;
     if (mode < 0) {
       const char* e = std::getenv("MCCBN_JIT");
       if (e && std::strcmp(e, "0") == 0) mode = 0;
       else if (e && std::strcmp(e, "1") == 0) mode = 1;
     }
+    return mode;
+  }
+  JitCache::Policy jit_policy(int mode, double samples_per_estep) const {
+    if (mode > 0) return JitCache::kCompileNow;
+    if (samples_per_estep * (double)std::max(1, expected_esteps) >= 5e9) return JitCache::kCompileNow;
+    return samples_per_estep >= 5e7 ? JitCache::kBackground : JitCache::kCachedOnly;
+  }
+  JitKernel* resolve_jit(const FlatPoset& f, bool times_given, int L) {
+    const int mode = jit_mode_effective();
     if (mode == 0) return nullptr;
     if (!ctx->jit) ctx->jit = new JitCache();
-    // auto: compile only when the announced sampling work (samples per E-step x expected E-steps) amortises the
-    // ~0.3 s compilation (generic 2.2e10, specialised 4.5e10 samples/s on B200); cached kernels are always used
-    const bool worth = (double)N * (double)L * (double)std::max(1, expected_esteps) >= 5e9;
-    return ctx->jit->get(f, times_given, /*only_if_cached=*/mode < 0 && !worth);
+    return ctx->jit->get(f, times_given, jit_policy(mode, (double)N * (double)L));
   }
 
   // the same policy for the conditional-proposal kernels (backward / bernoulli / OT-CBN / add-remove)
   JitKernel* resolve_jit_cond(const FlatPoset& f, bool times_given, int mode, double samples_per_estep,
                               bool required = false) {
-    int jm = ctx->jit_mode;
-    if (jm < 0) {
-      const char* e = std::getenv("MCCBN_JIT");
-      if (e && std::strcmp(e, "0") == 0) jm = 0;
-      else if (e && std::strcmp(e, "1") == 0) jm = 1;
-    }
+    int jm = jit_mode_effective();
     if (required) jm = 1;
     if (jm == 0) return nullptr;
     if (!ctx->jit) ctx->jit = new JitCache();
-    const bool worth = samples_per_estep * (double)std::max(1, expected_esteps) >= 5e9;
-    return ctx->jit->get_cond(f, times_given, mode, /*only_if_cached=*/jm < 0 && !worth);
+    return ctx->jit->get_cond(f, times_given, mode, jit_policy(jm, samples_per_estep));
   }
 
   void launch_forward_jit(JitKernel* jk, const FwdArgs& a, const FlatPoset& f, int c, int grid) {
@@ -306,6 +315,7 @@ struct mccbn_problem {
       MCCBN_CUDA(cudaLaunchKernel((const void*)jk->kern, dim3(grid), dim3(kFwdBlock), params, jk->smem, s));
     }
     ctx->launches++;
+    ctx->jit_launches++;
   }
 
   template <typename real>
@@ -358,15 +368,15 @@ struct mccbn_problem {
     MCCBN_CUDA(cudaGetLastError());
   }
 
-  // chunking of the L samples of one observation over warps (see DESIGN.md "work decomposition")
-  // `blocks_per_sm` = resident blocks of the kernel that will run (0: the generic forward kernel's launch bounds); the
-  // grid is exactly one resident wave, every warp strides over ~24 items
+  // Chunking of the L samples of one observation over warps.  The partition depends only on (N, L, #SMs) -- not on the
+  // kernel that will run -- so that the generic and the specialised kernel write the same records; the GRID is one
+  // resident wave of the kernel that runs (`blocks_per_sm`; 0: the generic forward kernel's launch bounds), its warps
+  // claim the items dynamically.
   void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x, int blocks_per_sm = 0) const {
     const int warps_per_block = kFwdBlock / 32;
     if (blocks_per_sm <= 0) blocks_per_sm = p > kFastMaxP ? kFwdWideMinB : (p > MCCBN_FWD_BIGP - 4 ? MCCBN_FWD_MINB_BIG : 6);
     const int resident_blocks = ctx->sm_count * blocks_per_sm;  // blocks of 4 warps
-    const long long total_warps = (long long)resident_blocks * warps_per_block;
-    long long want_items = total_warps * 24;  // 24 / 48 / 96 / 192 items per warp: 20.9 / 21.0 / 21.2 / 21.6 ms on cfg 3
+    const long long want_items = (long long)ctx->sm_count * 4 * warps_per_block * 24;  // ~24 items per warp at 4 blocks/SM
     long long c = (want_items + N - 1) / std::max(1, N);
     long long cmax = std::max(1, L / 256);
     c = std::max(1LL, std::min(c, cmax));
@@ -385,10 +395,11 @@ struct mccbn_problem {
   // E-step, finalize, reduction, M-step -- is captured into a CUDA graph and replayed: everything that changes from
   // one iteration to the next (parameters, tables, the iteration field of the Philox key, the trace row) lives in
   // device memory.  Small problems are launch-bound: 29 -> 13 us per EM iteration on BASELINE config 1.
+  size_t jit_generation() const { return ctx->jit ? ctx->jit->kernels.size() + (size_t)ctx->jit->tick_loaded : 0; }
   struct IterGraph {
     cudaGraphExec_t exec = nullptr;
     std::string key;
-    uint64_t launches_per_iter = 0;
+    uint64_t launches_per_iter = 0, jit_per_iter = 0;
   };
   IterGraph iter_graph[kMaxCand];
   unsigned model_version[kMaxCand] = {};
@@ -410,12 +421,12 @@ struct mccbn_problem {
       std::ostringstream k;
       k << (int)scheme << ':' << L << ':' << neighborhood_dist << ':' << times_given << ':' << seed << ':' << update_params
         << ':' << precision << ':' << N << ':' << p << ':' << model_version[c] << ':' << eval_id[c] << ':' << trace_rows << ':'
-        << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode;
+        << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode << ':' << jit_generation();
       IterGraph& g = iter_graph[c];
       if (!g.exec || g.key != k.str()) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
         g.exec = nullptr;
-        const uint64_t l0 = ctx->launches;
+        const uint64_t l0 = ctx->launches, j0 = ctx->jit_launches;
         const int it0 = iter_host[c];
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
@@ -432,7 +443,9 @@ struct mccbn_problem {
         if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&g.exec, graph, 0);
         if (graph) cudaGraphDestroy(graph);
         g.launches_per_iter = ctx->launches - l0;
+        g.jit_per_iter = ctx->jit_launches - j0;
         ctx->launches = l0;     // the captured iteration was recorded, not run
+        ctx->jit_launches = j0;
         iter_host[c] = it0;
         if (e != cudaSuccess || !g.exec) {  // capture unavailable: fall back to eager launches
           cudaGetLastError();
@@ -443,7 +456,8 @@ struct mccbn_problem {
           std::ostringstream k2;
           k2 << (int)scheme << ':' << L << ':' << neighborhood_dist << ':' << times_given << ':' << seed << ':'
              << update_params << ':' << precision << ':' << N << ':' << p << ':' << model_version[c] << ':' << eval_id[c]
-             << ':' << trace_rows << ':' << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode;
+             << ':' << trace_rows << ':' << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode
+             << ':' << jit_generation();
           g.key = k2.str();
         }
       }
@@ -451,6 +465,7 @@ struct mccbn_problem {
         for (; done < n; ++done) {
           MCCBN_CUDA(cudaGraphLaunch(g.exec, s));
           ctx->launches += g.launches_per_iter;
+          ctx->jit_launches += g.jit_per_iter;
           iter_host[c]++;
         }
       }
@@ -551,13 +566,6 @@ struct mccbn_problem {
     MCCBN_CUDA(cudaGetLastError());
     iter_host[c]++;
   }
-  // make candidate c's scales the __constant__ operands of the next sampling kernel (stream-ordered)
-  void bind_scales(int c) {
-    if (p <= kWideMaxP)
-      MCCBN_CUDA(cudaMemcpyToSymbolAsync(c_scale, scales.ptr + c, sizeof(FwdScale), 0, cudaMemcpyDeviceToDevice,
-                                         ctx->stream));
-  }
-
   // element-wise sum over ranks of a host vector (every rank gets the rank-ordered sum): peer mailboxes or NCCL
   DevBuf<double> xbuf;
   DevBuf<int> xerr;

@@ -97,14 +97,13 @@ def test_asa_matches_oracle_in_distribution(oracle, tmp_path, mode, n_seeds, kw)
     c = synth.make_config(6, 150, eps=0.05, seed=21, density=0.35)
     start = np.zeros((6, 6), np.int32)
     os.environ["MCCBN_ASA_BATCH"] = "8"
-    if mode == "pseudo":
-        os.environ["MCCBN_ASA_TEST_SCORE"] = "1"
     try:
         g, o = [], []
         for s in range(n_seeds):
             og = os.path.join(str(tmp_path), f"g{s}_")
             oo = os.path.join(str(tmp_path), f"o{s}_")
-            rg = mc.adaptive_simulated_annealing(start, c["obs"], outdir=og, seed=1 + s, T0=5.0, **kw)
+            rg = mc.adaptive_simulated_annealing(start, c["obs"], outdir=og, seed=1 + s, T0=5.0,
+                                                 _test_structural_score=(mode == "pseudo"), **kw)
             ro = oracle.adaptive_simulated_annealing(start, c["obs"], outdir=oo, seed=1001 + s, T0=5.0, thrds=2,
                                                      score_mode=1 if mode == "pseudo" else 0,
                                                      **{("max_iter" if k == "max_iter" else k): v for k, v in kw.items()})
@@ -116,4 +115,4 @@ def test_asa_matches_oracle_in_distribution(oracle, tmp_path, mode, n_seeds, kw)
         z = _two_sample_z(g, o)
         assert np.abs(z).max() < 4.0, (z, np.mean(g, axis=0), np.mean(o, axis=0))
     finally:
-        os.environ.pop("MCCBN_ASA_TEST_SCORE", None)
+        os.environ.pop("MCCBN_ASA_BATCH", None)
