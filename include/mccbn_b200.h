@@ -106,11 +106,16 @@ typedef struct mccbn_em_options {
   int* n_iter;
   /* 0 = fp32 sampling / fp64 reduction (default); 1 = fp64 sampling (validation mode, slower) */
   int precision;
-  /* pool scheme: 0 = Rao-Blackwellised expectations over the pool (default), 1 = draw L indices like the reference */
+  /* pool scheme: 0 = expectations sum_k q_k g_k / sum_k q_k over the whole pool (default: the quantity the reference's
+   * resampling estimates, without its extra Monte-Carlo noise), 1 = draw L indices with replacement from Discrete(q) and
+   * average over the drawn rows like the reference (src/mcem_hcbn.cpp:477-484); obs_llhood is the same in both modes */
   int pool_resample;
   /* stream id mixed into the Philox key so that independent evaluations (ASA candidates) decorrelate */
   uint32_t stream_id;
-  uint32_t reserved[5];
+  /* leading dimension of `obs`: when the N local rows are rows [r, r + N) of a larger column-major matrix with obs_ld
+   * rows, pass obs + r and obs_ld (the device upload is then a strided copy; no host-side gather).  0 => N. */
+  uint32_t obs_ld;
+  uint32_t reserved[4];
 } mccbn_em_options;
 
 /* ---- hot-path entry points (names/arguments follow the reference exports) -------------------------------- */
@@ -272,6 +277,18 @@ int mccbn_estep_forward_from_times(mccbn_ctx* ctx, const int* obs, int N, const 
                                    int sampling_times_available, int L, const double* Z, const double* T_sampling,
                                    float max_lambda, double* w_sum, double* w_sum_sq, double* dist, double* Tdiff,
                                    double* totals, double* eps_new, double* lambda_new, char* err, size_t errlen);
+
+/* pool scheme from a supplied pool (sample_times output T_pool / Tdiff_pool, K x p column-major; T_sampling[K] unless
+ * sampling_times_available): per observation the pool genotypes X_k = [T_pool(k,) <= T_s] and their Hamming distances
+ * (generate_genotypes :215-236, hamming_dist_mat :326-330; X_pool = K x p for observation 0, d_pool = K x N, both
+ * bit-exact), q_sum[i] = sum_k eps^d (1-eps)^(p-d) (so that obs_llhood_i = log(q_sum[i] / K), :491, :690), and the
+ * conditional expectations sum_k q_k g_k / sum_k q_k of d and Z that the reference's L-index resampling estimates
+ * (:477-484).  All outputs optional. */
+int mccbn_pool_from_times(mccbn_ctx* ctx, const int* obs, int N, const int* poset, int p, double eps,
+                          const double* weights, const double* times, int sampling_times_available, int K,
+                          const double* T_pool, const double* Tdiff_pool, const double* T_sampling, int* X_pool,
+                          int* d_pool, double* q_sum, double* dist, double* Tdiff, double* llhood, char* err,
+                          size_t errlen);
 
 /* conditional proposal (generate_mutation_times + cbn_density_log, src/add_remove.cpp:156-216) from supplied
  * uniforms u (L x p, indexed by event id) and sampling times: Tdiff (L x p), log q (L), log P(Z) (L),

@@ -6,7 +6,7 @@ Python mirror of the reference's R entry points (see api.py) over the C ABI of l
 from . import synth  # noqa: F401
 from ._capi import LIB_PATH, MccbnError  # noqa: F401
 from .api import (Context, Problem, MCEM_hcbn, adaptive_simulated_annealing, compatible_observations,  # noqa: F401
-                  conditional_from_uniforms, device_count, estep_forward_from_times, estimate_mutation_rates,
+                  conditional_from_uniforms, pool_from_times, device_count, estep_forward_from_times, estimate_mutation_rates,
                   flatten_poset,
                   forward_from_times, importance_weight, initialize_lambda, neighbors, nccl_unique_id,
                   obs_loglikelihood, poset_edit, set_jit, jit_launches, kernel_launches, jit_compile_forward, jit_compile_conditional, sample_genotypes, sample_times,

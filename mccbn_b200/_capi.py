@@ -26,7 +26,7 @@ class MccbnError(RuntimeError):
 class EmOptions(C.Structure):
     _fields_ = [("obs_offset", C.c_int64), ("N_global", C.c_int64), ("trace", C.c_void_p), ("n_iter", C.c_void_p),
                 ("precision", C.c_int), ("pool_resample", C.c_int), ("stream_id", C.c_uint32),
-                ("reserved", C.c_uint32 * 5)]
+                ("obs_ld", C.c_uint32), ("reserved", C.c_uint32 * 4)]
 
 
 _lib = None
@@ -39,7 +39,7 @@ SYMBOLS = [
     "mccbn_obs_log_likelihood", "mccbn_importance_weight", "mccbn_importance_weight_genotype",
     "mccbn_adaptive_simulated_annealing", "mccbn_MCEM", "mccbn_flatten_poset", "mccbn_compatible_observations",
     "mccbn_neighbors", "mccbn_initialize_lambda", "mccbn_forward_from_times", "mccbn_estep_forward_from_times",
-    "mccbn_conditional_from_uniforms", "mccbn_problem_create", "mccbn_problem_destroy", "mccbn_problem_set_model",
+    "mccbn_conditional_from_uniforms", "mccbn_pool_from_times", "mccbn_problem_create", "mccbn_problem_destroy", "mccbn_problem_set_model",
     "mccbn_problem_em_iterations", "mccbn_problem_read", "mccbn_problem_stream", "mccbn_microbench_philox",
     "mccbn_poset_edit", "mccbn_set_jit", "mccbn_jit_compile_forward", "mccbn_jit_compile_conditional", "mccbn_sample_genotypes", "mccbn_sample_times",
     "mccbn_generate_genotypes", "mccbn_scale_path_to_mutation", "mccbn_cbn_density_log",

@@ -119,7 +119,7 @@ def _options(obs_offset=0, N_global=0, trace=None, n_iter=None, precision=0, poo
 def MCEM_hcbn(lambda_, poset, obs, lambda_s=1.0, L=None, eps=None, sampling="forward", times=None, weights=None,
               max_iter=100, update_step_size=20, tol=0.001, max_lambda=1e6, neighborhood_dist=1, thrds=1,
               verbose=False, seed=None, ctx=None, obs_offset=0, N_global=0, precision=0, stream_id=0,
-              return_trace=False):
+              return_trace=False, pool_resample=False):
     """MCEM.hcbn (R/mcem_hcbn.R:51-90) -> `_MCEM_hcbn` (src/mcem_hcbn.cpp:804-864).
 
     Returns dict(lambda_=..., eps=..., llhood=...) like the R list(lambda, eps, llhood)."""
@@ -146,7 +146,7 @@ def MCEM_hcbn(lambda_, poset, obs, lambda_s=1.0, L=None, eps=None, sampling="for
     out_e, out_ll = C.c_double(0), C.c_double(0)
     trace = np.zeros((max(max_iter, 1), p + 2)) if return_trace else None
     nit = C.c_int(0)
-    opt = _options(obs_offset, N_global, trace, nit, precision, 0, stream_id)
+    opt = _options(obs_offset, N_global, trace, nit, precision, int(pool_resample), stream_id)
     e = ErrBuf()
     e.check(capi.lib().mccbn_MCEM_hcbn(
         _ctx(ctx), ptr(lam), ptr(poset), ptr(obs), ptr(t), C.c_float(lambda_s), C.c_double(eps), ptr(wt),
@@ -161,7 +161,7 @@ def MCEM_hcbn(lambda_, poset, obs, lambda_s=1.0, L=None, eps=None, sampling="for
 
 def obs_loglikelihood(obs, poset, lambda_, eps, weights=None, times=None, L=None, sampling="forward",
                       neighborhood_dist=1, lambda_s=1.0, thrds=1, seed=None, ctx=None, obs_offset=0, precision=0,
-                      stream_id=0):
+                      stream_id=0, pool_resample=False):
     """obs.loglikelihood (R/loglikelihood.R:25-57) -> `_obs_log_likelihood` (src/mcem_hcbn.cpp:762-797)."""
     sampling = _match_sampling(sampling)
     obs, poset, lam = i32(obs), i32(poset), f64(lambda_)
@@ -179,7 +179,7 @@ def obs_loglikelihood(obs, poset, lambda_, eps, weights=None, times=None, L=None
     if seed is None:
         seed = int(np.random.randint(1, 30001))
     out = C.c_double(0)
-    opt = _options(obs_offset=obs_offset, precision=precision, stream_id=stream_id)
+    opt = _options(obs_offset=obs_offset, precision=precision, stream_id=stream_id, pool_resample=int(pool_resample))
     e = ErrBuf()
     e.check(capi.lib().mccbn_obs_log_likelihood(
         _ctx(ctx), ptr(obs), ptr(poset), ptr(lam), C.c_double(eps), ptr(wt), ptr(t), C.c_uint(int(L)),
@@ -189,7 +189,8 @@ def obs_loglikelihood(obs, poset, lambda_, eps, weights=None, times=None, L=None
 
 
 def importance_weight(genotype, L, poset, lambda_, eps, time=None, sampling="forward", neighborhood_dist=1,
-                      lambda_s=1.0, thrds=1, seed=None, ctx=None, obs_offset=0, precision=0, stream_id=0):
+                      lambda_s=1.0, thrds=1, seed=None, ctx=None, obs_offset=0, precision=0, stream_id=0,
+                      pool_resample=False):
     """importance.weight (R/mcem_hcbn.R:138-195): matrix input -> `_importance_weight` (src/mcem_hcbn.cpp:914-1010),
     vector input -> `_importance_weight_genotype` (:866-912)."""
     sampling = _match_sampling(sampling)
@@ -198,7 +199,7 @@ def importance_weight(genotype, L, poset, lambda_, eps, time=None, sampling="for
     g = np.asarray(genotype)
     if seed is None:
         seed = int(np.random.randint(1, 30001))
-    opt = _options(obs_offset=obs_offset, precision=precision, stream_id=stream_id)
+    opt = _options(obs_offset=obs_offset, precision=precision, stream_id=stream_id, pool_resample=int(pool_resample))
     e = ErrBuf()
     if g.ndim == 2:
         obs = i32(g)
@@ -630,6 +631,27 @@ def estep_forward_from_times(obs, poset, lambda_, eps, Z, T_sampling, weights=No
         *e.args))
     return dict(w=w, w_sqrt=w2, dist=ed, Tdiff=eT, obs_llhood=tot[0], expected_dist=tot[1], N_eff=tot[2],
                 Tdiff_colsum=tot[3:].copy(), eps_new=en.value, lambda_new=ln)
+
+
+def pool_from_times(obs, poset, eps, T_pool, Tdiff_pool, T_sampling=None, times=None, weights=None, ctx=None):
+    """Pool scheme from a supplied pool (the supplied-randomness seam of the `pool` branch, src/mcem_hcbn.cpp:460-491)."""
+    obs, poset = i32(obs), i32(poset)
+    N, p = obs.shape
+    Tp, Zp = f64(T_pool), f64(Tdiff_pool)
+    K = Tp.shape[0]
+    ts = None if T_sampling is None else f64(T_sampling)
+    t = np.zeros(N) if times is None else f64(times)
+    wt = np.ones(N) if weights is None else f64(weights)
+    X = np.zeros((K, p), np.int32, order="F")
+    d = np.zeros((K, N), np.int32, order="F")
+    q, ed = np.zeros(N), np.zeros(N)
+    eT = np.zeros((N, p), order="F")
+    ll = C.c_double(0)
+    e = ErrBuf()
+    e.check(capi.lib().mccbn_pool_from_times(
+        _ctx(ctx), ptr(obs), N, ptr(poset), p, C.c_double(eps), ptr(wt), ptr(t), int(times is not None), K, ptr(Tp),
+        ptr(Zp), ptr(ts), ptr(X), ptr(d), ptr(q), ptr(ed), ptr(eT), C.byref(ll), *e.args))
+    return dict(X_pool=X, d_pool=d, q_sum=q, dist=ed, Tdiff=eT, llhood=ll.value)
 
 
 def conditional_from_uniforms(X, poset, lambda_, u, T_sampling, ctx=None):

@@ -19,6 +19,7 @@
 // speculation depth.  Exact stream parity with the reference is neither possible nor required.
 #pragma once
 #include <array>
+#include <deque>
 #include <fstream>
 #include <functional>
 #include <numeric>

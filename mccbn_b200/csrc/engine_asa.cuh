@@ -334,17 +334,28 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
   const unsigned batch_floor = pb.local_only ? std::min(batch_cap, (unsigned)pb.ctx->world) : 1u;
   unsigned batch_now = batch < 0 ? std::max(batch_floor, std::min(2u, batch_cap)) : batch_cap;
   unsigned iter = 1;
+  // Look-ahead: proposals are generated (cheap, host side) further ahead than they are scored, under the same "all
+  // rejected" assumption as the scoring batch, so that the NVRTC-specialised kernels of the next candidate posets can be
+  // compiled on background host threads while the device fits the current ones (a compilation takes about as long as
+  // ten candidate fits of BASELINE config 4).  The proposal sequence, and with it the result, does not depend on the
+  // depth: the proposals come from one generator in order, and an acceptance discards everything generated after it.
+  std::deque<Proposal> ahead;
+  const bool prefetch = pb.jit_mode_effective() != 0 && (double)pb.N * (double)L >= 5e6 && scheme != kPool;
+  unsigned depth = 12;
+  if (const char* e = std::getenv("MCCBN_ASA_LOOKAHEAD")) depth = (unsigned)std::max(1, std::min(64, std::atoi(e)));
   while (iter < ctl_asa.max_iter) {
     // 3.0 speculative batch: proposals for steps iter, iter+1, ... assuming every earlier one is rejected
     const unsigned B = std::min<unsigned>(batch_now, ctl_asa.max_iter - iter);
-    std::vector<Proposal> props;
-    props.reserve(B);
+    const unsigned want = std::min<unsigned>(prefetch ? std::max(B, depth) : B, ctl_asa.max_iter - iter);
+    while (ahead.size() < want) {
+      ahead.push_back(generate_proposal(pb, M, fraction_compatible, ctl_asa.compatible_fraction_factor, rng_prop, verbose));
+      if (prefetch && ahead.back().valid) pb.prefetch_kernel(ahead.back().cand.poset, scheme, times_given);
+    }
+    std::deque<Proposal>& props = ahead;  // the first B entries form the scoring batch
     std::vector<Candidate*> to_score;
     std::vector<uint32_t> ids;
     for (unsigned b = 0; b < B; ++b) {
-      props.push_back(generate_proposal(pb, M, fraction_compatible, ctl_asa.compatible_fraction_factor, rng_prop,
-                                        verbose));
-      Proposal& pr = props.back();
+      Proposal& pr = props[b];
       if (!pr.valid) continue;
       std::vector<double>* memo = memo_of(pr.move);
       if (memo && (*memo)[(size_t)pr.v2 * p + pr.v1] != 0.0) {  // :254, :374, :418 -- 0.0 means "not computed"
@@ -371,6 +382,7 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
     if (!to_score.empty()) score_candidates(pb, to_score, ids, scheme, L, ctl_em, times_given, seed, lambda_s, 0);
     // 3.b consume them in order with the reference's accept / reject rule (:436-468)
     bool accepted_any = false;
+    unsigned n_consumed = B;
     for (unsigned b = 0; b < B && !accepted_any; ++b, ++iter) {
       Proposal& pr = props[b];
       if (verbose) std::printf("Step %u - log-likelihood: %g\n", iter, llhood);
@@ -404,6 +416,7 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
         std::fill(memo_pres.begin(), memo_pres.end(), 0.0);
         rng_prop = pr.rng_after;  // discard the speculation beyond this step
         accepted_any = true;
+        n_consumed = b + 1;
         if (batch < 0) batch_now = std::max(batch_floor, std::min(batch_cap, b + 1u));
       }
       if (llhood > llhood_ML) {  // :541-545
@@ -427,6 +440,10 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
       }
     }
     if (batch < 0 && !accepted_any) batch_now = std::min(batch_cap, batch_now * 2u);
+    // proposals generated after an accepted one belong to the old poset: dropped (the generator was rewound above);
+    // without an acceptance only the consumed ones leave the look-ahead queue
+    if (accepted_any) ahead.clear();
+    else ahead.erase(ahead.begin(), ahead.begin() + n_consumed);
   }
   // 4. final fit of the ML poset with doubled EM budget; neighborhood_dist falls back to its default 1 (:583-585)
   EmControl last = ctl_em;

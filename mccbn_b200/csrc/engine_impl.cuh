@@ -41,6 +41,19 @@ struct CondLauncher {
   }
 };
 
+void mccbn_problem::prefetch_kernel(const Poset& P, int scheme, bool times_given) {
+  if (jit_mode_effective() == 0) return;
+  if (!ctx->jit) ctx->jit = new JitCache();
+  FlatPoset f;
+  P.flatten(f);
+  if (scheme == kForward) {
+    ctx->jit->get(f, times_given, JitCache::kBackground);
+  } else if (scheme == kBackward || scheme == kBernoulli || scheme == kAddRemove) {
+    const int mode = scheme == kBackward ? kCondBackward : (scheme == kBernoulli ? kCondBernoulli : kCondAddRemove);
+    ctx->jit->get_cond(f, times_given, mode, JitCache::kBackground);
+  }
+}
+
 void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neighborhood_dist, bool times_given,
                                       uint32_t seed, int update_params, bool per_obs_out, int precision) {
   if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");
@@ -80,10 +93,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
       const char* e = std::getenv("MCCBN_FWD_DYNAMIC");
       return !(e && std::strcmp(e, "0") == 0);
     }();
-    if (dynamic_items) {
-      a.next_item = item_counter.ensure(1);
-      MCCBN_CUDA(cudaMemsetAsync(a.next_item, 0, sizeof(unsigned long long), s));
-    }
+    if (dynamic_items) a.next_item = armed_item_counter();
     if (precision == 1)
       launch_forward<double>(a, flat[c], times_given, grid_x, c);
     else if (jk)
@@ -141,8 +151,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.key1 = key.k1;
     a.cw = eval_id[c];
     a.PS = PS();
-    a.next_item = item_counter.ensure(1);
-    MCCBN_CUDA(cudaMemsetAsync(a.next_item, 0, sizeof(unsigned long long), s));
+    a.next_item = armed_item_counter();
     const int warps_per_block = kFwdBlock / 32;
     long long blocks = (n_items + warps_per_block - 1) / warps_per_block;
     // 32 < p <= 64 exists as a specialised kernel only: compile regardless of the work announced
@@ -188,6 +197,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     const int nb = (N + kPoolBlock - 1) / kPoolBlock;
     long long want = ((long long)ctx->sm_count * 6 + nb - 1) / nb;
     chunks = (int)std::max(1LL, std::min<long long>(want, std::max(1, K / (4 * kPoolTile))));
+    if (pool_resample) chunks = 1;  // the resampling sweep walks the cumulative weights of the whole pool
     chunk_len = ((K + chunks - 1) / chunks + kPoolTile - 1) / kPoolTile * kPoolTile;
     chunks = (K + chunk_len - 1) / chunk_len;
     n_items = (long long)N * chunks;
@@ -210,6 +220,12 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     a.key1 = kts.k1;
     a.cw = eval_id[c];
     a.PS = PS();
+    if (pool_resample) {
+      a.dref = pool_dref.ensure(N);
+      a.qtot = pool_qtot.ensure(N);
+      a.L = L;
+      a.rkey1 = make_key(seed, (uint32_t)iter, 9u).k1;
+    }
     const dim3 grid(nb, chunks);
 #define MCCBN_POOL(PMX)                                                                                         \
   do {                                                                                                          \
@@ -222,6 +238,16 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
       estep_pool_kernel<PMX, true><<<grid, kPoolBlock, 0, s>>>(a, pg);                                          \
     else                                                                                                        \
       estep_pool_kernel<PMX, false><<<grid, kPoolBlock, 0, s>>>(a, pg);                                         \
+    if (pool_resample) { /* the reference's L-index resampling: two more sweeps over the pool */                \
+      if (times_given) {                                                                                        \
+        estep_pool_resample_kernel<PMX, true, 0><<<nb, kPoolBlock, 0, s>>>(a, pg);                              \
+        estep_pool_resample_kernel<PMX, true, 1><<<nb, kPoolBlock, 0, s>>>(a, pg);                              \
+      } else {                                                                                                  \
+        estep_pool_resample_kernel<PMX, false, 0><<<nb, kPoolBlock, 0, s>>>(a, pg);                             \
+        estep_pool_resample_kernel<PMX, false, 1><<<nb, kPoolBlock, 0, s>>>(a, pg);                             \
+      }                                                                                                         \
+      ctx->launches += 2;                                                                                       \
+    }                                                                                                           \
   } while (0)
     if (PM == 8) MCCBN_POOL(8);
     else if (PM == 16) MCCBN_POOL(16);
@@ -233,7 +259,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
   } else {
     throw Error(MCCBN_ERR_ARG, "unknown sampling scheme");
   }
-  run_finalize_mstep(c, chunks, n_items, L_eff, 0, per_obs_out, update_params);
+  run_finalize_mstep(c, chunks, n_items, L_eff, per_obs_out, update_params);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -434,9 +460,44 @@ static int report(const std::exception& e, char* err, size_t errlen) {
 // host memory, which every device of the process can address without enabling peer access (p + 5 doubles per
 // iteration: the few microseconds of PCIe latency are irrelevant next to a millisecond E-step, and no later
 // cudaMalloc has to be mapped into the peers).
+// One persistent host thread per team member: a call hands every worker its closure and waits for all of them (creating
+// and joining G threads per call cost a third of a millisecond at G = 8 -- a tenth of a BASELINE config-3 E-step there).
+struct TeamWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool has_job = false, done = false, quit = false;
+  void loop() {
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv.wait(lk, [&] { return has_job || quit; });
+      if (quit) return;
+      lk.unlock();
+      job();
+      lk.lock();
+      has_job = false;
+      done = true;
+      cv.notify_all();
+    }
+  }
+  void start() { th = std::thread([this] { loop(); }); }
+  void submit(std::function<void()> f) {
+    std::lock_guard<std::mutex> lk(mu);
+    job = std::move(f);
+    done = false;
+    has_job = true;
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done; });
+  }
+};
 struct Team {
   std::vector<mccbn_ctx*> ctx;
   Mailbox* boxes = nullptr;  // cudaHostAlloc(portable | mapped), one per member
+  std::vector<TeamWorker*> workers;  // intentionally never joined: they park on their condition variables until exit
 };
 static Team* g_team = nullptr;
 static int g_team_want = -1;  // -1: read MCCBN_GPUS on first use
@@ -456,13 +517,21 @@ static int team_want_locked() {
 }
 
 // devices a call with N observations would be sharded over (1 = no team); g_default_mu held
+// MCCBN_TEAM_OVERSUBSCRIBE=1 (tests on a one-GPU box): team members may share a device (member r runs on device
+// r mod #devices, with its own context, stream and mailbox) instead of the team being clamped to the device count.  The
+// result of a team call does not depend on the team size, so this is not a numerical knob.
+static bool team_oversubscribe() {
+  const char* e = std::getenv("MCCBN_TEAM_OVERSUBSCRIBE");
+  return e && std::strcmp(e, "1") == 0;
+}
 static int team_size_locked(int N) {
   int G = std::min(team_want_locked(), kMaxWorld);
   if (G > 1) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
     cudaGetLastError();
-    G = std::min(G, n);
+    if (n == 0) return 1;
+    if (!team_oversubscribe()) G = std::min(G, n);
   }
   return (G <= 1 || N < G) ? 1 : G;
 }
@@ -481,9 +550,11 @@ static Team* team_for(int N) {
   Team* t = new Team();
   MCCBN_CUDA(cudaHostAlloc((void**)&t->boxes, sizeof(Mailbox) * G, cudaHostAllocPortable | cudaHostAllocMapped));
   std::memset(t->boxes, 0, sizeof(Mailbox) * G);
+  int n_dev = 1;
+  cudaGetDeviceCount(&n_dev);
   for (int r = 0; r < G; ++r) {
     mccbn_ctx* c = new mccbn_ctx();
-    ctx_init(c, r);
+    ctx_init(c, r % std::max(1, n_dev));
     c->rank = r;
     c->world = G;
     c->mailbox = &t->boxes[r];
@@ -492,6 +563,9 @@ static Team* team_for(int N) {
     c->peer_ready = true;
     c->jit_mode = g_team_jit_mode;
     t->ctx.push_back(c);
+    TeamWorker* w = new TeamWorker();
+    w->start();
+    t->workers.push_back(w);
   }
   cudaSetDevice(caller_device);
   g_team = t;
@@ -511,12 +585,11 @@ static void team_run(Team& t, F&& f) {
   for (mccbn_ctx* c : t.ctx) c->xchg_seq = base;
   std::vector<int> rc(G, MCCBN_OK);
   std::vector<std::array<char, 512>> msg(G);
-  std::vector<std::thread> th;
   for (int r = 0; r < G; ++r) {
     msg[r][0] = 0;
-    th.emplace_back([&, r] { rc[r] = f(r, t.ctx[r], msg[r].data(), msg[r].size()); });
+    t.workers[r]->submit([&, r] { rc[r] = f(r, t.ctx[r], msg[r].data(), msg[r].size()); });
   }
-  for (auto& x : th) x.join();
+  for (int r = 0; r < G; ++r) t.workers[r]->wait();
   int bad = -1;
   for (int r = 0; r < G; ++r)
     if (rc[r] != MCCBN_OK && (bad < 0 || (std::strstr(msg[bad].data(), "timed out") && !std::strstr(msg[r].data(), "timed out"))))
@@ -524,13 +597,6 @@ static void team_run(Team& t, F&& f) {
   if (bad >= 0) throw Error(rc[bad], msg[bad].data());
 }
 
-// rows [lo, hi) of a column-major N x p matrix as a column-major (hi - lo) x p matrix
-static std::vector<int> shard_rows(const int* obs, int N, int p, int lo, int hi) {
-  std::vector<int> out((size_t)(hi - lo) * p);
-  for (int j = 0; j < p; ++j)
-    std::memcpy(out.data() + (size_t)j * (hi - lo), obs + (size_t)j * N + lo, sizeof(int) * (size_t)(hi - lo));
-  return out;
-}
 static inline int shard_begin(int N, int G, int r) { return (int)((long long)N * r / G); }
 // a call shards itself only when the caller passed no context and does not shard on its own
 static inline bool caller_shards(const mccbn_em_options* opt, int N) {
@@ -582,7 +648,6 @@ static void lambda_from_counts(const FlatPoset& f, const unsigned long long* cnt
 
 #include <array>
 #include <chrono>
-#include <functional>
 #include <thread>
 #include "engine_asa.cuh"
 
@@ -685,6 +750,14 @@ int mccbn_ctx_init_peers(mccbn_ctx* c, int rank, int world, const unsigned char*
     throw Error(MCCBN_ERR_ARG, "invalid rank/world for the peer exchange (at most 16 ranks)");
   if (!c->mailbox) throw Error(MCCBN_ERR_ARG, "call mccbn_ctx_peer_handle first");
   if (c->comm && (c->rank != rank || c->world != world)) throw Error(MCCBN_ERR_ARG, "rank/world differ from the NCCL communicator");
+  // the mailbox flags are monotone exchange numbers: a context that has already exchanged cannot be re-initialised (its
+  // flags would satisfy the waits of a restarted sequence) -- create a new context instead
+  if (c->xchg_seq != 0)
+    throw Error(MCCBN_ERR_ARG, "this context has already exchanged statistics: create a new context to change the peer group");
+  for (int q = 0; q < kMaxWorld; ++q) {  // a repeated bootstrap before the first exchange: drop the old mappings
+    if (c->peer_box[q] && c->peer_box[q] != c->mailbox) cudaIpcCloseMemHandle(c->peer_box[q]);
+    c->peer_box[q] = nullptr;
+  }
   for (int q = 0; q < world; ++q) {
     if (q == rank) {
       c->peer_box[q] = c->mailbox;
@@ -823,13 +896,13 @@ int mccbn_MCEM_hcbn(mccbn_ctx* c, const double* ilambda, const int* poset, const
       std::vector<double> eps_r(G), ll_r(G);
       team_run(*team, [&](int r, mccbn_ctx* cr, char* e, size_t el) {
         const int lo = shard_begin(N, G, r), hi = shard_begin(N, G, r + 1);
-        const std::vector<int> sh = shard_rows(obs, N, p, lo, hi);
         mccbn_em_options o;
         if (opt) o = *opt; else std::memset(&o, 0, sizeof(o));
         o.obs_offset = lo;
         o.N_global = N;
+        o.obs_ld = (uint32_t)N;  // rows [lo, hi) of the caller's matrix, uploaded by a strided copy
         if (r != 0) o.trace = nullptr, o.n_iter = nullptr;
-        return mccbn_MCEM_hcbn(cr, ilambda, poset, sh.data(), times ? times + lo : nullptr, lambda_s, eps,
+        return mccbn_MCEM_hcbn(cr, ilambda, poset, obs + lo, times ? times + lo : nullptr, lambda_s, eps,
                                weights ? weights + lo : nullptr, L, sampling, max_iter, update_step_size, tol,
                                max_lambda, neighborhood_dist, sampling_times_available, thrds, r == 0 ? verbose : 0,
                                seed, hi - lo, p, lam_r[r].data(), &eps_r[r], &ll_r[r], &o, e, el);
@@ -855,8 +928,9 @@ int mccbn_MCEM_hcbn(mccbn_ctx* c, const double* ilambda, const int* poset, const
   pb.p = p;
   pb.obs_offset = opt ? opt->obs_offset : 0;
   pb.N_global = (opt && opt->N_global > 0) ? opt->N_global : N;
-  pb.upload(obs, times, weights);
+  pb.upload(obs, times, weights, opt ? opt->obs_ld : 0);
   if (opt) pb.eval_id[0] = opt->stream_id;
+  pb.pool_resample = opt ? opt->pool_resample != 0 : false;
   pb.set_model(0, f, lam.data(), eps, lambda_s, max_lambda);
   EmControl ctl;
   ctl.max_iter = max_iter;
@@ -892,9 +966,10 @@ static void single_estep(mccbn_ctx* c, mccbn_problem& pb, const int* obs, const 
   pb.obs_offset = opt ? opt->obs_offset : 0;
   pb.N_global = (opt && opt->N_global > 0) ? opt->N_global : N;
   const auto t1 = now();
-  pb.upload(obs, times, weights);
+  pb.upload(obs, times, weights, opt ? opt->obs_ld : 0);
   const auto t2 = now();
   if (opt) pb.eval_id[0] = opt->stream_id;
+  pb.pool_resample = opt ? opt->pool_resample != 0 : false;
   pb.ensure_trace(1);
   pb.set_model(0, f, lambda, eps, lambda_s, 1e6f);
   const auto t3 = now();
@@ -918,12 +993,12 @@ int mccbn_obs_log_likelihood(mccbn_ctx* c, const int* obs, const int* poset, con
       std::vector<double> ll_r(G);
       team_run(*team, [&](int r, mccbn_ctx* cr, char* e, size_t el) {
         const int lo = shard_begin(N, G, r), hi = shard_begin(N, G, r + 1);
-        const std::vector<int> sh = shard_rows(obs, N, p, lo, hi);
         mccbn_em_options o;
         if (opt) o = *opt; else std::memset(&o, 0, sizeof(o));
         o.obs_offset = lo;
         o.N_global = N;
-        return mccbn_obs_log_likelihood(cr, sh.data(), poset, lambda, eps, weights ? weights + lo : nullptr,
+        o.obs_ld = (uint32_t)N;
+        return mccbn_obs_log_likelihood(cr, obs + lo, poset, lambda, eps, weights ? weights + lo : nullptr,
                                         times ? times + lo : nullptr, L, sampling, neighborhood_dist, lambda_s,
                                         sampling_times_available, thrds, seed, hi - lo, p, &ll_r[r], &o, e, el);
       });
@@ -955,13 +1030,13 @@ int mccbn_importance_weight(mccbn_ctx* c, const int* obs, unsigned L, const int*
       const int G = (int)team->ctx.size();
       team_run(*team, [&](int r, mccbn_ctx* cr, char* e, size_t el) {
         const int lo = shard_begin(N, G, r), hi = shard_begin(N, G, r + 1), n = hi - lo;
-        const std::vector<int> sh = shard_rows(obs, N, p, lo, hi);
         mccbn_em_options o;
         if (opt) o = *opt; else std::memset(&o, 0, sizeof(o));
         o.obs_offset = lo;
         o.N_global = N;
+        o.obs_ld = (uint32_t)N;
         std::vector<double> td(Tdiff ? (size_t)n * p : 0);
-        const int rc = mccbn_importance_weight(cr, sh.data(), L, poset, lambda, eps, times ? times + lo : nullptr,
+        const int rc = mccbn_importance_weight(cr, obs + lo, L, poset, lambda, eps, times ? times + lo : nullptr,
                                                sampling, neighborhood_dist, lambda_s, sampling_times_available, thrds,
                                                seed, n, p, w_sum ? w_sum + lo : nullptr,
                                                w_sum_sq ? w_sum_sq + lo : nullptr, L_eff ? L_eff + lo : nullptr,
@@ -1363,7 +1438,7 @@ int mccbn_estep_forward_from_times(mccbn_ctx* c, const int* obs, int N, const in
       pb.part.ptr, pb.PS());
   c->launches += 2;
   MCCBN_CUDA(cudaGetLastError());
-  pb.run_finalize(0, 1, N, L, 0, true);
+  pb.run_finalize(0, 1, N, L, true);
   // totals before the M-step overwrites nothing: stats = [LL, N_eff, D, zero, 0, S_k (topological order)]
   std::vector<double> st(pb.PS());
   MCCBN_CUDA(cudaMemcpyAsync(st.data(), pb.stats_of(0), sizeof(double) * pb.PS(), cudaMemcpyDeviceToHost, s));
@@ -1385,6 +1460,80 @@ int mccbn_estep_forward_from_times(mccbn_ctx* c, const int* obs, int N, const in
   }
   if (eps_new) *eps_new = dm.eps;
   if (lambda_new) std::memcpy(lambda_new, dm.lambda, sizeof(double) * p);
+  MCCBN_CATCH
+}
+
+// Pool scheme from a supplied pool: the supplied-randomness seam of SURVEY 8a-a9.  The pool branch of importance_weight
+// (src/mcem_hcbn.cpp:460-491) is, given the pool, deterministic up to its L-index resampling: q_k = eps^d (1-eps)^(p-d),
+// every resampled row carries the weight sum(q)/K, so obs_llhood_i = log(sum_k q_k / K); the resampled means estimate
+// sum_k q_k g_k / sum_k q_k, which is what `dist` / `Tdiff` return (fp64, host pow table: same libm expression as :463-464).
+int mccbn_pool_from_times(mccbn_ctx* c, const int* obs, int N, const int* poset, int p, double eps,
+                          const double* weights, const double* times, int sampling_times_available, int K,
+                          const double* T_pool, const double* Tdiff_pool, const double* T_sampling, int* X_pool,
+                          int* d_pool, double* q_sum, double* dist, double* Tdiff, double* llhood, char* err,
+                          size_t errlen) {
+  MCCBN_TRY
+  c = get_ctx(c);
+  if (N < 1 || K < 1) throw Error(MCCBN_ERR_ARG, "pool_from_times: N and K must be >= 1");
+  if (!sampling_times_available && !T_sampling) throw Error(MCCBN_ERR_ARG, "pool_from_times: sampling times expected");
+  Poset P;
+  FlatPoset f;
+  flatten_or_throw(poset, p, P, f);
+  mccbn_problem pb;
+  pb.ctx = c;
+  pb.N = N;
+  pb.p = p;
+  pb.upload(obs, times, weights);
+  pb.ensure_trace(1);
+  std::vector<double> lam1(p, 1.0);
+  pb.set_model(0, f, lam1.data(), eps, 1.0f, 1e6f);  // only the structure and eps matter here
+  cudaStream_t s = c->stream;
+  DevBuf<double> dZ, dT, dTs, dWt;
+  DevBuf<int> dD, dX, dD0;
+  const size_t KP = (size_t)K * p;
+  MCCBN_CUDA(cudaMemcpyAsync(dZ.ensure(KP), Tdiff_pool, sizeof(double) * KP, cudaMemcpyHostToDevice, s));
+  MCCBN_CUDA(cudaMemcpyAsync(dT.ensure(KP), T_pool, sizeof(double) * KP, cudaMemcpyHostToDevice, s));
+  dTs.ensure(K);
+  if (T_sampling) MCCBN_CUDA(cudaMemcpyAsync(dTs.ptr, T_sampling, sizeof(double) * K, cudaMemcpyHostToDevice, s));
+  const std::vector<double> wt = host_wtab(eps, p);
+  MCCBN_CUDA(cudaMemcpyAsync(dWt.ensure(65), wt.data(), sizeof(double) * 65, cudaMemcpyHostToDevice, s));
+  const int gx = std::min(2048, (K + 127) / 128);
+  if (d_pool) {
+    pool_dist_kernel<<<dim3(gx, N), 128, 0, s>>>(dT.ptr, dTs.ptr, pb.bits.ptr, pb.times.ptr, sampling_times_available, N,
+                                                 K, p, dD.ensure((size_t)K * N));
+    c->launches++;
+  }
+  if (X_pool) {  // genotypes of the pool at observation 0's sampling times (the same for all observations unless times are given)
+    DevBuf<double> dTs0;
+    const double* ts0 = dTs.ptr;
+    if (sampling_times_available) {
+      std::vector<double> t0((size_t)K, times[0]);
+      MCCBN_CUDA(cudaMemcpyAsync(dTs0.ensure(K), t0.data(), sizeof(double) * K, cudaMemcpyHostToDevice, s));
+      MCCBN_CUDA(cudaStreamSynchronize(s));
+      ts0 = dTs0.ptr;
+    }
+    forward_from_times_kernel<<<gx, 128, 0, s>>>(dT.ptr, ts0, 0ull, K, p, dWt.ptr, dX.ensure(KP), dD0.ensure(K), nullptr);
+    c->launches++;
+    MCCBN_CUDA(cudaMemcpyAsync(X_pool, dX.ptr, sizeof(int) * KP, cudaMemcpyDeviceToHost, s));
+    MCCBN_CUDA(cudaStreamSynchronize(s));
+  }
+  pb.part.ensure((size_t)N * pb.PS());
+  estep_from_times_kernel<<<std::min(N, c->sm_count * 8), kF64Block, 0, s>>>(
+      dZ.ptr, dT.ptr, dTs.ptr, pb.bits.ptr, pb.times.ptr, sampling_times_available, N, K, pb.posets.ptr, dWt.ptr,
+      pb.part.ptr, pb.PS());
+  c->launches++;
+  MCCBN_CUDA(cudaGetLastError());
+  pb.run_finalize(0, 1, N, K, true);  // L_eff = K: obs_llhood_i = log(sum q / K)
+  pb.run_mstep(0, 0);
+  DevModel dm;
+  pb.read_model(0, dm);
+  if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, kMsgZeroWeight);
+  if (d_pool) MCCBN_CUDA(cudaMemcpyAsync(d_pool, dD.ptr, sizeof(int) * (size_t)K * N, cudaMemcpyDeviceToHost, s));
+  if (q_sum) MCCBN_CUDA(cudaMemcpyAsync(q_sum, pb.out_w.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (dist) MCCBN_CUDA(cudaMemcpyAsync(dist, pb.out_dist.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  if (Tdiff) MCCBN_CUDA(cudaMemcpyAsync(Tdiff, pb.out_T.ptr, sizeof(double) * (size_t)N * p, cudaMemcpyDeviceToHost, s));
+  MCCBN_CUDA(cudaStreamSynchronize(s));
+  if (llhood) *llhood = dm.llhood;
   MCCBN_CATCH
 }
 
@@ -2044,7 +2193,12 @@ int mccbn_expectedTimeDifference(mccbn_ctx* c, int nrOfSamples, const int* O_vec
   otcbn_estep(c, pb, O_vec, &time, nullptr, poset, lambda, nrOfSamples, lambda_s, sampling_time_available, seed, 1, p);
   cudaStream_t s = c->stream;
   MCCBN_CUDA(cudaMemcpyAsync(time_difference, pb.out_T.ptr, sizeof(double) * p, cudaMemcpyDeviceToHost, s));
-  MCCBN_CUDA(cudaStreamSynchronize(s));
+  DevModel dm;
+  pb.read_model(0, dm);  // synchronises
+  // Weights are kept in log space on the device, so a compatible genotype never loses all its weight to underflow (the
+  // case the reference's uniform fallback, src/mcem.cpp:123-127, papers over); weight 0 for every draw means that the
+  // genotype is incompatible with the poset -- the reference would return NaN waiting times here.
+  if (dm.zero_weight) throw Error(MCCBN_ERR_ZERO_WEIGHT, "expectedTimeDifference: the genotype is incompatible with the poset (all importance weights are 0)");
   MCCBN_CATCH
 }
 
@@ -2062,13 +2216,13 @@ int mccbn_loglike_importance_sampling(mccbn_ctx* c, const int* poset, const doub
   otcbn_estep(c, pb, obs_events, sampling_times, weights, poset, lambda, nrOfSamples, lambda_s,
               sampling_times_available, seed, N, p);
   cudaStream_t s = c->stream;
-  std::vector<double> w(N);
-  MCCBN_CUDA(cudaMemcpyAsync(w.data(), pb.out_w.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
+  std::vector<double> lw(N);  // log sum_l w_il straight from the log-sum-exp of the partial records (no exp / log round trip)
+  MCCBN_CUDA(cudaMemcpyAsync(lw.data(), pb.out_logw.ptr, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
   MCCBN_CUDA(cudaStreamSynchronize(s));
   double total = 0.0;
   const double logn = std::log((double)nrOfSamples);
   for (int i = 0; i < N; ++i) {
-    const double v = (weights ? weights[i] : 1.0) * (std::log(w[i]) - logn);
+    const double v = (weights ? weights[i] : 1.0) * (lw[i] - logn);
     if (probs) probs[i] = v;
     total += v;
   }

@@ -470,7 +470,7 @@ struct JitCache {
       pending.erase(pit);
       have = !cc.cubin.empty();
     } else {
-      if (pol != kCompileNow && disk_misses.count(key)) return nullptr;  // per-iteration path of small problems
+      if (pol == kCachedOnly && disk_misses.count(key)) return nullptr;  // per-iteration path of small problems
       const std::string src = make_src();
       const std::string path = jit_cache_path(rtc, src);
       have = jit_disk_read(path, cc.cubin);

@@ -93,6 +93,23 @@ __global__ void __launch_bounds__(kF64Block) estep_from_times_kernel(
   }
 }
 
+// Pool scheme from a supplied pool (src/mcem_hcbn.cpp:215-236, :326-330, :676): d_pool[i, k] = Hamming distance between
+// observation i and the pool genotype X_k = [T_pool(k, j) <= T_s] (T_s = Ts[k], or times[i] when given).
+// d_out is K x N column-major (column i = the reference's d_pool vector of observation i).
+__global__ void pool_dist_kernel(const double* __restrict__ T_sum, const double* __restrict__ Ts,
+                                 const uint64_t* __restrict__ obs_bits, const double* __restrict__ times, int times_given,
+                                 int N, int K, int p, int* __restrict__ d_out) {
+  const int i = blockIdx.y;
+  if (i >= N) return;
+  const uint64_t yw = obs_bits[i];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    const double ts = times_given ? times[i] : Ts[k];
+    uint64_t x = 0;
+    for (int j = 0; j < p; ++j) x |= (uint64_t)(T_sum[(size_t)j * K + k] <= ts) << j;
+    d_out[(size_t)i * K + k] = __popcll(x ^ yw);
+  }
+}
+
 // Source of the randomness of the conditional seam kernel below.  enabled == 0: X, U and Ts are the caller's arrays
 // (supplied-randomness tier).  enabled == 1: one genotype `x_word` shared by all samples, 53-bit Philox uniforms
 // (counter = (sample l, 0, event >> 1, cw)) and, if draw_ts, T_s ~ Exp(lambda_s) per sample (block 64) -- the legacy

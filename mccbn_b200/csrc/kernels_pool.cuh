@@ -30,6 +30,7 @@ namespace mccbn {
 
 constexpr int kPoolBlock = 128;  // observations per block
 constexpr int kPoolTile = 64;    // pool entries per shared-memory tile
+constexpr int kPoolFlush = 1024; // pool entries between two flushes of a thread's fp32 partial sums into its fp64 record
 
 // Pool generation: entry k draws Z_j ~ Exp(lambda_j) and propagates T_j (sample_times, src/mcem_hcbn.cpp:184-213).
 // Output per entry: Tp[k][PMAX] the event times in ASCENDING order (padded with +inf), Mp[k][PMAX + 1] the prefix
@@ -97,6 +98,11 @@ struct PoolArgs {
   long long obs_offset;
   uint32_t key0, key1, cw;
   int PS;
+  // pool_resample = 1 (the reference's L-index resampling, src/mcem_hcbn.cpp:477-484); chunks == 1 in this mode
+  int* dref;        // N: reference distance of the observation's relative weights (written by estep_pool_kernel)
+  double* qtot;     // N: sum_k w'_k in fp64 with that fixed reference (estep_pool_resample_kernel, pass 0)
+  int L;            // indices drawn per observation
+  uint32_t rkey1;   // Philox key word 1 of the resampling stream
 };
 
 template <int PMAX, bool TIMES_GIVEN>
@@ -125,9 +131,37 @@ __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a
   float aw = 0.f, aw2 = 0.f, awd = 0.f;
   int dref = 1 << 20;
 
+  // The per-thread sums are fp32 only over kPoolFlush pool entries: then they are added to the observation's fp64
+  // record (L2-resident; rescaled first if the reference distance has moved since the last flush) -- the same
+  // "short fp32 partial sums, fp64 beyond" rule as in the forward kernel (<= L / 32 samples per lane there).
+  double* out = a.part + ((size_t)(live ? i : 0) * a.chunks + ch) * a.PS;
+  int fdref = 1 << 20;  // reference distance of what the record holds; 1 << 20: nothing flushed yet
+  auto flush = [&]() {
+    if (!live || dref == (1 << 20)) return;
+    if (fdref == (1 << 20)) {
+      out[0] = (double)aw, out[1] = (double)aw2, out[2] = (double)awd;
+#pragma unroll
+      for (int j = 0; j < PMAX; ++j)
+        if (j < p) out[kStatHdr + j] = (double)acc[j];
+    } else {
+      const double sc = fdref != dref ? mdl->rtab_d[min(fdref - dref, kRtabN - 1)] : 1.0;  // dref only decreases
+      out[0] = out[0] * sc + (double)aw;
+      out[1] = out[1] * sc * sc + (double)aw2;
+      out[2] = out[2] * sc + (double)awd;
+#pragma unroll
+      for (int j = 0; j < PMAX; ++j)
+        if (j < p) out[kStatHdr + j] = out[kStatHdr + j] * sc + (double)acc[j];
+    }
+    fdref = dref;
+    aw = aw2 = awd = 0.f;
+#pragma unroll
+    for (int j = 0; j < PMAX; ++j) acc[j] = 0.f;
+  };
+
   const int k_begin = ch * a.chunk_len, k_end = min(a.K, k_begin + a.chunk_len);
   for (int k0 = k_begin; k0 < k_end; k0 += kPoolTile) {
     __syncthreads();
+    if (k0 > k_begin && ((k0 - k_begin) % kPoolFlush) == 0) flush();
     const int nk = min(kPoolTile, k_end - k0);
     for (int t = threadIdx.x; t < nk * PMAX / 4; t += kPoolBlock) {  // coalesced float4 copy of the tile
       reinterpret_cast<float4*>(s_Tt)[t] = reinterpret_cast<const float4*>(a.Tp + (size_t)k0 * PMAX)[t];
@@ -179,17 +213,138 @@ __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a
       }
     }
   }
+  flush();
   if (live) {
-    double* out = a.part + ((size_t)i * a.chunks + ch) * a.PS;
-    out[0] = (double)aw;
-    out[1] = (double)aw2;
-    out[2] = (double)awd;
     out[3] = (double)(k_end - k_begin);
     out[4] = mdl->log_base + (dref > 0 ? (double)dref * mdl->log_r : 0.0);
-#pragma unroll
-    for (int j = 0; j < PMAX; ++j)
-      if (j < p) out[kStatHdr + j] = (double)acc[j];
+    if (a.dref) a.dref[i] = dref;
   }
+}
+
+// pool_resample = 1: the reference does not average over the whole pool but draws L indices with replacement from
+// Discrete(q) and averages d and Z over the drawn rows (src/mcem_hcbn.cpp:477-484, rdiscrete_std :44-54).  The K weights
+// of an observation are never stored: L iid indices from Discrete(q) are distributed like the cells that the ORDER
+// STATISTICS of L iid uniforms fall into along the cumulative weights, and those can be generated one by one in
+// increasing order (the smallest of m iid U(a, 1) is 1 - (1 - a) V^(1/m)), i.e. during ONE more sweep over the pool.
+//   PASS 0: qtot[i] = sum_k w'_k in fp64 for the fixed reference distance dref[i] (the total the order statistics scale to)
+//   PASS 1: sweep with the running cumulative weight; entry k is drawn cnt_k times; the record's sum w' d and sum w' Z_j
+//           become sum w' x (resampled mean), so that finalize_kernel's ratios are the reference's resampled means
+//           (sum w' itself, hence obs_llhood = log(sum q / K), is untouched: every drawn row has weight sum q / K, :491)
+// Same tiles, sampling-time stream and rank search as estep_pool_kernel; one thread per observation, whole pool.
+template <int PMAX, bool TIMES_GIVEN, int PASS>
+__global__ void __launch_bounds__(kPoolBlock) estep_pool_resample_kernel(const PoolArgs a,
+                                                                         const __grid_constant__ PosetProg pg) {
+  __shared__ __align__(16) float s_Tt[kPoolTile * PMAX];
+  __shared__ __align__(16) float s_Zt[kPoolTile * PMAX];
+  __shared__ uint32_t s_Mt[kPoolTile * (PMAX + 1)];
+  __shared__ float s_rtab[kRtabN];
+  const DevModel* __restrict__ mdl = a.model;
+  const int p = pg.p;
+  for (int t = threadIdx.x; t < kRtabN; t += kPoolBlock) s_rtab[t] = mdl->rtab[t];
+  const int flip = mdl->flip;
+  const uint32_t key1 = iter_key(a.key1, mdl), rkey1 = iter_key(a.rkey1, mdl);
+  const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+  const bool live = i < a.N;
+  const uint32_t yt = live ? to_topo_bits<PMAX>(pg, a.obs_bits[i]) : 0u;
+  const float ts_given = (TIMES_GIVEN && live) ? (float)a.times[i] : 0.f;
+  const uint32_t gi = (uint32_t)(a.obs_offset + i);
+  const float cs = a.scale->cs;
+  const int dref = live ? a.dref[i] : 0;
+
+  double C = 0.0;                              // running cumulative weight
+  const double S = (PASS == 1 && live) ? a.qtot[i] : 0.0;
+  int m = (PASS == 1 && live) ? a.L : 0;       // order statistics still to come
+  uint32_t draw = 0;                           // index of the next uniform of the resampling stream
+  double rem = 1.0;                            // 1 - (current order statistic)
+  double thr = 0.0;                            // S * (current order statistic): the next draw falls into the first
+                                               // entry whose cumulative weight exceeds it
+  auto next_order_statistic = [&]() {
+    const uint4 r = philox4x32_10(draw >> 1, gi, 1u, a.cw, a.key0, rkey1);
+    const double v = (draw & 1u) ? u01_open0_d(r.z, r.w) : u01_open0_d(r.x, r.y);
+    ++draw;
+    rem *= exp(log(v) / (double)m);
+    thr = S * (1.0 - rem);
+  };
+  if (m > 0) next_order_statistic();
+  double sd = 0.0;
+  double acc[PMAX];  // sums of up to L rows: fp64 (this sweep is bound by the rank searches, not by these adds)
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j) acc[j] = 0.0;
+  int last_k = -1;  // last entry with a positive weight (takes the draws a rounding of S may leave over)
+
+  for (int k0 = 0; k0 < a.K; k0 += kPoolTile) {
+    __syncthreads();
+    const int nk = min(kPoolTile, a.K - k0);
+    for (int t = threadIdx.x; t < nk * PMAX / 4; t += kPoolBlock) {
+      reinterpret_cast<float4*>(s_Tt)[t] = reinterpret_cast<const float4*>(a.Tp + (size_t)k0 * PMAX)[t];
+      if (PASS == 1) reinterpret_cast<float4*>(s_Zt)[t] = reinterpret_cast<const float4*>(a.Zp + (size_t)k0 * PMAX)[t];
+    }
+    for (int t = threadIdx.x; t < nk * (PMAX + 1); t += kPoolBlock) s_Mt[t] = a.Mp[(size_t)k0 * (PMAX + 1) + t];
+    __syncthreads();
+    uint4 r = make_uint4(0, 0, 0, 0);
+    for (int kk = 0; kk < nk; ++kk) {
+      float Ts = ts_given;
+      if (!TIMES_GIVEN) {
+        const int k = k0 + kk;
+        if ((kk & 3) == 0) r = philox4x32_10((uint32_t)(k >> 2), gi, 0u, a.cw, a.key0, key1);
+        const uint32_t bits = (kk & 3) == 0 ? r.x : ((kk & 3) == 1 ? r.y : ((kk & 3) == 2 ? r.z : r.w));
+        Ts = fast_lg2(u01_open0(bits)) * cs;
+      }
+      const float* Tk = s_Tt + kk * PMAX;
+      int rank = 0;
+#pragma unroll
+      for (int step = PMAX / 2; step >= 1; step >>= 1)
+        if (Tk[rank + step - 1] <= Ts) rank += step;
+      if (Tk[rank] <= Ts) rank += 1;
+      const uint32_t X = s_Mt[kk * (PMAX + 1) + rank];
+      const int d = __popc(X ^ yt);
+      const int de = flip ? p - d : d;
+      const float wr = s_rtab[min(max(de - dref, 0), kRtabN - 1)];
+      C += (double)wr;
+      if (PASS == 1 && wr > 0.f) {
+        last_k = k0 + kk;
+        int cnt = 0;
+        while (m > 0 && thr < C) {  // the order statistics that fall into this entry's cell
+          ++cnt;
+          --m;
+          if (m > 0) next_order_statistic();
+        }
+        if (cnt > 0) {
+          const double fc = (double)cnt;
+          sd += (double)(cnt * d);
+#pragma unroll
+          for (int j = 0; j < PMAX; ++j) acc[j] = fma(fc, (double)s_Zt[kk * PMAX + j], acc[j]);
+        }
+      }
+    }
+  }
+  if (!live) return;
+  if (PASS == 0) {
+    a.qtot[i] = C;
+    return;
+  }
+  double* out = a.part + (size_t)i * a.PS;
+  const double W = out[0], invL = 1.0 / (double)a.L;
+  double left = (double)m;  // > 0 only if S (pass 0) and C (this pass) differ in the last bit
+  int d_last = 0;
+  if (m > 0 && last_k >= 0) {
+    float Ts = ts_given;
+    if (!TIMES_GIVEN) {
+      const uint4 r = philox4x32_10((uint32_t)(last_k >> 2), gi, 0u, a.cw, a.key0, key1);
+      const int q = last_k & 3;
+      Ts = fast_lg2(u01_open0(q == 0 ? r.x : (q == 1 ? r.y : (q == 2 ? r.z : r.w)))) * cs;
+    }
+    int rank = 0;
+    for (int j = 0; j < PMAX; ++j) rank += a.Tp[(size_t)last_k * PMAX + j] <= Ts ? 1 : 0;  // row is sorted, padded with +inf
+    d_last = __popc(a.Mp[(size_t)last_k * (PMAX + 1) + rank] ^ yt);
+  }
+  out[2] = W * (sd + left * (double)d_last) * invL;
+#pragma unroll
+  for (int j = 0; j < PMAX; ++j)
+    if (j < p) {
+      const double zl = (m > 0 && last_k >= 0) ? left * (double)a.Zp[(size_t)last_k * PMAX + j] : 0.0;
+      out[kStatHdr + j] = W * (acc[j] + zl) * invL;
+    }
 }
 
 }  // namespace mccbn

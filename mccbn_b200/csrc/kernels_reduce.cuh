@@ -31,7 +31,7 @@ struct FinArgs {
   int N, chunks, PS, p;
   long long n_items;
   int L_eff;                // > 0: fixed L_eff (forward / bernoulli / pool: L); <= 0: #{w > 0} (backward, :688-689)
-  int uniform_fallback;     // OT-CBN: sum w == 0 => uniform weights instead of an error (src/mcem.cpp:123-127)
+  double* log_w;            // optional: natural log of sum w per observation (no underflow; OT-CBN log-likelihood caller)
 };
 
 // Partial record (one per observation and chunk): [0]=sum w', [1]=sum w'^2, [2]=sum w' d, [3]=#{w>0},
@@ -70,6 +70,7 @@ __device__ __forceinline__ void finalize_body(const FinArgs& a) {
     if (lane == 0) {
       accA += ok ? wt * (logW - log(Leff)) : 0.0;
       if (a.w_sum) a.w_sum[i] = w_true;
+      if (a.log_w) a.log_w[i] = logW;
       if (a.L_eff_out) a.L_eff_out[i] = (int)npos;
     } else if (lane == 1) {
       accA += ok ? wt : 0.0;
@@ -279,16 +280,20 @@ __device__ __forceinline__ void mstep_body(double* __restrict__ st, const DevPos
 
 __global__ void mstep_kernel(double* __restrict__ st, const DevPoset* pos, DevModel* mdl, FwdScale* scale,
                              double* trace, int trace_stride, int max_trace_rows, int PS, int update_params,
-                             const PeerView pv) {
+                             const PeerView pv, unsigned long long* rearm) {
+  if (threadIdx.x == 0 && rearm) *rearm = 0ull;  // work counter of the E-step kernels, for the next E-step
   mstep_body(st, pos, mdl, scale, trace, trace_stride, max_trace_rows, PS, update_params, pv);
 }
 
-// Single-GPU tail of an EM iteration in ONE launch: per-observation finalize in every block; the block that finishes
-// last (ticket counter) sums the block partials and runs the M-step.  Small problems are bound by the latency of the
-// launch chain: three launches become one.
+// Tail of an EM iteration in ONE launch: per-observation finalize in every block; the block that finishes last (ticket
+// counter) sums the block partials, -- when the observations are sharded over ranks -- pushes the vector into every
+// rank's mailbox, waits for the vectors of all ranks and sums them in rank order, and runs the M-step.  An EM iteration
+// is two launches (E-step + tail) on one GPU and on several.
 struct FusedTail {
   double* stats;
   unsigned* counter;  // zero before the first launch; re-armed by the last block
+  unsigned long long* rearm;  // work counter of the E-step kernels (FwdArgs / CondArgs::next_item): zeroed for the next one
+  PeerView pv;        // world > 1: the last block also exchanges the statistic vector with the other ranks
   const DevPoset* pos;
   DevModel* mdl;
   FwdScale* scale;
@@ -303,20 +308,30 @@ __global__ void __launch_bounds__(kFinBlock) finalize_mstep_kernel(const FinArgs
   if (threadIdx.x == 0) s_ticket = atomicAdd(t.counter, 1u);
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
-  if (threadIdx.x == 0) *t.counter = 0u;
+  if (threadIdx.x == 0) {
+    *t.counter = 0u;
+    if (t.rearm) *t.rearm = 0ull;
+  }
   __threadfence();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int par = (int)(t.pv.seq & 1ull);
   for (int s = warp; s < a.PS; s += kFinWarps) {  // same order as slot_total; L2 loads: other blocks wrote the data
     double v = 0.0;
     for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(a.blk_part + (size_t)b * a.PS + s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) t.stats[s] = v;
+    // sharded over ranks: lane q stores this rank's value into rank q's mailbox (NVLink peer store / pinned host memory)
+    if (t.pv.world > 1 && lane < t.pv.world) t.pv.box[lane]->slot[par][t.pv.rank][s] = v;
+  }
+  if (t.pv.world > 1) {  // publish: all slot stores of this block before the flags (release at system scope)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < t.pv.world) st_release_sys(&t.pv.box[threadIdx.x]->flag[t.pv.rank], t.pv.seq);
   }
   __syncthreads();
-  PeerView pv;
-  pv.world = 1;
-  mstep_body(t.stats, t.pos, t.mdl, t.scale, t.trace, t.trace_stride, t.max_trace_rows, a.PS, t.update_params, pv);
+  // world > 1: mstep_body first waits for every rank's flag and sums the slots in rank order (peer_pull)
+  mstep_body(t.stats, t.pos, t.mdl, t.scale, t.trace, t.trace_stride, t.max_trace_rows, a.PS, t.update_params, t.pv);
 }
 
 // ---- indexing kernels ---------------------------------------------------------------------------------------

@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <thread>
 #include <cfloat>
 #include <mutex>
@@ -163,11 +165,14 @@ struct mccbn_problem {
   DevBuf<DevModel> models;
   DevBuf<FwdScale> scales;
   DevBuf<double> part, blk, stats, trace;
-  DevBuf<double> out_w, out_w2, out_dist, out_T;
+  DevBuf<double> out_w, out_w2, out_dist, out_T, out_logw;
   DevBuf<int> out_leff;
   DevBuf<uint64_t> ball;  // backward scheme: flip masks of the Hamming ball
   DevBuf<float> pool_T, pool_Z;  // pool scheme: K x PMAX sorted event times / waiting times
   DevBuf<uint32_t> pool_M;       // pool scheme: K x (PMAX + 1) prefix genotypes
+  DevBuf<int> pool_dref;         // pool_resample: reference distance per observation
+  DevBuf<double> pool_qtot;      // pool_resample: fp64 total weight per observation
+  bool pool_resample = false;    // mccbn_em_options.pool_resample
   DevBuf<unsigned long long> counts;  // compatibility / initialize_lambda counters
   int ball_p = -1, ball_k = -1;
   int trace_rows = 0;
@@ -200,11 +205,17 @@ struct mccbn_problem {
   double* stats_of(int c) { return stats.ptr + (size_t)c * kMaxPS; }
   double* trace_of(int c) { return trace.ptr + (size_t)c * trace_rows * (p + 2); }
 
-  void upload(const int* obs, const double* t, const double* w) {
+  // `ld`: leading dimension of the column-major host matrix `obs` (rows of the full matrix when obs points at a block of
+  // rows of it, mccbn_em_options.obs_ld); 0 = N
+  void upload(const int* obs, const double* t, const double* w, size_t ld = 0) {
     cudaStream_t s = ctx->stream;
     DevBuf<int> tmp;
     tmp.ensure((size_t)N * p);
-    MCCBN_CUDA(cudaMemcpyAsync(tmp.ptr, obs, sizeof(int) * (size_t)N * p, cudaMemcpyHostToDevice, s));
+    if (ld == 0 || ld == (size_t)N)
+      MCCBN_CUDA(cudaMemcpyAsync(tmp.ptr, obs, sizeof(int) * (size_t)N * p, cudaMemcpyHostToDevice, s));
+    else  // p columns of N ints each, ld ints apart on the host
+      MCCBN_CUDA(cudaMemcpy2DAsync(tmp.ptr, sizeof(int) * (size_t)N, obs, sizeof(int) * ld, sizeof(int) * (size_t)N, (size_t)p,
+                                   cudaMemcpyHostToDevice, s));
     bits.ensure(N);
     pack_obs_kernel<<<std::min(1024, (N + 255) / 256), 256, 0, s>>>(tmp.ptr, bits.ptr, N, p);
     ctx->launches++;
@@ -290,6 +301,9 @@ struct mccbn_problem {
     if (!ctx->jit) ctx->jit = new JitCache();
     return ctx->jit->get(f, times_given, jit_policy(mode, (double)N * (double)L));
   }
+
+  // start compiling the specialised kernel of a poset on a background thread (annealer look-ahead); never blocks
+  void prefetch_kernel(const Poset& P, int scheme /* Scheme */, bool times_given);
 
   // the same policy for the conditional-proposal kernels (backward / bernoulli / OT-CBN / add-remove)
   JitKernel* resolve_jit_cond(const FlatPoset& f, bool times_given, int mode, double samples_per_estep,
@@ -418,12 +432,17 @@ struct mccbn_problem {
       enqueue_iteration(c, scheme, L, neighborhood_dist, times_given, seed, update_params, false, precision);  // eager
       ++done;
       cudaStream_t s = ctx->stream;
-      std::ostringstream k;
-      k << (int)scheme << ':' << L << ':' << neighborhood_dist << ':' << times_given << ':' << seed << ':' << update_params
-        << ':' << precision << ':' << N << ':' << p << ':' << model_version[c] << ':' << eval_id[c] << ':' << trace_rows << ':'
-        << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode << ':' << jit_generation();
+      auto graph_key = [&] {  // everything a captured iteration depends on besides device memory
+        std::ostringstream k;
+        k << (int)scheme << ':' << L << ':' << neighborhood_dist << ':' << times_given << ':' << seed << ':' << update_params
+          << ':' << precision << ':' << pool_resample << ':' << N << ':' << p << ':' << model_version[c] << ':' << eval_id[c]
+          << ':' << trace_rows << ':' << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode
+          << ':' << jit_generation();
+        return k.str();
+      };
+      const std::string key_now = graph_key();
       IterGraph& g = iter_graph[c];
-      if (!g.exec || g.key != k.str()) {
+      if (!g.exec || g.key != key_now) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
         g.exec = nullptr;
         const uint64_t l0 = ctx->launches, j0 = ctx->jit_launches;
@@ -453,12 +472,7 @@ struct mccbn_problem {
           g.key.clear();
         } else {
           // allocation epoch as of AFTER the eager iteration and the capture (neither allocates in steady state)
-          std::ostringstream k2;
-          k2 << (int)scheme << ':' << L << ':' << neighborhood_dist << ':' << times_given << ':' << seed << ':'
-             << update_params << ':' << precision << ':' << N << ':' << p << ':' << model_version[c] << ':' << eval_id[c]
-             << ':' << trace_rows << ':' << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode
-             << ':' << jit_generation();
-          g.key = k2.str();
+          g.key = graph_key();
         }
       }
       if (g.exec) {
@@ -477,22 +491,31 @@ struct mccbn_problem {
   // finalize + second-stage reduction + M-step; one fused launch on a single GPU (finalize_mstep_kernel)
   DevBuf<unsigned> fuse_counter;
   DevBuf<unsigned long long> item_counter;  // dynamic work distribution of the conditional kernels
-  void run_finalize_mstep(int c, int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out,
+  void run_finalize_mstep(int c, int chunks, long long n_items, int L_eff, bool per_obs_out,
                           int update_params) {
     static const bool fuse = [] {
       const char* e = std::getenv("MCCBN_FUSE_TAIL");
       return !(e && std::strcmp(e, "0") == 0);
     }();
-    if (fuse && !sharded()) {
-      run_finalize(c, chunks, n_items, L_eff, uniform_fallback, per_obs_out, update_params, /*fused=*/true);
+    if (fuse && (!sharded() || ctx->peer_ready)) {  // the NCCL exchange needs a host-enqueued collective in between
+      run_finalize(c, chunks, n_items, L_eff, per_obs_out, update_params, /*fused=*/true);
       iter_host[c]++;
     } else {
-      run_finalize(c, chunks, n_items, L_eff, uniform_fallback, per_obs_out);
+      run_finalize(c, chunks, n_items, L_eff, per_obs_out);
       run_mstep(c, update_params);
     }
   }
 
-  void run_finalize(int c, int chunks, long long n_items, int L_eff, int uniform_fallback, bool per_obs_out,
+  // work counter of the E-step kernels: zeroed when it is allocated, re-armed by the tail kernel of every iteration
+  unsigned long long* armed_item_counter() {
+    if (!item_counter.ptr) {
+      item_counter.ensure(1);
+      MCCBN_CUDA(cudaMemsetAsync(item_counter.ptr, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    return item_counter.ptr;
+  }
+
+  void run_finalize(int c, int chunks, long long n_items, int L_eff, bool per_obs_out,
                     int update_params = 0, bool fused = false) {
     cudaStream_t s = ctx->stream;
     FinArgs fa;
@@ -508,6 +531,7 @@ struct mccbn_problem {
       fa.dist = out_dist.ensure(N);
       fa.Tdiff = out_T.ensure((size_t)N * p);
       fa.L_eff_out = out_leff.ensure(N);
+      fa.log_w = out_logw.ensure(N);
     }
     fa.N = N;
     fa.chunks = chunks;
@@ -515,7 +539,6 @@ struct mccbn_problem {
     fa.p = p;
     fa.n_items = n_items;
     fa.L_eff = L_eff;
-    fa.uniform_fallback = uniform_fallback;
     if (fused) {
       if (!fuse_counter.ptr) {
         fuse_counter.ensure(1);
@@ -524,6 +547,14 @@ struct mccbn_problem {
       FusedTail ft;
       ft.stats = stats_of(c);
       ft.counter = fuse_counter.ptr;
+      ft.rearm = item_counter.ptr;
+      if (sharded()) {
+        xchg_seq[c] = ++ctx->xchg_seq;
+        ft.pv = peer_view(xchg_seq[c]);
+      } else {
+        ft.pv = peer_view(0);
+        ft.pv.world = 1;
+      }
       ft.pos = posets.ptr + c;
       ft.mdl = models.ptr + c;
       ft.scale = scales.ptr + c;
@@ -561,7 +592,8 @@ struct mccbn_problem {
       }
     }
     mstep_kernel<<<1, 64, 0, s>>>(stats_of(c), posets.ptr + c, models.ptr + c, scales.ptr + c,
-                                  trace.ptr ? trace_of(c) : nullptr, p + 2, trace_rows, PS(), update_params, pv);
+                                  trace.ptr ? trace_of(c) : nullptr, p + 2, trace_rows, PS(), update_params, pv,
+                                  item_counter.ptr);
     ctx->launches++;
     MCCBN_CUDA(cudaGetLastError());
     iter_host[c]++;

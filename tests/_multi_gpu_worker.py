@@ -20,8 +20,18 @@ def main():
     from mccbn_b200 import dist as mdist, synth
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # MCCBN_TEST_ONE_DEVICE=1: every rank on device 0 (a one-GPU box).  NCCL refuses two ranks on one device, so the
+    # plumbing (handle all-gather, result comparison) goes over gloo and only the peer-memory exchange is exercised.
+    one_device = os.environ.get("MCCBN_TEST_ONE_DEVICE") == "1"
+    if one_device:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if one_device:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    exchanges = ("peer",) if one_device else ("peer", "nccl")
+    tdev = "cpu" if one_device else "cuda"
     res = {}
     verbose = bool(os.environ.get("MCCBN_TEST_VERBOSE"))
 
@@ -48,7 +58,7 @@ def main():
                 pb.close()
                 ctx1.close()
                 say(sampling, "single-GPU reference done")
-            for exchange in ("peer", "nccl"):
+            for exchange in exchanges:
                 ctx = mdist.init_context(local, dist, exchange=exchange)
                 say(sampling, exchange, "context ready")
                 pb = mc.Problem(obs, ctx=ctx, obs_offset=lo, N_global=N)
@@ -56,7 +66,7 @@ def main():
                 pb.em_iterations(L, n_iter=4, sampling=sampling, neighborhood_dist=kdist, seed=3)
                 out = pb.read()
                 say(sampling, exchange, "EM done", out["eps"])
-                vec = torch.tensor(np.concatenate([out["lambda_"], [out["eps"], out["llhood"]]]), device="cuda")
+                vec = torch.tensor(np.concatenate([out["lambda_"], [out["eps"], out["llhood"]]]), device=tdev)
                 allv = [torch.zeros_like(vec) for _ in range(world)]
                 dist.all_gather(allv, vec)
                 same = all(bool(torch.equal(allv[0], v)) for v in allv)
@@ -80,13 +90,13 @@ def main():
         ctx1 = mc.Context(local)
         ref = mc.adaptive_simulated_annealing(start, ca["obs"], outdir=tempfile.mkdtemp() + "/", ctx=ctx1, **kw)
         ctx1.close()
-        for exchange in ("peer", "nccl"):
+        for exchange in exchanges:
             ctx = mdist.init_context(local, dist, exchange=exchange)
             out = tempfile.mkdtemp() + "/"
             r = mc.adaptive_simulated_annealing(start, ca["obs"], outdir=out, ctx=ctx, **kw)
             same = (np.array_equal(r["poset"], ref["poset"]) and np.array_equal(r["lambda_"], ref["lambda_"]) and
                     r["eps"] == ref["eps"] and r["llhood"] == ref["llhood"])
-            flag = torch.tensor([1.0 if same else 0.0], device="cuda")
+            flag = torch.tensor([1.0 if same else 0.0], device=tdev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             res[f"asa/{exchange}"] = {"identical_to_single_gpu_on_all_ranks": bool(flag.item() == 1.0),
                                       "rank0_wrote_files": (rank != 0) or os.path.exists(out + "params.txt")}
