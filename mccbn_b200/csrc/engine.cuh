@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: a no-op unless a profiler (nsys / ncu --nvtx) is attached
+
 #include "../../include/mccbn_b200.h"
 #include "device_types.cuh"
 #include "poset.hpp"
@@ -32,6 +34,26 @@ struct Error : std::runtime_error {
       throw ::mccbn::Error(MCCBN_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + \
                                                __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")"); \
   } while (0)
+
+// NVTX range (tracing): `nsys profile --trace=cuda,nvtx` / `ncu --nvtx --nvtx-include "mccbn/"` show
+// the phases of a call -- upload, EM batches, E-step enqueues, annealing steps -- on the timeline.  Domain "mccbn".
+struct NvtxRange {
+  static nvtxDomainHandle_t domain() {
+    static nvtxDomainHandle_t d = nvtxDomainCreateA("mccbn");
+    return d;
+  }
+  explicit NvtxRange(const char* name) {
+    nvtxEventAttributes_t a = {};
+    a.version = NVTX_VERSION;
+    a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+    a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+    a.message.ascii = name;
+    nvtxDomainRangePushEx(domain(), &a);
+  }
+  ~NvtxRange() { nvtxDomainRangePop(domain()); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 static const char* kMsgNotAcyclic = "Poset does not correspond to an acyclic graph";
 static const char* kMsgZeroWeight = "ERROR: all samples have weight 0. Consider increasing L";

@@ -10,6 +10,19 @@ namespace mccbn {
 static int count_compatible(mccbn_problem& pb, const Poset& P, int* num_incompatible_events = nullptr) {
   FlatPoset f;
   P.flatten(f);
+  if (!pb.host_bits.empty()) {
+    // moderate N: the same integer counts on the host from the bit-packed observations (a device round trip costs as
+    // much, and the annealer generates its look-ahead proposals while the device is busy fitting the current candidate)
+    int n_comp = 0, n_inc = 0;
+    for (const uint64_t g : pb.host_bits) {
+      int bad = 0;
+      for (uint64_t m = g; m; m &= m - 1) bad += __builtin_popcountll(f.parent_ev[ctz64(m)] & ~g);
+      n_inc += bad;
+      n_comp += bad == 0;
+    }
+    if (num_incompatible_events) *num_incompatible_events = n_inc;
+    return n_comp;
+  }
   DevPoset dp;
   fill_dev_poset(f, dp);
   cudaStream_t s = pb.ctx->stream;
@@ -52,9 +65,10 @@ static void initialize_candidate(mccbn_problem& pb, Candidate& c, float lambda_s
 }
 
 // scores candidates [0, n) concurrently; results are written back into the candidates (lambda, eps, llhood)
+// `while_device_busy` (optional): host work to do once the first EM iterations are enqueued, before waiting for them
 static void score_candidates(mccbn_problem& pb, std::vector<Candidate*>& cands, const std::vector<uint32_t>& eval_ids,
                              Scheme scheme, unsigned L, const EmControl& ctl, bool times_given, uint32_t seed,
-                             float lambda_s, int precision) {
+                             float lambda_s, int precision, const std::function<void()>& while_device_busy = nullptr) {
   // test seam (reachable only through the test-only entry point mccbn_test_asa_structural_score; mirrored by the
   // oracle's score_mode 1): a deterministic score of the poset instead of the MCEM fit, so that the move generator and
   // the annealing bookkeeping can be compared without Monte-Carlo noise.  Not part of the reference.
@@ -64,6 +78,7 @@ static void score_candidates(mccbn_problem& pb, std::vector<Candidate*>& cands, 
       count_compatible(pb, c->poset, &n_inc);
       c->llhood = -1000.0 - (double)n_inc + 3.0 * (double)c->poset.num_edges();
     }
+    if (while_device_busy) while_device_busy();
     return;
   }
   // Several GPUs (candidate-parallel annealing, pb.local_only): rank r fits the candidates q with q % world == r; the
@@ -86,7 +101,10 @@ static void score_candidates(mccbn_problem& pb, std::vector<Candidate*>& cands, 
     const int saved_world = pb.ctx->world;
     pb.ctx->world = 1;      // ... and its EM iterations stay local
     try {
-      if (!mine.empty()) score_candidates(pb, mine, mine_ids, scheme, L, ctl, times_given, seed, lambda_s, precision);
+      if (!mine.empty())
+        score_candidates(pb, mine, mine_ids, scheme, L, ctl, times_given, seed, lambda_s, precision, while_device_busy);
+      else if (while_device_busy)
+        while_device_busy();
     } catch (...) {
       pb.ctx->world = saved_world;
       throw;
@@ -121,7 +139,7 @@ static void score_candidates(mccbn_problem& pb, std::vector<Candidate*>& cands, 
       slots.push_back((int)q);
     }
     std::vector<EmResult> r = run_mcem_multi(pb, slots, scheme, L, ctl, times_given, seed, false, precision, nullptr,
-                                             nullptr);
+                                             nullptr, done == 0 ? while_device_busy : nullptr);
     for (size_t q = 0; q < n; ++q) {
       Candidate& c = *cands[done + q];
       c.lambda = r[q].lambda;
@@ -290,6 +308,7 @@ static void stream_lambda(std::ostream& os, const std::vector<double>& l) {
 static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& ctl_asa, unsigned L, Scheme scheme,
                                   const EmControl& ctl_em, bool times_given, uint32_t seed, float lambda_s,
                                   bool verbose, int batch) {
+  NvtxRange nvtx("simulated_annealing");
   const int p = pb.p;
   const float scaling_const = -std::log(2.0) / std::log(ctl_asa.acceptance_rate);  // :484
   int num_accept = 0;
@@ -343,14 +362,16 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
   const bool prefetch = pb.jit_mode_effective() != 0 && (double)pb.N * (double)L >= 5e6 && scheme != kPool;
   unsigned depth = 12;
   if (const char* e = std::getenv("MCCBN_ASA_LOOKAHEAD")) depth = (unsigned)std::max(1, std::min(64, std::atoi(e)));
-  while (iter < ctl_asa.max_iter) {
-    // 3.0 speculative batch: proposals for steps iter, iter+1, ... assuming every earlier one is rejected
-    const unsigned B = std::min<unsigned>(batch_now, ctl_asa.max_iter - iter);
-    const unsigned want = std::min<unsigned>(prefetch ? std::max(B, depth) : B, ctl_asa.max_iter - iter);
+  auto top_up = [&](unsigned want) {
     while (ahead.size() < want) {
       ahead.push_back(generate_proposal(pb, M, fraction_compatible, ctl_asa.compatible_fraction_factor, rng_prop, verbose));
       if (prefetch && ahead.back().valid) pb.prefetch_kernel(ahead.back().cand.poset, scheme, times_given);
     }
+  };
+  while (iter < ctl_asa.max_iter) {
+    // 3.0 speculative batch: proposals for steps iter, iter+1, ... assuming every earlier one is rejected
+    const unsigned B = std::min<unsigned>(batch_now, ctl_asa.max_iter - iter);
+    top_up(B);  // usually already there: generated while the device was fitting the previous batch (below)
     std::deque<Proposal>& props = ahead;  // the first B entries form the scoring batch
     std::vector<Candidate*> to_score;
     std::vector<uint32_t> ids;
@@ -379,7 +400,18 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
       ids.push_back(iter + b);
     }
     // 3.a score all distinct, un-memoised proposals of the batch concurrently
-    if (!to_score.empty()) score_candidates(pb, to_score, ids, scheme, L, ctl_em, times_given, seed, lambda_s, 0);
+    // ... and, once their first EM iterations are enqueued, generate the look-ahead proposals and start / collect the
+    // compilation of their kernels while the device is busy
+    const unsigned want = std::min<unsigned>(B + depth, ctl_asa.max_iter - iter);
+    const std::function<void()> look_ahead = [&] {
+      if (prefetch) top_up(want);
+    };
+    if (!to_score.empty()) {
+      NvtxRange nvtx_score("ASA: score candidate batch");
+      score_candidates(pb, to_score, ids, scheme, L, ctl_em, times_given, seed, lambda_s, 0, look_ahead);
+    } else {
+      look_ahead();
+    }
     // 3.b consume them in order with the reference's accept / reject rule (:436-468)
     bool accepted_any = false;
     unsigned n_consumed = B;

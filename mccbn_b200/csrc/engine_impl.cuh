@@ -41,6 +41,15 @@ struct CondLauncher {
   }
 };
 
+bool mccbn_problem::jit_ready(int c, int scheme, bool times_given) const {
+  if (!ctx->jit) return false;
+  if (scheme == kForward) return ctx->jit->has(flat[c], times_given, -1);
+  if (scheme == kPool) return false;
+  const int mode = scheme == kBackward ? kCondBackward
+                                       : (scheme == kBernoulli ? kCondBernoulli : (scheme == kAddRemove ? kCondAddRemove : kCondOtcbn));
+  return ctx->jit->has(flat[c], times_given, mode);
+}
+
 void mccbn_problem::prefetch_kernel(const Poset& P, int scheme, bool times_given) {
   if (jit_mode_effective() == 0) return;
   if (!ctx->jit) ctx->jit = new JitCache();
@@ -56,6 +65,7 @@ void mccbn_problem::prefetch_kernel(const Poset& P, int scheme, bool times_given
 
 void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neighborhood_dist, bool times_given,
                                       uint32_t seed, int update_params, bool per_obs_out, int precision) {
+  NvtxRange nvtx(scheme == kForward ? "E-step forward" : (scheme == kPool ? "E-step pool" : "E-step conditional"));
   if (p > kWideMaxP) throw Error(MCCBN_ERR_ARG, "the Philox E-step supports p <= 64");
   if (p > kFastMaxP && (scheme == kPool || scheme == kAddRemove || precision == 1))
     throw Error(MCCBN_ERR_ARG, "32 < p <= 64 is supported by the forward, backward and bernoulli schemes (fp32 path)");
@@ -295,7 +305,9 @@ struct EmRun {
 // applies the reference's batch-average / convergence rule per slot.  With one slot this is exactly MCEM_hcbn.
 static std::vector<EmResult> run_mcem_multi(mccbn_problem& pb, const std::vector<int>& slots, Scheme scheme,
                                             unsigned L, const EmControl& ctl, bool times_given, uint32_t seed,
-                                            bool verbose, int precision, double* trace_out, int* n_iter_out) {
+                                            bool verbose, int precision, double* trace_out, int* n_iter_out,
+                                            const std::function<void()>& while_device_busy = nullptr) {
+  NvtxRange nvtx("MCEM_hcbn");
   const int p = pb.p;
   if (ctl.update_step_size == 0) throw Error(MCCBN_ERR_ARG, "update_step_size must be >= 1");
   const int stride = p + 2;
@@ -320,6 +332,7 @@ static std::vector<EmResult> run_mcem_multi(mccbn_problem& pb, const std::vector
   }
   std::vector<std::vector<double>> rows(slots.size());
   std::vector<DevModel> dms(slots.size());
+  bool first_round = true;
   for (;;) {
     bool any = false;
     std::vector<unsigned> n_run(slots.size(), 0);
@@ -353,7 +366,15 @@ static std::vector<EmResult> run_mcem_multi(mccbn_problem& pb, const std::vector
       any = true;
     }
     if (!any) break;
-    MCCBN_CUDA(cudaStreamSynchronize(pb.ctx->stream));  // one host sync per round
+    if (first_round) {  // the device is busy with the first batch: the caller's host-side work overlaps with it
+      first_round = false;
+      if (while_device_busy) while_device_busy();
+    }
+    if (pb.ctx->jit) pb.ctx->jit->service();  // load specialised kernels whose background compilation has finished
+    {
+      NvtxRange nvtx_sync("EM batch: wait for the device");
+      MCCBN_CUDA(cudaStreamSynchronize(pb.ctx->stream));  // one host sync per round
+    }
     for (size_t r = 0; r < runs.size(); ++r) {
       EmRun& R = runs[r];
       if (R.done || n_run[r] == 0) continue;
@@ -517,21 +538,17 @@ static int team_want_locked() {
 }
 
 // devices a call with N observations would be sharded over (1 = no team); g_default_mu held
-// MCCBN_TEAM_OVERSUBSCRIBE=1 (tests on a one-GPU box): team members may share a device (member r runs on device
-// r mod #devices, with its own context, stream and mailbox) instead of the team being clamped to the device count.  The
-// result of a team call does not depend on the team size, so this is not a numerical knob.
-static bool team_oversubscribe() {
-  const char* e = std::getenv("MCCBN_TEAM_OVERSUBSCRIBE");
-  return e && std::strcmp(e, "1") == 0;
-}
 static int team_size_locked(int N) {
   int G = std::min(team_want_locked(), kMaxWorld);
   if (G > 1) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
     cudaGetLastError();
-    if (n == 0) return 1;
-    if (!team_oversubscribe()) G = std::min(G, n);
+    // one member per device: members that shared a device would deadlock -- a member's tail kernel spins until the
+    // other member has published its statistics, and any device-wide synchronising call of that other member's host
+    // thread (cudaMalloc, a module load) waits for the spinning kernel.  (Separate PROCESSES on one device are fine:
+    // tests/test_gpu_multi.py::test_sharded_em_two_ranks_one_gpu.)
+    G = std::min(G, n);
   }
   return (G <= 1 || N < G) ? 1 : G;
 }
@@ -550,11 +567,9 @@ static Team* team_for(int N) {
   Team* t = new Team();
   MCCBN_CUDA(cudaHostAlloc((void**)&t->boxes, sizeof(Mailbox) * G, cudaHostAllocPortable | cudaHostAllocMapped));
   std::memset(t->boxes, 0, sizeof(Mailbox) * G);
-  int n_dev = 1;
-  cudaGetDeviceCount(&n_dev);
   for (int r = 0; r < G; ++r) {
     mccbn_ctx* c = new mccbn_ctx();
-    ctx_init(c, r % std::max(1, n_dev));
+    ctx_init(c, r);
     c->rank = r;
     c->world = G;
     c->mailbox = &t->boxes[r];
@@ -1963,6 +1978,14 @@ static int asa_entry(mccbn_ctx* c, const int* poset, const int* obs, const doubl
   pb.N = N;
   pb.p = p;
   pb.upload(obs, times, weights);
+  if (N <= 65536) {  // moderate N: compatibility counts of the move generator on the host (engine_asa.cuh::count_compatible)
+    pb.host_bits.resize((size_t)N);
+    for (int i = 0; i < N; ++i) {
+      uint64_t w = 0;
+      for (int j = 0; j < p; ++j) w |= (uint64_t)(obs[(size_t)j * N + i] != 0) << j;
+      pb.host_bits[i] = w;
+    }
+  }
   pb.test_structural_score = structural_score;
   // several GPUs: candidate-parallel -- every rank is given ALL observations and fits its share of each speculative batch
   pb.local_only = c->world > 1;

@@ -276,6 +276,7 @@ struct JitCompiled {
 
 // compile only (no device needed): returns false + log on failure
 static bool jit_compile(NvrtcApi& rtc, const std::string& src, JitCompiled& out) {
+  NvtxRange nvtx("NVRTC compile specialised kernel");
   if (!rtc.load()) {
     out.log = "libnvrtc.so.12 could not be loaded";
     return false;
@@ -416,6 +417,9 @@ struct JitCache {
   struct Pending {
     std::future<JitCompiled> fut;
     std::string path;
+    const char* kname = nullptr;
+    bool forward = true;
+    int p = 0;
   };
   std::map<std::string, Pending> pending;  // compilations running on background threads
   int minb = jit_default_minb();
@@ -450,8 +454,13 @@ struct JitCache {
     return 2;  // cfg 5 backward: 2 / 3 / 4 resident blocks = 3.18 / 3.67 / 15.1 ms (4 blocks: 128 registers, spills in the loop)
   }
 
-  // start compiling on a background thread without waiting (the annealer announces the posets it is about to score)
-  void prefetch(const FlatPoset& f, bool times_given) { get(f, times_given, kBackground); }
+  // is the specialised kernel of this poset loaded (no side effects)
+  bool has(const FlatPoset& f, bool times_given, int cond_mode /* < 0: forward */) const {
+    const int mb = cond_mode >= 0 ? cond_minb() : (f.p > kFastMaxP ? std::min(minb, 2) : minb);
+    const std::string key = (cond_mode >= 0 ? "c" + std::to_string(cond_mode) : std::string()) + jit_key(f, times_given, mb);
+    auto it = kernels.find(key);
+    return it != kernels.end() && it->second.ok;
+  }
 
   template <typename SrcFn>
   JitKernel* get_kernel(const std::string& key, SrcFn make_src, const char* kname, bool forward, int p, Policy pol) {
@@ -484,6 +493,9 @@ struct JitCache {
         NvrtcApi* api = &rtc;  // the cache outlives its futures (~JitCache waits for them)
         Pending pd;
         pd.path = path;
+        pd.kname = kname;
+        pd.forward = forward;
+        pd.p = p;
         pd.fut = std::async(std::launch::async, [api, src, path] {
           JitCompiled out;
           if (jit_compile(*api, src, out)) jit_disk_write(path, out.cubin);
@@ -498,6 +510,26 @@ struct JitCache {
         if (have) jit_disk_write(path, cc.cubin);
       }
     }
+    return load(key, cc, have, kname, forward, p);
+  }
+
+  // load every specialised kernel whose background compilation has finished (called where the host is about to wait
+  // for the device anyway, so that the module load does not sit between two E-steps)
+  void service() {
+    for (auto it = pending.begin(); it != pending.end();) {
+      if (it->second.fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready) {
+        ++it;
+        continue;
+      }
+      JitCompiled cc = it->second.fut.get();
+      const std::string key = it->first;
+      const Pending pd = std::move(it->second);
+      it = pending.erase(it);
+      if (!kernels.count(key)) load(key, cc, !cc.cubin.empty(), pd.kname, pd.forward, pd.p);
+    }
+  }
+
+  JitKernel* load(const std::string& key, JitCompiled& cc, bool have, const char* kname, bool forward, int p) {
     JitKernel jk;
     if (have) {
       cudaError_t e = cudaLibraryLoadData(&jk.lib, cc.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);

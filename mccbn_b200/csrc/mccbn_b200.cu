@@ -182,6 +182,7 @@ struct mccbn_problem {
   // candidate-parallel annealing: every rank holds ALL observations and scores its share of the candidate posets, so the
   // EM iterations of this problem must not exchange statistics with the other ranks
   bool local_only = false;
+  std::vector<uint64_t> host_bits;  // annealer, moderate N: bit-packed observations on the host (compatibility counts)
   bool test_structural_score = false;  // set by mccbn_test_asa_structural_score only (engine_asa.cuh)
   bool sharded() const { return ctx->world > 1 && !local_only; }
   unsigned long long xchg_seq[kMaxCand] = {};  // exchange number of the candidate's pending reduce_push
@@ -208,6 +209,7 @@ struct mccbn_problem {
   // `ld`: leading dimension of the column-major host matrix `obs` (rows of the full matrix when obs points at a block of
   // rows of it, mccbn_em_options.obs_ld); 0 = N
   void upload(const int* obs, const double* t, const double* w, size_t ld = 0) {
+    NvtxRange nvtx("upload+pack observations");
     cudaStream_t s = ctx->stream;
     DevBuf<int> tmp;
     tmp.ensure((size_t)N * p);
@@ -302,6 +304,8 @@ struct mccbn_problem {
     return ctx->jit->get(f, times_given, jit_policy(mode, (double)N * (double)L));
   }
 
+  // is the specialised kernel that an E-step of candidate c would use loaded?
+  bool jit_ready(int c, int scheme, bool times_given) const;
   // start compiling the specialised kernel of a poset on a background thread (annealer look-ahead); never blocks
   void prefetch_kernel(const Poset& P, int scheme /* Scheme */, bool times_given);
 
@@ -409,7 +413,6 @@ struct mccbn_problem {
   // E-step, finalize, reduction, M-step -- is captured into a CUDA graph and replayed: everything that changes from
   // one iteration to the next (parameters, tables, the iteration field of the Philox key, the trace row) lives in
   // device memory.  Small problems are launch-bound: 29 -> 13 us per EM iteration on BASELINE config 1.
-  size_t jit_generation() const { return ctx->jit ? ctx->jit->kernels.size() + (size_t)ctx->jit->tick_loaded : 0; }
   struct IterGraph {
     cudaGraphExec_t exec = nullptr;
     std::string key;
@@ -423,6 +426,7 @@ struct mccbn_problem {
   }
   void enqueue_iterations(int c, int n, Scheme scheme, int L, unsigned neighborhood_dist, bool times_given,
                           uint32_t seed, int update_params, int precision) {
+    NvtxRange nvtx("enqueue EM iterations");
     static const bool enabled = [] {
       const char* e = std::getenv("MCCBN_GRAPHS");
       return !(e && std::strcmp(e, "0") == 0);
@@ -437,7 +441,7 @@ struct mccbn_problem {
         k << (int)scheme << ':' << L << ':' << neighborhood_dist << ':' << times_given << ':' << seed << ':' << update_params
           << ':' << precision << ':' << pool_resample << ':' << N << ':' << p << ':' << model_version[c] << ':' << eval_id[c]
           << ':' << trace_rows << ':' << device_cache().epoch_of_current_device() << ':' << (void*)s << ':' << ctx->jit_mode
-          << ':' << jit_generation();
+          << ':' << jit_ready(c, scheme, times_given);  // a finished background compilation is picked up
         return k.str();
       };
       const std::string key_now = graph_key();

@@ -48,8 +48,8 @@ def test_pool_from_supplied_times(oracle, p, K, times_given):
 
 def test_pool_resample_against_oracle_and_default_mode(oracle):
     """pool_resample = 1: per-observation E[d] and E[Z] over replicate seeds agree with the oracle (which resamples like
-    the reference); the log-likelihood part is bit-identical to the default mode for the same seed (the resampled rows
-    all carry the weight sum q / K); the resampled means are unbiased for the default mode's expectations."""
+    the reference); the log-likelihood part equals the default mode's for the same seed (the resampled rows all carry the
+    weight sum q / K); the resampled means are unbiased for the default mode's expectations."""
     c = synth.make_config(8, 12, eps=0.1, seed=17, density=0.3)
     L, n_rep = 128, 32
     kw = dict(sampling="pool")
@@ -62,8 +62,8 @@ def test_pool_resample_against_oracle_and_default_mode(oracle):
     def vec(r):
         return np.concatenate([r["w"] / L, r["dist"], r["Tdiff"].ravel(order="F")])
 
-    for a, b in zip(g1, g0):
-        assert np.array_equal(a["w"], b["w"])
+    for a, b in zip(g1, g0):  # same pool, same sum q (the two modes chunk the pool differently: fp32 partial sums)
+        np.testing.assert_allclose(a["w"], b["w"], rtol=5e-6)
     z, nu = replicate_z([vec(r) for r in g1], [vec(r) for r in o])
     joint_check(z, nu, "pool_resample vs oracle")
     # paired with the default mode on the same pools: mean difference ~ 0, and the resampling adds variance
@@ -80,8 +80,8 @@ def test_pool_resample_fixed_point(oracle):
     def pack(r):
         return np.concatenate([r["lambda_"], [r["eps"], r["llhood"]]])
 
-    g = [pack(mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], seed=s, pool_resample=True, **kw)) for s in range(1, 17)]
+    g = [pack(mc.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], seed=s, pool_resample=True, **kw)) for s in range(1, 33)]
     o = [pack(oracle.MCEM_hcbn(c["lambda0"], c["poset"], c["obs"], seed=100 + s, thrds=oracle.num_threads(), **kw))
-         for s in range(1, 17)]
+         for s in range(1, 33)]
     z, nu = replicate_z(g, o)
     joint_check(z, nu, "pool_resample fixed point")
