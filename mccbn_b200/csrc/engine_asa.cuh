@@ -139,7 +139,7 @@ static void score_candidates(mccbn_problem& pb, std::vector<Candidate*>& cands, 
       slots.push_back((int)q);
     }
     std::vector<EmResult> r = run_mcem_multi(pb, slots, scheme, L, ctl, times_given, seed, false, precision, nullptr,
-                                             nullptr, done == 0 ? while_device_busy : nullptr);
+                                             nullptr, while_device_busy);
     for (size_t q = 0; q < n; ++q) {
       Candidate& c = *cands[done + q];
       c.lambda = r[q].lambda;
@@ -403,8 +403,15 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
     // ... and, once their first EM iterations are enqueued, generate the look-ahead proposals and start / collect the
     // compilation of their kernels while the device is busy
     const unsigned want = std::min<unsigned>(B + depth, ctl_asa.max_iter - iter);
+    // (a slice per call: it runs once per EM round of the fit, between enqueueing ~20 iterations and waiting for them,
+    // and must not take longer than the device needs for those)
     const std::function<void()> look_ahead = [&] {
-      if (prefetch) top_up(want);
+      if (!prefetch) return;
+      const auto t0 = std::chrono::steady_clock::now();
+      while (ahead.size() < want) {
+        top_up((unsigned)ahead.size() + 1);
+        if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > 1.5) break;
+      }
     };
     if (!to_score.empty()) {
       NvtxRange nvtx_score("ASA: score candidate batch");

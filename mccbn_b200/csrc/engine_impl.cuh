@@ -366,11 +366,10 @@ static std::vector<EmResult> run_mcem_multi(mccbn_problem& pb, const std::vector
       any = true;
     }
     if (!any) break;
-    if (first_round) {  // the device is busy with the first batch: the caller's host-side work overlaps with it
-      first_round = false;
-      if (while_device_busy) while_device_busy();
-    }
-    if (pb.ctx->jit) pb.ctx->jit->service();  // load specialised kernels whose background compilation has finished
+    // the device is busy with the iterations just enqueued: a slice of the caller's host-side work overlaps with them
+    (void)first_round;
+    if (while_device_busy) while_device_busy();
+    if (pb.ctx->jit) pb.ctx->jit->service();  // collect finished background compilations
     {
       NvtxRange nvtx_sync("EM batch: wait for the device");
       MCCBN_CUDA(cudaStreamSynchronize(pb.ctx->stream));  // one host sync per round

@@ -422,6 +422,13 @@ struct JitCache {
     int p = 0;
   };
   std::map<std::string, Pending> pending;  // compilations running on background threads
+  struct Ready {
+    JitCompiled cc;
+    const char* kname = nullptr;
+    bool forward = true;
+    int p = 0;
+  };
+  std::map<std::string, Ready> ready;  // compiled (or read from disk) ahead of use, loaded when first requested
   int minb = jit_default_minb();
   uint64_t tick = 0;
   uint64_t tick_loaded = 0;  // modules loaded so far (captured CUDA graphs are re-captured when it changes)
@@ -471,6 +478,13 @@ struct JitCache {
     }
     JitCompiled cc;
     bool have = false;
+    auto rit = ready.find(key);
+    if (rit != ready.end()) {  // compiled ahead of use
+      if (pol == kBackground) return nullptr;  // a prefetch: nothing more to do
+      cc = std::move(rit->second.cc);
+      ready.erase(rit);
+      return load(key, cc, true, kname, forward, p);
+    }
     auto pit = pending.find(key);
     if (pit != pending.end()) {  // a background compilation of this kernel is under way
       if (pol != kCompileNow && pit->second.fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready)
@@ -483,13 +497,25 @@ struct JitCache {
       const std::string src = make_src();
       const std::string path = jit_cache_path(rtc, src);
       have = jit_disk_read(path, cc.cubin);
+      if (have && pol == kBackground) {  // a prefetch that hit the disk cache: keep the cubin, load on first use
+        Ready r;
+        r.cc = std::move(cc);
+        r.kname = kname;
+        r.forward = forward;
+        r.p = p;
+        if (ready.size() > 256) ready.clear();
+        ready.emplace(key, std::move(r));
+        return nullptr;
+      }
       if (!have && pol == kCachedOnly) {
         if (disk_misses.size() > 4096) disk_misses.clear();
         disk_misses.insert(key);
         return nullptr;
       }
       if (!have && pol == kBackground) {
-        if (!rtc.load() || pending.size() >= 64) return nullptr;
+        // at most (host threads - 2) compilations in flight: the thread that drives the device must stay responsive
+        static const size_t max_bg = (size_t)std::max(1, (int)std::thread::hardware_concurrency() - 2);
+        if (!rtc.load() || pending.size() >= std::min<size_t>(64, max_bg)) return nullptr;
         NvrtcApi* api = &rtc;  // the cache outlives its futures (~JitCache waits for them)
         Pending pd;
         pd.path = path;
@@ -513,23 +539,28 @@ struct JitCache {
     return load(key, cc, have, kname, forward, p);
   }
 
-  // load every specialised kernel whose background compilation has finished (called where the host is about to wait
-  // for the device anyway, so that the module load does not sit between two E-steps)
+  // collect the background compilations that have finished (cheap; the module itself is loaded when the kernel is first
+  // requested for a launch -- most look-ahead candidates of an annealing run are never scored)
   void service() {
     for (auto it = pending.begin(); it != pending.end();) {
       if (it->second.fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready) {
         ++it;
         continue;
       }
-      JitCompiled cc = it->second.fut.get();
-      const std::string key = it->first;
-      const Pending pd = std::move(it->second);
+      Ready r;
+      r.cc = it->second.fut.get();
+      r.kname = it->second.kname;
+      r.forward = it->second.forward;
+      r.p = it->second.p;
+      if (ready.size() > 256) ready.clear();
+      if (!r.cc.cubin.empty()) ready.emplace(it->first, std::move(r));
       it = pending.erase(it);
-      if (!kernels.count(key)) load(key, cc, !cc.cubin.empty(), pd.kname, pd.forward, pd.p);
     }
   }
 
   JitKernel* load(const std::string& key, JitCompiled& cc, bool have, const char* kname, bool forward, int p) {
+    NvtxRange nvtx("load specialised kernel module");
+    const auto t_load0 = std::chrono::steady_clock::now();
     JitKernel jk;
     if (have) {
       cudaError_t e = cudaLibraryLoadData(&jk.lib, cc.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
@@ -560,8 +591,10 @@ struct JitCache {
       std::fprintf(stderr, "mccbn_b200: NVRTC specialisation failed, using the generic kernel\n%s\n", cc.log.c_str());
     }
     if (std::getenv("MCCBN_JIT_VERBOSE"))
-      std::fprintf(stderr, "mccbn_b200: specialised kernel %s p=%d: %s in %.0f ms\n%s\n", kname, p,
-                   jk.ok ? "ready" : "FAILED", cc.compile_ms, cc.log.c_str());
+      std::fprintf(stderr, "mccbn_b200: specialised kernel %s p=%d: %s (compiled in %.0f ms, module loaded in %.2f ms)\n%s\n",
+                   kname, p, jk.ok ? "ready" : "FAILED", cc.compile_ms,
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_load0).count(),
+                   cc.log.c_str());
     evict_lru();
     ++tick_loaded;
     jk.last_use = ++tick;

@@ -30,7 +30,7 @@ namespace mccbn {
 
 constexpr int kPoolBlock = 128;  // observations per block
 constexpr int kPoolTile = 64;    // pool entries per shared-memory tile
-constexpr int kPoolFlush = 256;  // pool entries between two flushes of a thread's fp32 partial sums into its fp64 record
+constexpr int kPoolFlush = 512;  // pool entries between two flushes of a thread's fp32 partial sums into its fp64 record
 
 // Pool generation: entry k draws Z_j ~ Exp(lambda_j) and propagates T_j (sample_times, src/mcem_hcbn.cpp:184-213).
 // Output per entry: Tp[k][PMAX] the event times in ASCENDING order (padded with +inf), Mp[k][PMAX + 1] the prefix
