@@ -362,10 +362,14 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
   const bool prefetch = pb.jit_mode_effective() != 0 && (double)pb.N * (double)L >= 5e6 && scheme != kPool;
   unsigned depth = 12;
   if (const char* e = std::getenv("MCCBN_ASA_LOOKAHEAD")) depth = (unsigned)std::max(1, std::min(64, std::atoi(e)));
+  // kernels are compiled ahead only while proposals are being rejected: at high temperature nearly every move is
+  // accepted, the look-ahead is discarded each step and the compilations would be wasted host work
+  unsigned steps_since_accept = 0;
   auto top_up = [&](unsigned want) {
     while (ahead.size() < want) {
       ahead.push_back(generate_proposal(pb, M, fraction_compatible, ctl_asa.compatible_fraction_factor, rng_prop, verbose));
-      if (prefetch && ahead.back().valid) pb.prefetch_kernel(ahead.back().cand.poset, scheme, times_given);
+      if (prefetch && steps_since_accept >= 3 && ahead.back().valid)
+        pb.prefetch_kernel(ahead.back().cand.poset, scheme, times_given);
     }
   };
   while (iter < ctl_asa.max_iter) {
@@ -456,8 +460,10 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
         rng_prop = pr.rng_after;  // discard the speculation beyond this step
         accepted_any = true;
         n_consumed = b + 1;
+        steps_since_accept = 0;
         if (batch < 0) batch_now = std::max(batch_floor, std::min(batch_cap, b + 1u));
       }
+      if (!accept) ++steps_since_accept;
       if (llhood > llhood_ML) {  // :541-545
         llhood_ML = llhood;
         M_ML = M;

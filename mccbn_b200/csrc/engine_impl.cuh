@@ -133,8 +133,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
       // chunk over ball genotypes; keep >= ~256 samples per chunk
       const int per_geno = bp.reps;
       int genos_per_chunk = std::max(1, (256 + per_geno - 1) / per_geno);
-      const long long total_warps = (long long)ctx->sm_count * 16;
-      long long want = (total_warps * 24 + N - 1) / std::max(1, N);
+      const long long Ng = std::max<long long>(1, N_global > 0 ? N_global : N);  // chunking independent of the sharding
+      long long want = (want_items_global() / 4 + Ng - 1) / Ng;  // items of a few ball genotypes are cheap: coarser than the forward rule
       int max_chunks = std::max(1, bp.n_ball / genos_per_chunk);
       chunks = (int)std::max(1LL, std::min<long long>(want, max_chunks));
       chunk_len = (bp.n_ball + chunks - 1) / chunks;
@@ -205,7 +205,8 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     const PhiloxKey kts = make_key(seed, (uint32_t)iter, 4u);
     const int ggen = std::max(1, std::min((K + kFwdBlock - 1) / kFwdBlock, ctx->sm_count * 6));
     const int nb = (N + kPoolBlock - 1) / kPoolBlock;
-    long long want = ((long long)ctx->sm_count * 6 + nb - 1) / nb;
+    const long long nb_global = ((N_global > 0 ? N_global : N) + kPoolBlock - 1) / kPoolBlock;  // independent of the sharding
+    long long want = ((long long)ctx->sm_count * 6 * kShardHeadroom + nb_global - 1) / nb_global;
     chunks = (int)std::max(1LL, std::min<long long>(want, std::max(1, K / (4 * kPoolTile))));
     if (pool_resample) chunks = 1;  // the resampling sweep walks the cumulative weights of the whole pool
     chunk_len = ((K + chunks - 1) / chunks + kPoolTile - 1) / kPoolTile * kPoolTile;

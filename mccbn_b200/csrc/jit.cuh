@@ -17,7 +17,9 @@
 #include <thread>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/resource.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <chrono>
@@ -513,8 +515,8 @@ struct JitCache {
         return nullptr;
       }
       if (!have && pol == kBackground) {
-        // at most (host threads - 2) compilations in flight: the thread that drives the device must stay responsive
-        static const size_t max_bg = (size_t)std::max(1, (int)std::thread::hardware_concurrency() - 2);
+        // at most half of the host threads compile at once, at low priority: the thread that drives the device must stay responsive
+        static const size_t max_bg = (size_t)std::max(1, (int)std::thread::hardware_concurrency() / 2);
         if (!rtc.load() || pending.size() >= std::min<size_t>(64, max_bg)) return nullptr;
         NvrtcApi* api = &rtc;  // the cache outlives its futures (~JitCache waits for them)
         Pending pd;
@@ -523,6 +525,7 @@ struct JitCache {
         pd.forward = forward;
         pd.p = p;
         pd.fut = std::async(std::launch::async, [api, src, path] {
+          setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 10);  // this thread only (Linux: per-thread nice value)
           JitCompiled out;
           if (jit_compile(*api, src, out)) jit_disk_write(path, out.cubin);
           else out.cubin.clear();

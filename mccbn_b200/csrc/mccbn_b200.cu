@@ -386,16 +386,23 @@ struct mccbn_problem {
     MCCBN_CUDA(cudaGetLastError());
   }
 
-  // Chunking of the L samples of one observation over warps.  The partition depends only on (N, L, #SMs) -- not on the
-  // kernel that will run -- so that the generic and the specialised kernel write the same records; the GRID is one
-  // resident wave of the kernel that runs (`blocks_per_sm`; 0: the generic forward kernel's launch bounds), its warps
-  // claim the items dynamically.
+  // Chunking of the L samples of one observation over warps.  The partition fixes which samples share a per-lane fp32
+  // partial sum, i.e. the rounding of a record, so it must not depend on anything a caller may vary without expecting
+  // the result to change: it is a function of (L, GLOBAL number of observations, #SMs) only -- not of the kernel that
+  // runs (generic / specialised) and not of how the observations are sharded over ranks (kShardHeadroom: fine enough
+  // for up to 8 ranks to find ~24 items per warp).  Results are therefore identical, up to the fp64 summation order of
+  // the final statistic vector (~1e-15), for every --gpus N.  The GRID is one resident wave of the kernel that runs
+  // (`blocks_per_sm`; 0: the generic forward kernel's launch bounds); its warps claim the items dynamically.
+  static constexpr long long kShardHeadroom = 8;
+  long long want_items_global() const {
+    return (long long)ctx->sm_count * 4 * (kFwdBlock / 32) * 24 * kShardHeadroom;  // ~24 items per warp at 4 blocks/SM
+  }
   void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x, int blocks_per_sm = 0) const {
     const int warps_per_block = kFwdBlock / 32;
     if (blocks_per_sm <= 0) blocks_per_sm = p > kFastMaxP ? kFwdWideMinB : (p > MCCBN_FWD_BIGP - 4 ? MCCBN_FWD_MINB_BIG : 6);
     const int resident_blocks = ctx->sm_count * blocks_per_sm;  // blocks of 4 warps
-    const long long want_items = (long long)ctx->sm_count * 4 * warps_per_block * 24;  // ~24 items per warp at 4 blocks/SM
-    long long c = (want_items + N - 1) / std::max(1, N);
+    const long long Ng = std::max<long long>(1, N_global > 0 ? N_global : N);
+    long long c = (want_items_global() + Ng - 1) / Ng;
     long long cmax = std::max(1, L / 256);
     c = std::max(1LL, std::min(c, cmax));
     chunk_len = (int)(((L + c - 1) / c + 31) / 32 * 32);
