@@ -410,17 +410,16 @@ __device__ __forceinline__ void estep_conditional_body(const CondArgs& a, const 
       // natural-log scale of this record: true weights = exp(lscale) * relative weights
       out[4] = (mmax > (real)-1e29) ? (double)mmax * 0.693147180559945309417 + lscale_extra : -__longlong_as_double(0x7ff0000000000000LL) /* -inf */;
     }
-    double mine = 0.0, mine_hi = 0.0;  // lane k owns slots k and (p > 32) k + 32
+    double mine, mine_hi = 0.0;  // lane k owns slots k and (p > 32) k + 32
+    {
+      double v[32];
 #pragma unroll
-    for (int k = 0; k < PMAX; ++k) {
-      if (k < p) {
-        double v = (double)(acc[k] * s);
+      for (int k = 0; k < 32; ++k) v[k] = k < PMAX ? (double)(acc[k] * s) : 0.0;
+      mine = warp_transpose_sum(v, lane);
+      if constexpr (PMAX > 32) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == (k & 31)) {
-          if (k < 32) mine = v;
-          else mine_hi = v;
-        }
+        for (int k = 0; k < 32; ++k) v[k] = k + 32 < PMAX ? (double)(acc[k + 32] * s) : 0.0;
+        mine_hi = warp_transpose_sum(v, lane);
       }
     }
     if (lane < p) out[kStatHdr + lane] = mine;

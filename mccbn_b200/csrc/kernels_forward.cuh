@@ -154,6 +154,27 @@ __device__ __forceinline__ float4 lds128_f(uint32_t saddr) {
   return v;
 }
 
+// Warp reduction of a vector of per-lane partial sums: v[j] of every lane is summed over the 32 lanes, and lane l returns
+// the total of component l.  A butterfly transpose: at distance o = 16, 8, .. 1 a lane keeps the half of its components
+// that its bit o selects, sends the other half to lane ^ o and adds what it receives -- 31 exchanges for 32 components,
+// where 32 independent xor-reductions take 160 (an fp64 exchange is two SHFL: 62 instead of 320 per record; the record
+// epilogue is per (observation, chunk) item, which for short chunks -- L = 1000 gives 11 sample iterations per item --
+// was a quarter of the kernel).  Fixed exchange order: the result is deterministic and the same on every lane layout.
+__device__ __forceinline__ double warp_transpose_sum(double (&v)[32], const int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const double lo = v[i], hi = v[i + o];
+      const double send = up ? lo : hi;
+      const double keep = up ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+
 // max over the parents of node k (0 without parents): two unconditional loads (absent parents read the dummy
 // row, which holds 0); nodes with in-degree > 2 (warp-uniform test) read four more rows unconditionally, and only
 // in-degree > 6 falls back to a loop.
@@ -430,17 +451,16 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog&
       // natural-log scale of the record: true w = exp(scale) * w', scale = log(base) + dref * log(r)
       out[4] = mdl->log_base + (dref > 0 ? (double)dref * mdl->log_r : 0.0);
     }
-    double mine = 0.0, mine_hi = 0.0;  // lane k owns slots k and (p > 32) k + 32
+    double mine, mine_hi = 0.0;  // lane k owns slots k and (p > 32) k + 32
+    {
+      double v[32];
 #pragma unroll
-    for (int k = 0; k < PMAX; ++k) {
-      if (k < p) {
-        double v = (double)acc[k];
+      for (int k = 0; k < 32; ++k) v[k] = k < PMAX ? (double)acc[k] : 0.0;
+      mine = warp_transpose_sum(v, lane);
+      if constexpr (PMAX > 32) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == (k & 31)) {
-          if (k < 32) mine = v;
-          else mine_hi = v;
-        }
+        for (int k = 0; k < 32; ++k) v[k] = k + 32 < PMAX ? (double)acc[k + 32] : 0.0;
+        mine_hi = warp_transpose_sum(v, lane);
       }
     }
     // acc holds sum w' e_k: the waiting time is Z_k = e_k c_k (c_k = -ln2/lambda_k in fp32, -1/lambda_k in fp64)

@@ -62,8 +62,10 @@ def test_pool_resample_against_oracle_and_default_mode(oracle):
     def vec(r):
         return np.concatenate([r["w"] / L, r["dist"], r["Tdiff"].ravel(order="F")])
 
-    for a, b in zip(g1, g0):  # same pool, same sum q (the two modes chunk the pool differently: fp32 partial sums)
-        np.testing.assert_allclose(a["w"], b["w"], rtol=5e-6)
+    # same pool, same sum q.  The two modes chunk the pool differently and each thread adds <= kPoolFlush = 512 relative
+    # weights in fp32 before it flushes to its fp64 record: worst case 512 * 2^-24 = 3e-5 relative, typically ~1e-6
+    for a, b in zip(g1, g0):
+        np.testing.assert_allclose(a["w"], b["w"], rtol=4e-5)
     z, nu = replicate_z([vec(r) for r in g1], [vec(r) for r in o])
     joint_check(z, nu, "pool_resample vs oracle")
     # paired with the default mode on the same pools: mean difference ~ 0, and the resampling adds variance
