@@ -206,7 +206,7 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
     const int ggen = std::max(1, std::min((K + kFwdBlock - 1) / kFwdBlock, ctx->sm_count * 6));
     const int nb = (N + kPoolBlock - 1) / kPoolBlock;
     const long long nb_global = ((N_global > 0 ? N_global : N) + kPoolBlock - 1) / kPoolBlock;  // independent of the sharding
-    long long want = ((long long)ctx->sm_count * 6 * kShardHeadroom + nb_global - 1) / nb_global;
+    long long want = ((long long)ctx->sm_count * 6 * kShardRanks + nb_global - 1) / nb_global;
     chunks = (int)std::max(1LL, std::min<long long>(want, std::max(1, K / (4 * kPoolTile))));
     if (pool_resample) chunks = 1;  // the resampling sweep walks the cumulative weights of the whole pool
     chunk_len = ((K + chunks - 1) / chunks + kPoolTile - 1) / kPoolTile * kPoolTile;

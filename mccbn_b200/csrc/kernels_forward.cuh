@@ -278,20 +278,24 @@ __device__ __forceinline__ void sample_forward(const Prog& pg, const uint32_t tc
 // observed genotype word (event-id bit order) -> topological-position bit order
 template <int PMAX, typename Prog>
 __device__ __forceinline__ typename Prog::word_t to_topo_bits(const Prog& pg, const uint64_t yw) {
-  typename Prog::word_t yt = 0;
+  typedef typename Prog::word_t word_t;
+  word_t yt = 0;
+  const word_t y = (word_t)yw;  // p <= 32: 32-bit shifts
 #pragma unroll
   for (int k = 0; k < PMAX; ++k)
-    if (k < pg.p) yt |= (typename Prog::word_t)((yw >> pg.ev[k]) & 1ull) << k;
+    if (k < pg.p) yt |= ((y >> pg.ev[k]) & (word_t)1) << k;
   return yt;
 }
 
 // the same in the bit order of the forward samplers' X: node k (topological position) -> bit p - 1 - k
 template <int PMAX, typename Prog>
 __device__ __forceinline__ typename Prog::word_t to_topo_bits_rev(const Prog& pg, const uint64_t yw) {
-  typename Prog::word_t yt = 0;
+  typedef typename Prog::word_t word_t;
+  word_t yt = 0;
+  const word_t y = (word_t)yw;  // p <= 32: events 0..31 live in the low word -- 32-bit shifts
 #pragma unroll
   for (int k = 0; k < PMAX; ++k)
-    if (k < pg.p) yt |= (typename Prog::word_t)((yw >> pg.ev[k]) & 1ull) << (pg.p - 1 - k);
+    if (k < pg.p) yt |= ((y >> pg.ev[k]) & (word_t)1) << (pg.p - 1 - k);
   return yt;
 }
 

@@ -386,16 +386,24 @@ struct mccbn_problem {
     MCCBN_CUDA(cudaGetLastError());
   }
 
-  // Chunking of the L samples of one observation over warps.  The partition fixes which samples share a per-lane fp32
-  // partial sum, i.e. the rounding of a record, so it must not depend on anything a caller may vary without expecting
-  // the result to change: it is a function of (L, GLOBAL number of observations, #SMs) only -- not of the kernel that
-  // runs (generic / specialised) and not of how the observations are sharded over ranks (kShardHeadroom: fine enough
-  // for up to 8 ranks to find ~24 items per warp).  Results are therefore identical, up to the fp64 summation order of
-  // the final statistic vector (~1e-15), for every --gpus N.  The GRID is one resident wave of the kernel that runs
+  // Chunking of the L samples of one observation into records (one warp per record).  The partition fixes which samples
+  // share a per-lane fp32 partial sum, i.e. the rounding of a record, so it must not depend on anything a caller may
+  // vary without expecting the result to change: it is a function of (L, GLOBAL number of observations, #SMs) only --
+  // not of the kernel that runs (generic / specialised) and not of how the observations are sharded over ranks.
+  // Results are therefore identical, up to the fp64 summation order of the final statistic vector (~1e-15), for every
+  // --gpus N.  Every record costs an epilogue (fp64 butterfly reduction, ~500 instructions) and restarts the running
+  // reference distance, so records are as long as load balance allows (measured on B200, r2h: cfg 3 with 1 / 2 / 3 / 5 /
+  // 8 / 12 records per observation = 19.67 / 19.71 / 19.82 / 20.09 / 20.53 / 21.06 ms; cfg 4, L = 1000: 1 / 2 / 3 = 0.184 /
+  // 0.198 / 0.210 ms):
+  //   * the kernel is issue-bound, so when a warp runs out of items the other warps of its scheduler speed up: balance
+  //     is a matter of items per SCHEDULER, not per warp -- 16 per scheduler on each of up to 8 ranks (kShardRanks) keeps
+  //     the quantisation loss at a few per cent;
+  //   * a record is at least 1024 samples (32 sample iterations: the epilogue stays below ~5 % of it).
+  // BASELINE configs 1-4 get one record per observation.  The GRID is one resident wave of the kernel that runs
   // (`blocks_per_sm`; 0: the generic forward kernel's launch bounds); its warps claim the items dynamically.
-  static constexpr long long kShardHeadroom = 8;
+  static constexpr long long kShardRanks = 8;
   long long want_items_global() const {
-    return (long long)ctx->sm_count * 4 * (kFwdBlock / 32) * 24 * kShardHeadroom;  // ~24 items per warp at 4 blocks/SM
+    return (long long)ctx->sm_count * 4 /* schedulers */ * 16 * kShardRanks;
   }
   void choose_chunks(int L, int& chunks, int& chunk_len, int& grid_x, int blocks_per_sm = 0) const {
     const int warps_per_block = kFwdBlock / 32;
@@ -403,8 +411,11 @@ struct mccbn_problem {
     const int resident_blocks = ctx->sm_count * blocks_per_sm;  // blocks of 4 warps
     const long long Ng = std::max<long long>(1, N_global > 0 ? N_global : N);
     long long c = (want_items_global() + Ng - 1) / Ng;
-    long long cmax = std::max(1, L / 256);
+    long long cmax = std::max(1, L / 1024);
     c = std::max(1LL, std::min(c, cmax));
+#ifdef MCCBN_DIAG_BUILD  // tools/ profiling builds only
+    if (const char* e = std::getenv("MCCBN_DIAG_CHUNKS")) c = std::max(1LL, std::min<long long>(std::atoll(e), std::max(1, L / 32)));
+#endif
     chunk_len = (int)(((L + c - 1) / c + 31) / 32 * 32);
     chunks = (L + chunk_len - 1) / chunk_len;
     long long items = (long long)N * chunks;
