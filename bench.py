@@ -259,7 +259,7 @@ def run_ours(args):
     def e2e_call(seed):
         try:
             mc.obs_loglikelihood(obs, cfg["poset"], cfg["lambda0"], 0.1, L=L, sampling=sampling, seed=seed, ctx=ctx,
-                                 obs_offset=lo)
+                                 obs_offset=lo, N_global=N)
         except mc.MccbnError as e:  # the reference's "all samples have weight 0" abort (see run_note above)
             if e.code != 2:
                 raise
@@ -326,8 +326,21 @@ def run_ours(args):
                     continue
                 try:
                     other[name] = time_other_workload(torch, mc, ctx, stream, flush, name, peak, sm_hz, n_sm, peaks)
+                    if CONFIGS[name][4] == "forward" and not other[name]["specialised_kernel"]:
+                        # 1e7 samples per E-step is below the default policy's compile threshold: the number above is the
+                        # generic kernel's; the specialised kernel's (mccbn_set_jit(1), what a long fit would reach) beside it
+                        mc.set_jit(1, ctx=ctx)
+                        try:
+                            other[name + "_specialised"] = time_other_workload(torch, mc, ctx, stream, flush, name, peak,
+                                                                               sm_hz, n_sm, peaks)
+                        finally:
+                            mc.set_jit(-1, ctx=ctx)
                 except Exception as e:  # a side measurement must never take the headline down
                     other[name] = {"error": str(e)[:200]}
+            try:
+                other["cfg4_asa"] = time_asa(mc, ctx)
+            except Exception as e:
+                other["cfg4_asa"] = {"error": str(e)[:200]}
             line["config"]["other_workloads"] = other
             if sampling == "forward":
                 try:
@@ -445,6 +458,25 @@ def time_other_workload(torch, mc, ctx, stream, flush, name, philox_peak, sm_hz,
          "roofline": workload_roofline(name, cfg, p, N, L, sampling, ms, philox_peak, sm_hz, n_sm, peaks)}
     pb.close()
     return r
+
+
+def time_asa(mc, ctx, steps=100):
+    """BASELINE config 4 end to end through the reference-facing call: adaptive.simulated.annealing, p = 20, N = 10,000,
+    L = 1,000, max.iter.asa = 100 (host buffers in, files and the fitted model out; every step is one candidate MCEM fit of
+    up to 100 EM iterations, scored speculatively in batches).  Wall clock of the whole call."""
+    import tempfile
+    cfg, p, N, L, sampling, desc = make_problem("cfg4")
+    outdir = tempfile.mkdtemp() + "/"
+    ctx.kernel_launches(reset=True)
+    ctx.jit_launches(reset=True)
+    t0 = time.perf_counter()
+    r = mc.adaptive_simulated_annealing(cfg["poset"], cfg["obs"], L=L, max_iter=100, update_step_size=20,
+                                        max_iter_asa=steps, outdir=outdir, seed=10, ctx=ctx)
+    dt = time.perf_counter() - t0
+    return {"workload": "cfg4: adaptive.simulated.annealing p=20 N=10,000 L=1,000 max.iter.asa=100", "seconds": dt,
+            "candidate_fits_per_s": steps / dt, "llhood": float(r["llhood"]), "gpu_launches": int(ctx.kernel_launches()),
+            "gpu_launches_specialised": int(ctx.jit_launches()),
+            "call": "mccbn_adaptive_simulated_annealing (host buffers, default JIT policy and batch size)"}
 
 
 def time_fp64_mode(torch, mc, ctx, stream, cfg, obs, p, N, L, steps=2):

@@ -160,8 +160,8 @@ def MCEM_hcbn(lambda_, poset, obs, lambda_s=1.0, L=None, eps=None, sampling="for
 
 
 def obs_loglikelihood(obs, poset, lambda_, eps, weights=None, times=None, L=None, sampling="forward",
-                      neighborhood_dist=1, lambda_s=1.0, thrds=1, seed=None, ctx=None, obs_offset=0, precision=0,
-                      stream_id=0, pool_resample=False):
+                      neighborhood_dist=1, lambda_s=1.0, thrds=1, seed=None, ctx=None, obs_offset=0, N_global=0,
+                      precision=0, stream_id=0, pool_resample=False):
     """obs.loglikelihood (R/loglikelihood.R:25-57) -> `_obs_log_likelihood` (src/mcem_hcbn.cpp:762-797)."""
     sampling = _match_sampling(sampling)
     obs, poset, lam = i32(obs), i32(poset), f64(lambda_)
@@ -179,7 +179,8 @@ def obs_loglikelihood(obs, poset, lambda_, eps, weights=None, times=None, L=None
     if seed is None:
         seed = int(np.random.randint(1, 30001))
     out = C.c_double(0)
-    opt = _options(obs_offset=obs_offset, precision=precision, stream_id=stream_id, pool_resample=int(pool_resample))
+    opt = _options(obs_offset=obs_offset, N_global=N_global, precision=precision, stream_id=stream_id,
+                   pool_resample=int(pool_resample))
     e = ErrBuf()
     e.check(capi.lib().mccbn_obs_log_likelihood(
         _ctx(ctx), ptr(obs), ptr(poset), ptr(lam), C.c_double(eps), ptr(wt), ptr(t), C.c_uint(int(L)),
@@ -189,7 +190,7 @@ def obs_loglikelihood(obs, poset, lambda_, eps, weights=None, times=None, L=None
 
 
 def importance_weight(genotype, L, poset, lambda_, eps, time=None, sampling="forward", neighborhood_dist=1,
-                      lambda_s=1.0, thrds=1, seed=None, ctx=None, obs_offset=0, precision=0, stream_id=0,
+                      lambda_s=1.0, thrds=1, seed=None, ctx=None, obs_offset=0, N_global=0, precision=0, stream_id=0,
                       pool_resample=False):
     """importance.weight (R/mcem_hcbn.R:138-195): matrix input -> `_importance_weight` (src/mcem_hcbn.cpp:914-1010),
     vector input -> `_importance_weight_genotype` (:866-912)."""
@@ -199,7 +200,8 @@ def importance_weight(genotype, L, poset, lambda_, eps, time=None, sampling="for
     g = np.asarray(genotype)
     if seed is None:
         seed = int(np.random.randint(1, 30001))
-    opt = _options(obs_offset=obs_offset, precision=precision, stream_id=stream_id, pool_resample=int(pool_resample))
+    opt = _options(obs_offset=obs_offset, N_global=N_global, precision=precision, stream_id=stream_id,
+                   pool_resample=int(pool_resample))
     e = ErrBuf()
     if g.ndim == 2:
         obs = i32(g)

@@ -227,4 +227,32 @@ struct mccbn_ctx {
   unsigned long long xchg_seq = 0;
   mccbn::JitCache* jit = nullptr;  // poset-specialised kernels (jit.cuh)
   int jit_mode = -1;               // -1 auto (large problems only), 0 off, 1 always
+  // Pinned staging ring for the small host -> device parameter blocks (poset + model of a candidate): copies from it
+  // are truly asynchronous, so set_model does not have to drain the stream before its stack objects go out of scope.
+  // A slot is reused only after the event recorded behind its copies has completed.
+  static constexpr int kStageSlots = 32;
+  static constexpr size_t kStageBytes = 8192;
+  unsigned char* stage = nullptr;
+  cudaEvent_t stage_ev[kStageSlots] = {};
+  int stage_next = 0;
+  unsigned char* stage_slot(int& slot) {
+    if (!stage) {
+      if (cudaHostAlloc((void**)&stage, kStageSlots * kStageBytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        stage = nullptr;
+        return nullptr;
+      }
+      for (int i = 0; i < kStageSlots; ++i) cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming);
+    }
+    slot = stage_next;
+    stage_next = (stage_next + 1) % kStageSlots;
+    cudaEventSynchronize(stage_ev[slot]);  // completed long ago unless 32 parameter uploads are in flight
+    return stage + (size_t)slot * kStageBytes;
+  }
+  void stage_release() {
+    if (!stage) return;
+    for (int i = 0; i < kStageSlots; ++i) cudaEventDestroy(stage_ev[i]);
+    cudaFreeHost(stage);
+    stage = nullptr;
+  }
 };

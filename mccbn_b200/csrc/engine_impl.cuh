@@ -701,6 +701,7 @@ void mccbn_ctx_destroy(mccbn_ctx* c) {
   if (c->mailbox && !c->mailbox_host) cudaFree(c->mailbox);
   if (c->comm) c->nccl.CommDestroy(c->comm);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  c->stage_release();
   delete c;
 }
 
@@ -841,6 +842,9 @@ int mccbn_problem_create(mccbn_ctx* c, const int* obs, const double* times, cons
   pb->N_global = N_global > 0 ? N_global : N;
   try {
     pb->upload(obs, times, weights);
+    MCCBN_CUDA(cudaStreamSynchronize(c->stream));  // the caller's buffers are free to go when this entry returns
+    pb->upload_inflight = false;
+    pb->release_upload_staging();
   } catch (...) {
     delete pb;
     throw;

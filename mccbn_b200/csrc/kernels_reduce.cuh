@@ -336,6 +336,10 @@ __global__ void __launch_bounds__(kFinBlock) finalize_mstep_kernel(const FinArgs
 
 // ---- indexing kernels ---------------------------------------------------------------------------------------
 
+__global__ void fill_kernel(double* __restrict__ v, int n, double x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = x;
+}
+
 // R's N x p int32 column-major observation matrix -> one 64-bit word per observation (bit j = event j)
 __global__ void pack_obs_kernel(const int* __restrict__ obs, uint64_t* __restrict__ bits, int N, int p) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {

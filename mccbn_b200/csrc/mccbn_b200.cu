@@ -208,10 +208,17 @@ struct mccbn_problem {
 
   // `ld`: leading dimension of the column-major host matrix `obs` (rows of the full matrix when obs points at a block of
   // rows of it, mccbn_em_options.obs_ld); 0 = N
+  DevBuf<int> obs_unpacked;
+  bool upload_inflight = false;
+  void release_upload_staging() { obs_unpacked.release(); }  // only after the stream has been drained
   void upload(const int* obs, const double* t, const double* w, size_t ld = 0) {
     NvtxRange nvtx("upload+pack observations");
     cudaStream_t s = ctx->stream;
-    DevBuf<int> tmp;
+    // the unpacked matrix stays allocated until the problem is destroyed (or release_upload_staging after a sync): its
+    // block must not return to the per-device cache -- which other contexts allocate from -- while the copy and the
+    // pack kernel are in flight
+    upload_inflight = true;
+    DevBuf<int>& tmp = obs_unpacked;
     tmp.ensure((size_t)N * p);
     if (ld == 0 || ld == (size_t)N)
       MCCBN_CUDA(cudaMemcpyAsync(tmp.ptr, obs, sizeof(int) * (size_t)N * p, cudaMemcpyHostToDevice, s));
@@ -223,19 +230,17 @@ struct mccbn_problem {
     ctx->launches++;
     times.ensure(N);
     weights.ensure(N);
-    std::vector<double> ones;
-    if (!w) {
-      ones.assign(N, 1.0);
-      w = ones.data();
+    // caller-owned buffers stay valid until the entry that called upload() returns, and every entry drains the stream
+    // before it returns: no sync here, the E-step is enqueued while the observations are still in flight.  Absent
+    // vectors (times: 0, weights: 1) are filled on the device.
+    if (t) MCCBN_CUDA(cudaMemcpyAsync(times.ptr, t, sizeof(double) * N, cudaMemcpyHostToDevice, s));
+    else MCCBN_CUDA(cudaMemsetAsync(times.ptr, 0, sizeof(double) * N, s));
+    if (w) {
+      MCCBN_CUDA(cudaMemcpyAsync(weights.ptr, w, sizeof(double) * N, cudaMemcpyHostToDevice, s));
+    } else {
+      fill_kernel<<<std::min(1024, (N + 255) / 256), 256, 0, s>>>(weights.ptr, N, 1.0);
+      ctx->launches++;
     }
-    std::vector<double> zeros;
-    if (!t) {
-      zeros.assign(N, 0.0);
-      t = zeros.data();
-    }
-    MCCBN_CUDA(cudaMemcpyAsync(times.ptr, t, sizeof(double) * N, cudaMemcpyHostToDevice, s));
-    MCCBN_CUDA(cudaMemcpyAsync(weights.ptr, w, sizeof(double) * N, cudaMemcpyHostToDevice, s));
-    MCCBN_CUDA(cudaStreamSynchronize(s));  // host staging buffers go out of scope
     posets.ensure(kMaxCand);
     models.ensure(kMaxCand);
     scales.ensure(kMaxCand);
@@ -258,9 +263,19 @@ struct mccbn_problem {
     dm.eps = eps;
     dm.lambda_s = (double)lambda_s;
     dm.max_lambda = (double)max_lambda;
-    MCCBN_CUDA(cudaMemcpyAsync(posets.ptr + c, &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
-    MCCBN_CUDA(cudaMemcpyAsync(models.ptr + c, &dm, sizeof(dm), cudaMemcpyHostToDevice, s));
-    MCCBN_CUDA(cudaStreamSynchronize(s));  // dp/dm are stack objects
+    static_assert(sizeof(DevPoset) + sizeof(DevModel) <= mccbn_ctx::kStageBytes, "staging slot too small");
+    int slot = 0;
+    if (unsigned char* st = ctx->stage_slot(slot)) {  // pinned staging: asynchronous, no drain of the stream
+      std::memcpy(st, &dp, sizeof(dp));
+      std::memcpy(st + sizeof(dp), &dm, sizeof(dm));
+      MCCBN_CUDA(cudaMemcpyAsync(posets.ptr + c, st, sizeof(dp), cudaMemcpyHostToDevice, s));
+      MCCBN_CUDA(cudaMemcpyAsync(models.ptr + c, st + sizeof(dp), sizeof(dm), cudaMemcpyHostToDevice, s));
+      MCCBN_CUDA(cudaEventRecord(ctx->stage_ev[slot], s));
+    } else {
+      MCCBN_CUDA(cudaMemcpyAsync(posets.ptr + c, &dp, sizeof(dp), cudaMemcpyHostToDevice, s));
+      MCCBN_CUDA(cudaMemcpyAsync(models.ptr + c, &dm, sizeof(dm), cudaMemcpyHostToDevice, s));
+      MCCBN_CUDA(cudaStreamSynchronize(s));  // dp/dm are stack objects
+    }
     iter_host[c] = 0;
     model_version[c]++;
     prepare_kernel<<<1, 128, 0, s>>>(posets.ptr + c, models.ptr + c, scales.ptr + c);
@@ -439,6 +454,9 @@ struct mccbn_problem {
   IterGraph iter_graph[kMaxCand];
   unsigned model_version[kMaxCand] = {};
   ~mccbn_problem() {
+    // uploads are asynchronous: nothing may still read the caller's buffers (or the staging block that goes back to the
+    // device cache with this object) when the entry that owns this problem returns -- on the error path either
+    if (upload_inflight && ctx) cudaStreamSynchronize(ctx->stream);
     for (IterGraph& g : iter_graph)
       if (g.exec) cudaGraphExecDestroy(g.exec);
   }
