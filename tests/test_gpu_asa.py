@@ -8,6 +8,7 @@ import pytest
 
 import mccbn_b200 as mc
 from mccbn_b200 import synth
+from stat_criteria import joint_check
 
 pytestmark = pytest.mark.gpu
 
@@ -113,6 +114,6 @@ def test_asa_matches_oracle_in_distribution(oracle, tmp_path, mode, n_seeds, kw)
                 synth.topological_sort(r["poset"])
                 assert np.array_equal(synth.transitive_reduction(r["poset"]), r["poset"])
         z = _two_sample_z(g, o)
-        assert np.abs(z).max() < 4.0, (z, np.mean(g, axis=0), np.mean(o, axis=0))
+        joint_check(z, 2 * n_seeds - 2, f"ASA {mode}")
     finally:
         os.environ.pop("MCCBN_ASA_BATCH", None)

@@ -6,6 +6,7 @@ import pytest
 import exact
 import mccbn_b200 as mc
 from mccbn_b200 import synth
+from stat_criteria import joint_check
 
 pytestmark = pytest.mark.gpu
 
@@ -19,7 +20,7 @@ def test_single_event_single_observation():
         px = lam[0] / (lam[0] + 1.0)
         want = (0.9 * px + 0.1 * (1 - px)) if y else (0.9 * (1 - px) + 0.1 * px)
         est = np.array([mc.importance_weight(obs, 4096, poset, lam, 0.1, seed=s)["w"][0] / 4096 for s in range(1, 17)])
-        assert abs(est.mean() - want) < 4.5 * est.std(ddof=1) / 4 + 1e-12
+        joint_check(np.array([(est.mean() - want) / (est.std(ddof=1) / 4 + 1e-300)]), 15, "p = 1")
 
 
 @pytest.mark.parametrize("L", [1, 5, 31, 32, 33, 100])
@@ -33,7 +34,7 @@ def test_L_below_and_around_a_warp(oracle, L):
     o = np.array([oracle.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.1, seed=s)["w"] / L
                   for s in range(101, 141)])
     se = np.sqrt(g.var(axis=0, ddof=1) / 40 + o.var(axis=0, ddof=1) / 40)
-    assert np.abs((g.mean(axis=0) - o.mean(axis=0)) / np.maximum(se, 1e-300)).max() < 4.5
+    joint_check((g.mean(axis=0) - o.mean(axis=0)) / np.maximum(se, 1e-300), 78, f"L = {L}")
 
 
 def test_ragged_N_and_duplicates_and_weights(oracle):
@@ -68,4 +69,4 @@ def test_all_zero_and_all_one_observations():
     want = np.array([exact.obs_prob_and_dist(px, exact.mask_of(o), 0.1, 8)[0] for o in obs])
     est = np.array([mc.importance_weight(obs, 8192, c["poset"], c["lambdas"], 0.1, seed=s)["w"] / 8192 for s in range(1, 25)])
     z = (est.mean(axis=0) - want) / (est.std(axis=0, ddof=1) / np.sqrt(24))
-    assert np.abs(z).max() < 4.5
+    joint_check(z, 23, "all-zero / all-one observations")

@@ -6,6 +6,9 @@ import pytest
 import exact
 import mccbn_b200 as mc
 from mccbn_b200 import synth
+from stat_criteria import joint_check
+
+NU_NORMAL = 10 ** 6  # large-sample z statistics (N >= 3000 draws): the joint rule of stat_criteria with normal tails
 
 pytestmark = pytest.mark.gpu
 
@@ -30,7 +33,7 @@ def test_sample_times_structure_and_marginals():
     np.testing.assert_allclose(r["mutation_times"], _consistent(c["poset"], c["lambdas"], r), rtol=1e-14)
     # waiting times are Exp(lambda_j): mean 1/lambda, variance 1/lambda^2
     z = (r["Tdiff"].mean(axis=0) - 1 / c["lambdas"]) / (1 / c["lambdas"] / np.sqrt(N))
-    assert np.abs(z).max() < 4.5, z
+    joint_check(z, NU_NORMAL, "Exp(lambda) means")
     # reproducible, seed-dependent
     assert np.array_equal(mc.sample_times(100, c["poset"], c["lambdas"], seed=5)["Tdiff"], r["Tdiff"][:100])
     assert not np.array_equal(mc.sample_times(100, c["poset"], c["lambdas"], seed=6)["Tdiff"], r["Tdiff"][:100])
@@ -50,13 +53,13 @@ def test_sample_genotypes_matches_exact_distribution(oracle):
     codes = (r["samples"] << np.arange(6)).sum(axis=1)
     freq = np.bincount(codes, minlength=64) / N
     se = np.sqrt(np.maximum(px * (1 - px), 1e-12) / N)
-    assert np.abs((freq - px) / se)[px > 1e-4].max() < 4.5
+    joint_check(((freq - px) / se)[px > 1e-4], NU_NORMAL, "genotype frequencies vs K2")
     assert freq[px == 0].sum() == 0
     # same marginals as the oracle's mt19937 draw
     o_samples, _, _ = oracle.sample_genotypes(N, c["poset"], c["lambdas"], seed=4)
     fo = o_samples.mean(axis=0)
     fg = r["samples"].mean(axis=0)
-    assert np.abs((fg - fo) / np.sqrt(2 * 0.25 / N)).max() < 4.5
+    joint_check((fg - fo) / np.sqrt(fg * (1 - fg) / N + fo * (1 - fo) / N), NU_NORMAL, "marginals vs oracle")
 
 
 def test_sample_genotypes_with_given_times_and_generate_genotypes(oracle):
@@ -75,4 +78,4 @@ def test_sample_genotypes_with_given_times_and_generate_genotypes(oracle):
     g2 = mc.generate_genotypes(T, c["poset"], lambda_s=2.0, seed=8)
     assert np.array_equal(g2["samples"], (T <= g2["sampling_time"][:, None]).astype(np.int32))
     z = (g2["sampling_time"].mean() - 0.5) / (0.5 / np.sqrt(N))
-    assert abs(z) < 4.5
+    joint_check(np.array([z]), NU_NORMAL, "T_s ~ Exp(lambda_s)")
