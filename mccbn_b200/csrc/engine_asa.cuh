@@ -458,6 +458,9 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
         std::fill(memo_swap.begin(), memo_swap.end(), 0.0);
         std::fill(memo_pres.begin(), memo_pres.end(), 0.0);
         rng_prop = pr.rng_after;  // discard the speculation beyond this step
+        // the accepted poset's own kernel serves every label-swap candidate of the following steps (move 3 relabels
+        // the events: same structure by topological position, same kernel) and a return to it after a detour
+        if (prefetch) pb.prefetch_kernel(M.poset, scheme, times_given);
         accepted_any = true;
         n_consumed = b + 1;
         steps_since_accept = 0;

@@ -2138,6 +2138,10 @@ int mccbn_MCEM(mccbn_ctx* c, const double* ilambda, const int* poset, const int*
       avg_llhood += llhood;
     }
   }
+  // The reference's "sum(w) == 0 -> uniform weights" rule (src/mcem.cpp:123-127) has nothing to act on here: every
+  // genotype with a non-zero weight was checked to be compatible with the poset above, so each of its draws has a
+  // positive weight P(Z)/q(Z), and the per-observation log-sum-exp of the E-step cannot underflow to zero.  (Zero-weight
+  // observations may be incompatible; they enter neither W nor T_colsum.)
   for (int j = 0; j < p; ++j) lambda_out[j] = avg_lambda[j] / (max_iter - record_iter);  // :206-207
   *llhood_out = (double)(avg_llhood / (max_iter - record_iter));
   MCCBN_CATCH

@@ -147,11 +147,19 @@ def test_dump_marginals_are_exponential():
 
 
 def test_shard_invariance():
-    """Philox counters use global observation indices: scoring a shard with obs_offset reproduces the rows of the
-    full run (up to fp32 summation order, which depends on the chunking chosen for N)."""
+    """Philox counters use global observation indices and the record partition depends on (L, GLOBAL N) only: scoring a
+    shard with obs_offset / N_global reproduces the rows of the full run BIT FOR BIT -- per-observation outputs do not
+    depend on how the observations are sharded (one record per observation here, and also with several records)."""
     c = _cfg(p=10, N=300, seed=8)
-    full = mc.importance_weight(c["obs"], 640, c["poset"], c["lambdas"], 0.05, seed=5)
-    part = mc.importance_weight(c["obs"][100:220], 640, c["poset"], c["lambdas"], 0.05, seed=5, obs_offset=100)
+    for L in (640, 5000):  # 1 record per observation; 4 records per observation (global N = 300 is small)
+        full = mc.importance_weight(c["obs"], L, c["poset"], c["lambdas"], 0.05, seed=5)
+        part = mc.importance_weight(c["obs"][100:220], L, c["poset"], c["lambdas"], 0.05, seed=5, obs_offset=100,
+                                    N_global=300)
+        assert np.array_equal(part["w"], full["w"][100:220])
+        assert np.array_equal(part["Tdiff"], full["Tdiff"][100:220])
+        assert np.array_equal(part["dist"], full["dist"][100:220])
+    # without N_global the shard chooses its own partition: same samples, fp32 summation order may differ
+    part = mc.importance_weight(c["obs"][100:220], 5000, c["poset"], c["lambdas"], 0.05, seed=5, obs_offset=100)
     np.testing.assert_allclose(part["w"], full["w"][100:220], rtol=1e-5)
     np.testing.assert_allclose(part["Tdiff"], full["Tdiff"][100:220], rtol=1e-4)
 
