@@ -290,7 +290,7 @@ def run_ours(args):
                    "parallelism": (f"observations sharded over {world} rank(s); per iteration one exchange of p+5 doubles, " +
                                    ("fused into the reduction/M-step kernels over NVLink peer memory"
                                     if args.exchange == "peer" else "ncclAllReduce")),
-                   "kernel": ({"forward": "estep_forward", "pool": "pool_generate + estep_pool"}.get(
+                   "kernel": ({"forward": "estep_forward", "pool": "pool_generate + estep_pool_mma"}.get(
                        sampling, "estep_conditional") + (" (NVRTC poset-specialised, default JIT policy)"
                                                          if jit_launches else " (generic)"))},
         "e2e": {"value": N * L_eff / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
@@ -411,13 +411,20 @@ def workload_roofline(name, cfg, p, N_local, L, sampling, ms, philox_peak, sm_hz
     elif sampling == "pool":
         PM = 8 if p <= 8 else (16 if p <= 16 else 32)
         pairs = float(N_local) * p * L  # (observation, pool entry) pairs, K = p L entries
-        ach = pairs * (PM + 3) / t     # weighted sums: PMAX + 3 FFMA per pair
-        out.update({"achieved": ach / 1e12, "peak": fp32_peak / 1e12, "unit": "TFFMA/s (fp32, PMAX + 3 per pair)",
-                    "frac": ach / fp32_peak, "pairs_per_s": pairs / t,
-                    "also": {"philox_frac": (pairs / t / philox_peak) if philox_peak else None,  # one word per pair (T_s)
-                             "mufu_frac": pairs / t / mufu_peak},
-                    "peak_source": "128 FFMA/clk/SM x SMs x SM clock; per pair the kernel also does a 5-step binary search "
-                                   "in shared memory, one popc and one 32-bit uniform + MUFU.LG2 for the sampling time"})
+        # per pair: one 32-bit Philox word + MUFU.LG2 (the pair's sampling time), a 6-step rank search in the entry's sorted
+        # times, one popc, one table look-up -- and PMAX + 3 weighted sums, which run as TF32 mma with split operands
+        # (estep_pool_mma_kernel).  No single pipe bounds it (ncu r2l: issue slots 74 %, shared-memory wavefronts 65 %); the
+        # line reports the same ceiling as the forward kernels, the multiplier pipe's share, and the others beside it.
+        ach = pairs / t  # Philox words/s: one per pair
+        mma_flops = pairs * PM * 2 * 3  # three TF32 products per (pair, event)
+        out.update({"achieved": ach / 1e9, "peak": philox_peak / 1e9 if philox_peak else None,
+                    "unit": "Gword/s (32-bit Philox output, one word per pair)",
+                    "frac": ach / philox_peak if philox_peak else None, "pairs_per_s": pairs / t,
+                    "also": {"mufu_frac": pairs / t / mufu_peak, "ffma_equivalent_frac": pairs * (PM + 3) / t / fp32_peak,
+                             "mma_tf32_TFLOPs": mma_flops / t / 1e12},
+                    "peak_source": "pure Philox4x32-10 generator micro-kernel measured live on this GPU; the kernel is bound by "
+                                   "the issue of its per-pair scalar work, not by one pipe: without any of the weighted-sum "
+                                   "work it takes 21.8 of its 25.8 ms (profiles/README.md r2n)"})
     else:
         nblk = ((24 * p + 23) // 32) // 4 + 1
         executed = executed_backward_samples(cfg, p, L) * (N_local / cfg["obs"].shape[0]) if sampling == "backward" \

@@ -365,10 +365,22 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
   // kernels are compiled ahead only while proposals are being rejected: at high temperature nearly every move is
   // accepted, the look-ahead is discarded each step and the compilations would be wasted host work
   unsigned steps_since_accept = 0;
+  unsigned gate = 3;
+  if (const char* e = std::getenv("MCCBN_ASA_PREFETCH_GATE")) gate = (unsigned)std::max(0, std::atoi(e));
+  static const bool trace = std::getenv("MCCBN_ASA_TRACE") != nullptr;  // dev: where the host time of a run goes
+  double t_gen = 0.0, t_score = 0.0, t_init = 0.0;
+  unsigned n_gen = 0;
+  auto clk = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [](std::chrono::steady_clock::time_point a) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+  };
   auto top_up = [&](unsigned want) {
     while (ahead.size() < want) {
+      const auto tg = clk();
       ahead.push_back(generate_proposal(pb, M, fraction_compatible, ctl_asa.compatible_fraction_factor, rng_prop, verbose));
-      if (prefetch && steps_since_accept >= 3 && ahead.back().valid)
+      t_gen += ms_since(tg);
+      ++n_gen;
+      if (prefetch && steps_since_accept >= gate && ahead.back().valid)
         pb.prefetch_kernel(ahead.back().cand.poset, scheme, times_given);
     }
   };
@@ -398,7 +410,9 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
         }
       }
       if (pr.same_as >= 0) continue;
+      const auto ti = clk();
       initialize_candidate(pb, pr.cand, lambda_s, ctl_em.max_lambda);  // :256-258
+      t_init += ms_since(ti);
       pr.score_slot = (int)to_score.size();
       to_score.push_back(&pr.cand);
       ids.push_back(iter + b);
@@ -419,7 +433,9 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
     };
     if (!to_score.empty()) {
       NvtxRange nvtx_score("ASA: score candidate batch");
+      const auto ts = clk();
       score_candidates(pb, to_score, ids, scheme, L, ctl_em, times_given, seed, lambda_s, 0, look_ahead);
+      t_score += ms_since(ts);
     } else {
       look_ahead();
     }
@@ -493,6 +509,9 @@ static double simulated_annealing(mccbn_problem& pb, Candidate& M, AsaControl& c
     if (accepted_any) ahead.clear();
     else ahead.erase(ahead.begin(), ahead.begin() + n_consumed);
   }
+  if (trace)
+    std::fprintf(stderr, "mccbn asa: %u proposals generated in %.1f ms (%.2f ms each), candidate initialisation %.1f ms, "
+                         "scoring (incl. look-ahead inside) %.1f ms\n", n_gen, t_gen, n_gen ? t_gen / n_gen : 0.0, t_init, t_score);
   // 4. final fit of the ML poset with doubled EM budget; neighborhood_dist falls back to its default 1 (:583-585)
   EmControl last = ctl_em;
   last.max_iter = ctl_em.max_iter * 2;

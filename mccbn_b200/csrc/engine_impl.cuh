@@ -238,6 +238,11 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
       a.rkey1 = make_key(seed, (uint32_t)iter, 9u).k1;
     }
     const dim3 grid(nb, chunks);
+    // weighted sums on the tensor cores (estep_pool_mma_kernel); MCCBN_POOL_MMA=0 keeps the FFMA kernel (A/B runs)
+    static const bool pool_mma = [] {
+      const char* e = std::getenv("MCCBN_POOL_MMA");
+      return !(e && std::strcmp(e, "0") == 0);
+    }();
 #define MCCBN_POOL(PMX)                                                                                         \
   do {                                                                                                          \
     const PosetProg pg = build_prog(flat[c], PMX, 4);                                                           \
@@ -245,7 +250,10 @@ void mccbn_problem::enqueue_iteration(int c, Scheme scheme, int L, unsigned neig
                                                                                     kgen.k1, eval_id[c],       \
                                                                                     models.ptr + c,            \
                                                                                     scales.ptr + c, pg);        \
-    if (times_given)                                                                                            \
+    if (pool_mma) {                                                                                             \
+      if (times_given) estep_pool_mma_kernel<PMX, true><<<grid, kPoolBlock, 0, s>>>(a, pg);                     \
+      else estep_pool_mma_kernel<PMX, false><<<grid, kPoolBlock, 0, s>>>(a, pg);                                \
+    } else if (times_given)                                                                                     \
       estep_pool_kernel<PMX, true><<<grid, kPoolBlock, 0, s>>>(a, pg);                                          \
     else                                                                                                        \
       estep_pool_kernel<PMX, false><<<grid, kPoolBlock, 0, s>>>(a, pg);                                         \

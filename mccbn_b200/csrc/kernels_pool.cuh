@@ -221,6 +221,225 @@ __global__ void __launch_bounds__(kPoolBlock) estep_pool_kernel(const PoolArgs a
   }
 }
 
+// ---- tensor-core variant of estep_pool_kernel -------------------------------------------------------------------
+// The weighted sums  S_ij = sum_k q_ik Z_kj  ARE a contraction: (observations x pool entries) weights against (pool
+// entries x events) waiting times.  In estep_pool_kernel they cost PMAX FFMA + PMAX/4 broadcast LDS.128 per
+// (observation, entry) pair -- 40 of the kernel's 112 instructions per pair.  Here a warp (32 observations, lane =
+// observation for everything that is NOT a contraction: sampling time, rank search, distance, weight, the three header
+// sums) hands the 32 x 8 weights of eight pool entries to `mma.sync.m16n8k8` (TF32 inputs, fp32 accumulation) against
+// the entries' 8 x PMAX waiting times.  fp32 accuracy is kept by splitting both operands into a TF32 head and the
+// fp32 remainder (q = qh + ql, Z = Zh + Zl: three products qh Zh + ql Zh + qh Zl; the dropped ql Zl term is 2^-22
+// relative).  The accumulator of observation row r lives in the lanes of its fragment row, so when a lane lowers its
+// running reference distance the scale factor travels to those lanes by shuffle (rare: at most p times per row).
+__device__ __forceinline__ uint32_t pool_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void pool_mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+#ifndef MCCBN_POOL_MMA_TERMS
+#define MCCBN_POOL_MMA_TERMS 3  // 3: qh Zh + ql Zh + qh Zl (fp32 accuracy); fewer only in profiling builds
+#endif
+constexpr int kPoolZStride = kPoolTile + 4;  // Z tile stored [event][entry], stride 68: B-fragment loads hit 32 banks
+constexpr int kPoolQStride = 12;             // weights staged [observation][8 entries], stride 12: A-fragment loads too
+
+template <int PMAX, bool TIMES_GIVEN>
+__global__ void __launch_bounds__(kPoolBlock, 4) estep_pool_mma_kernel(const PoolArgs a,
+                                                                       const __grid_constant__ PosetProg pg) {
+  static_assert(PMAX % 8 == 0 && (PMAX & (PMAX - 1)) == 0, "PMAX: power of two, multiple of the mma N = 8");
+  constexpr int NCB = PMAX / 8;  // column blocks of the accumulator
+  __shared__ __align__(16) float s_Tt[kPoolTile * PMAX];
+  __shared__ uint32_t s_Mt[kPoolTile * (PMAX + 1)];
+  __shared__ uint32_t s_Zh[PMAX * kPoolZStride], s_Zl[PMAX * kPoolZStride];
+  __shared__ __align__(16) uint32_t s_Q[kPoolBlock / 32][2][32 * kPoolQStride];
+  __shared__ float s_rtab[kRtabN];
+  const DevModel* __restrict__ mdl = a.model;
+  const int p = pg.p;
+  for (int t = threadIdx.x; t < kRtabN; t += kPoolBlock) s_rtab[t] = mdl->rtab[t];
+  const int flip = mdl->flip;
+  const uint32_t key1 = iter_key(a.key1, mdl);
+  const int ch = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane >> 2, t4 = lane & 3;  // fragment coordinates: groupID, thread-in-group
+  const int i = blockIdx.x * kPoolBlock + threadIdx.x;
+  const int i_warp = blockIdx.x * kPoolBlock + w * 32;  // observation of fragment row 0 of this warp
+  const bool live = i < a.N;
+  const uint32_t yt = live ? to_topo_bits<PMAX>(pg, a.obs_bits[i]) : 0u;
+  const float ts_given = (TIMES_GIVEN && live) ? (float)a.times[i] : 0.f;
+  const uint32_t gi = (uint32_t)(a.obs_offset + i);
+  const float cs = a.scale->cs;
+
+  float acc[2][NCB][4];  // accumulator fragments: [row block][column block][c0..c3]
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[rb][cb][e] = 0.f;
+  float aw = 0.f, aw2 = 0.f, awd = 0.f;
+  int dref = 1 << 20;
+
+  double* out = a.part + ((size_t)(live ? i : 0) * a.chunks + ch) * a.PS;
+  int fdref = 1 << 20;  // reference distance of what this lane's record holds; 1 << 20: nothing flushed yet
+  // fp32 partial sums -> the observations' fp64 records (same rule as estep_pool_kernel: at most kPoolFlush entries in fp32).
+  // The header sums belong to the lane, the S_ij of fragment row r to the lanes that hold that row.
+  auto flush = [&]() {
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = 16 * rb + g + 8 * h;
+        const int dref_r = __shfl_sync(0xffffffffu, dref, row), fdref_r = __shfl_sync(0xffffffffu, fdref, row);
+        const int i_r = i_warp + row;
+        if (i_r < a.N && dref_r != (1 << 20)) {
+          double* o = a.part + ((size_t)i_r * a.chunks + ch) * a.PS + kStatHdr;
+          const bool first = fdref_r == (1 << 20);
+          const double sc = (!first && fdref_r != dref_r) ? mdl->rtab_d[min(fdref_r - dref_r, kRtabN - 1)] : 1.0;
+#pragma unroll
+          for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = 8 * cb + 2 * t4 + e;
+              if (col < p) o[col] = first ? (double)acc[rb][cb][2 * h + e] : o[col] * sc + (double)acc[rb][cb][2 * h + e];
+            }
+        }
+      }
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+      for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[rb][cb][e] = 0.f;
+    if (live && dref != (1 << 20)) {
+      if (fdref == (1 << 20)) {
+        out[0] = (double)aw, out[1] = (double)aw2, out[2] = (double)awd;
+      } else {
+        const double sc = fdref != dref ? mdl->rtab_d[min(fdref - dref, kRtabN - 1)] : 1.0;  // dref only decreases
+        out[0] = out[0] * sc + (double)aw;
+        out[1] = out[1] * sc * sc + (double)aw2;
+        out[2] = out[2] * sc + (double)awd;
+      }
+      fdref = dref;
+    }
+    aw = aw2 = awd = 0.f;
+  };
+
+  uint32_t* Qh = s_Q[w][0];
+  uint32_t* Ql = s_Q[w][1];
+  const int k_begin = ch * a.chunk_len, k_end = min(a.K, k_begin + a.chunk_len);
+  for (int k0 = k_begin; k0 < k_end; k0 += kPoolTile) {
+    __syncthreads();
+    if (k0 > k_begin && ((k0 - k_begin) % kPoolFlush) == 0) flush();
+    const int nk = min(kPoolTile, k_end - k0);
+    for (int t = threadIdx.x; t < nk * PMAX / 4; t += kPoolBlock)  // coalesced float4 copy of the sorted times
+      reinterpret_cast<float4*>(s_Tt)[t] = reinterpret_cast<const float4*>(a.Tp + (size_t)k0 * PMAX)[t];
+    for (int t = threadIdx.x; t < kPoolTile * PMAX / 4; t += kPoolBlock) {  // Z tile: transposed, split into TF32 head + remainder
+      const int e = t / (PMAX / 4), cg = t % (PMAX / 4);
+      const float4 z = e < nk ? reinterpret_cast<const float4*>(a.Zp + (size_t)k0 * PMAX)[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const uint32_t hi = pool_tf32(zz[c4]);
+        s_Zh[(4 * cg + c4) * kPoolZStride + e] = hi;
+        s_Zl[(4 * cg + c4) * kPoolZStride + e] = __float_as_uint(zz[c4] - __uint_as_float(hi));
+      }
+    }
+    for (int t = threadIdx.x; t < nk * (PMAX + 1); t += kPoolBlock) s_Mt[t] = a.Mp[(size_t)k0 * (PMAX + 1) + t];
+    __syncthreads();
+    uint4 r = make_uint4(0, 0, 0, 0);
+    for (int kk = 0; kk < nk; kk += 8) {
+      // --- lane = observation: distances of the eight entries kk .. kk + 7
+      int dj[8], dej[8];
+      int dmin = dref;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float Ts = ts_given;
+        if (!TIMES_GIVEN) {
+          if ((j & 3) == 0) r = philox4x32_10((uint32_t)((k0 + kk + j) >> 2), gi, 0u, a.cw, a.key0, key1);
+          const uint32_t bits = (j & 3) == 0 ? r.x : ((j & 3) == 1 ? r.y : ((j & 3) == 2 ? r.z : r.w));
+          Ts = fast_lg2(u01_open0(bits)) * cs;
+        }
+        const float* Tk = s_Tt + (kk + j) * PMAX;
+        int rank = 0;
+#pragma unroll
+        for (int step = PMAX / 2; step >= 1; step >>= 1)
+          if (Tk[rank + step - 1] <= Ts) rank += step;
+        if (Tk[rank] <= Ts) rank += 1;
+        const uint32_t X = s_Mt[(kk + j) * (PMAX + 1) + rank];
+        const int d = __popc(X ^ yt);
+        dj[j] = d;
+        dej[j] = (kk + j < nk) ? (flip ? p - d : d) : (1 << 19);  // beyond the tile: the zero tail of the weight table
+        dmin = min(dmin, dej[j]);
+      }
+      // --- running reference distance of this observation; the scale of what has been accumulated so far
+      float myscale = 1.f;
+      if (dmin < dref) {
+        myscale = s_rtab[min(dref - dmin, kRtabN - 1)];
+        aw *= myscale;
+        aw2 *= myscale * myscale;
+        awd *= myscale;
+        dref = dmin;
+      }
+      uint32_t qh[8], ql[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float q = s_rtab[min(dej[j] - dref, kRtabN - 1)];
+        aw += q;
+        aw2 = fmaf(q, q, aw2);
+        awd = fmaf(q, (float)dj[j], awd);
+        qh[j] = pool_tf32(q);
+        ql[j] = __float_as_uint(q - __uint_as_float(qh[j]));
+      }
+      if (__ballot_sync(0xffffffffu, myscale != 1.f)) {  // some row moved its reference: rescale its accumulator row
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          const float s0 = __shfl_sync(0xffffffffu, myscale, 16 * rb + g), s1 = __shfl_sync(0xffffffffu, myscale, 16 * rb + g + 8);
+#pragma unroll
+          for (int cb = 0; cb < NCB; ++cb) {
+            acc[rb][cb][0] *= s0, acc[rb][cb][1] *= s0;
+            acc[rb][cb][2] *= s1, acc[rb][cb][3] *= s1;
+          }
+        }
+      }
+      // --- the 32 x 8 weights of this group -> A fragments (through the warp's staging rows)
+      __syncwarp();
+      *reinterpret_cast<uint4*>(Qh + lane * kPoolQStride) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+      *reinterpret_cast<uint4*>(Qh + lane * kPoolQStride + 4) = make_uint4(qh[4], qh[5], qh[6], qh[7]);
+      *reinterpret_cast<uint4*>(Ql + lane * kPoolQStride) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+      *reinterpret_cast<uint4*>(Ql + lane * kPoolQStride + 4) = make_uint4(ql[4], ql[5], ql[6], ql[7]);
+      __syncwarp();
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb) {
+        const int b0 = (16 * rb + g) * kPoolQStride + t4, b1 = b0 + 8 * kPoolQStride;
+        ah[rb][0] = Qh[b0], ah[rb][1] = Qh[b1], ah[rb][2] = Qh[b0 + 4], ah[rb][3] = Qh[b1 + 4];
+        al[rb][0] = Ql[b0], al[rb][1] = Ql[b1], al[rb][2] = Ql[b0 + 4], al[rb][3] = Ql[b1 + 4];
+      }
+#pragma unroll
+      for (int cb = 0; cb < NCB; ++cb) {
+        const int zb = (8 * cb + g) * kPoolZStride + kk + t4;
+        const uint32_t bh0 = s_Zh[zb], bh1 = s_Zh[zb + 4], bl0 = s_Zl[zb], bl1 = s_Zl[zb + 4];
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb) {
+          pool_mma_tf32(acc[rb][cb], ah[rb], bh0, bh1);
+          if (MCCBN_POOL_MMA_TERMS >= 2) pool_mma_tf32(acc[rb][cb], al[rb], bh0, bh1);
+          if (MCCBN_POOL_MMA_TERMS >= 3) pool_mma_tf32(acc[rb][cb], ah[rb], bl0, bl1);
+        }
+      }
+    }
+  }
+  flush();
+  if (live) {
+    out[3] = (double)(k_end - k_begin);
+    out[4] = mdl->log_base + (dref > 0 ? (double)dref * mdl->log_r : 0.0);
+    if (a.dref) a.dref[i] = dref;
+  }
+}
+
 // pool_resample = 1: the reference does not average over the whole pool but draws L indices with replacement from
 // Discrete(q) and averages d and Z over the drawn rows (src/mcem_hcbn.cpp:477-484, rdiscrete_std :44-54).  The K weights
 // of an observation are never stored: L iid indices from Discrete(q) are distributed like the cells that the ORDER

@@ -10,7 +10,7 @@ from bench import make_problem
 
 cfg, p, N, L, sampling, desc = make_problem("cfg4")
 steps = int(os.environ.get("ASA_STEPS", "100"))
-for batch in (1, 8, 0):
+for batch in [int(b) for b in os.environ.get("ASA_BATCHES", "1,8,0").split(",")]:
     if batch:
         os.environ["MCCBN_ASA_BATCH"] = str(batch)
     else:
@@ -20,8 +20,9 @@ for batch in (1, 8, 0):
     r = mc.adaptive_simulated_annealing(cfg["poset"], cfg["obs"], L=L, max_iter=100, update_step_size=20, max_iter_asa=steps,
                                         outdir=d, seed=10)
     dt = time.perf_counter() - t0
-    print(f"GPU ASA cfg4: batch={batch:2d}  {steps} steps in {dt:7.2f} s  -> {steps/dt:6.2f} candidate MCEM fits/s, llhood {r['llhood']:.2f}",
-          flush=True)
+    n_all, n_jit = mc.kernel_launches(reset=True), mc.jit_launches(reset=True)
+    print(f"GPU ASA cfg4: batch={batch:2d}  {steps} steps in {dt:7.2f} s  -> {steps/dt:6.2f} candidate MCEM fits/s, llhood {r['llhood']:.2f}"
+          f"  ({n_all} launches, {n_jit} specialised)", flush=True)
 if os.environ.get("PROBE_CPU", "1") == "1":
     import oracle as orc
     orc.build()
