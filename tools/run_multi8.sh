@@ -17,12 +17,14 @@ for c in cfg5 cfg5pool; do
   tr 8 bench.py --gpus 8 --steps 5 --warmup 3 --config $c > gpurun_out/${tag}_scale8_$c.json 2> gpurun_out/${tag}_scale8_$c.err
   echo "bench $c N=8 rc=$?"
 done
+tr 4 bench.py --gpus 4 --steps 5 --warmup 3 --config cfg5 > gpurun_out/${tag}_scale4_cfg5.json 2> gpurun_out/${tag}_scale4_cfg5.err
+echo "bench cfg5 N=4 rc=$?"
 timeout 200 python tools/team_probe.py cfg3 8 > gpurun_out/${tag}_team_probe_8gpu.log 2>&1; tail -5 gpurun_out/${tag}_team_probe_8gpu.log | cut -c1-400
 tr 8 tools/asa_probe_multi.py > gpurun_out/${tag}_asa_8gpu.log 2>&1; tail -3 gpurun_out/${tag}_asa_8gpu.log
 python - "$tag" <<'PY'
 import json, glob, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2g"
-for f in sorted(glob.glob("gpurun_out/%s_scale_*.json" % tag)):
+for f in sorted(glob.glob("gpurun_out/%s_scale*.json" % tag)):
     for l in open(f):
         if l.startswith("{"):
             d = json.loads(l)
