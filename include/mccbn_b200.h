@@ -342,6 +342,27 @@ int mccbn_jit_compile_conditional(const int* poset, int p, int times_given, int 
 int mccbn_poset_edit(const int* poset, int p, int op, int u, int v, int* poset_out, int* flags, char* err,
                      size_t errlen);
 
+/* ---- environment ------------------------------------------------------------------------------------------------
+ * None of these changes WHAT is computed (random streams, records, estimators); they select code paths for A/B runs,
+ * size caches or print diagnostics.
+ *   MCCBN_GPUS=G|all         in-process device team (see mccbn_set_gpus)
+ *   MCCBN_JIT=0|1            never / always use poset-specialised kernels (see mccbn_set_jit)
+ *   MCCBN_CACHE_DIR          on-disk cubin cache (default ~/.cache/mccbn_b200); MCCBN_JIT_MAX_LOADED: LRU bound on
+ *                            loaded modules (256)
+ *   MCCBN_DEVICE_CACHE_MB    per-device cache of the one-call entries' buffers (4096; 0 disables it)
+ *   MCCBN_ASA_BATCH=B        fixed speculative batch of the annealer (default: adaptive);  MCCBN_ASA_LOOKAHEAD,
+ *                            MCCBN_ASA_PREFETCH_GATE: look-ahead depth (12) and the number of consecutive rejections (3)
+ *                            after which look-ahead candidates' kernels are compiled in the background
+ *   MCCBN_PEER_TIMEOUT_S     give up waiting for a rank's statistic vector after this many seconds (30)
+ *   MCCBN_GRAPHS=0, MCCBN_FUSE_TAIL=0, MCCBN_FWD_DYNAMIC=0, MCCBN_POOL_MMA=0
+ *                            A/B switches: no CUDA graphs; unfused tail kernels; static item assignment in the forward
+ *                            kernel; FFMA instead of TF32-mma weighted sums in the pool kernel (fp32 rounding differs)
+ *   MCCBN_JIT_MINB, MCCBN_JIT_RESIDENT, MCCBN_JIT_COND_MINB, MCCBN_JIT_PHILOX_ILP, MCCBN_JIT_PTXAS_O, MCCBN_JIT_VERBOSE
+ *                            code-generation knobs of the specialised kernels (tuning runs)
+ *   MCCBN_TRACE_E2E, MCCBN_ASA_TRACE
+ *                            print host time per phase of the one-call path / of an annealing run to stderr
+ */
+
 /* ---- measurement helper ------------------------------------------------------------------------------------ */
 /* 32-bit random words per second of a pure Philox4x32-10 generator kernel on this GPU: the INT32 ceiling against
  * which bench.py reports the E-step kernels (the path is instruction-issue bound, not HBM/tensor bound). */
