@@ -181,10 +181,16 @@ __device__ __forceinline__ double warp_transpose_sum(double (&v)[32], const int 
 __device__ __forceinline__ int popc_word(uint32_t x) { return __popc(x); }
 __device__ __forceinline__ int popc_word(uint64_t x) { return __popcll(x); }
 
-template <typename real, typename Prog>
+// LEAN = 3: the poset has no node with more than three parents (the host checks; true for most candidate posets of an
+// annealing run): three unconditional loads (absent parents read the dummy row), one FMNMX3, and none of the per-node
+// in-degree tests.  LEAN = 0 is the general path (any in-degree).  (Six unconditional loads, LEAN = 6, were tried for
+// in-degree <= 6: 227 LDS per sample at PMAX = 32 and register spills -- slower than the general path, kept out.)
+template <typename real, typename Prog, int LEAN = 0>
 __device__ __forceinline__ real parents_max(const Prog& pg, const typename Prog::word_t multi_mask, const int k,
                                             const uint32_t tcol_s) {
   const uint2 o = pg.off[k];
+  if constexpr (LEAN == 3)
+    return max(max(lds_at<real>(tcol_s + o.x), lds_at<real>(tcol_s + o.y)), lds_at<real>(tcol_s + pg.xo[k].x));
   real m = max(lds_at<real>(tcol_s + o.x), lds_at<real>(tcol_s + o.y));
   if ((multi_mask >> k) & 1u) {
     const uint4 x = pg.xo[k];
@@ -214,7 +220,7 @@ __device__ __forceinline__ real parents_max(const Prog& pg, const typename Prog:
 // fp64 path (validation mode) -- absolute times and the reference's comparison T_k <= T_s, X_k at bit p - 1 - k too.
 // Random stream of a sample (fp32): field 0 = sampling time, field k + 1 = node k (field_u01); Philox block b is
 // generated right before the first field that touches it, and only if that field belongs to a real node.
-template <typename real, int PMAX, bool TIMES_GIVEN, typename Prog>
+template <typename real, int PMAX, bool TIMES_GIVEN, typename Prog, int LEAN = 0>
 __device__ __forceinline__ void sample_forward(const Prog& pg, const uint32_t tcol_s, const uint32_t zrow_s,
                                                const uint32_t l, const uint32_t gi, const uint32_t k0,
                                                const uint32_t k1, const uint32_t cw, const real ts_given,
@@ -247,7 +253,7 @@ __device__ __forceinline__ void sample_forward(const Prog& pg, const uint32_t tc
         }
       }
       const float e = fast_lg2(field_u01(W, k + 1, one));  // log2(u) <= 0;  Z = e * c,  c = -ln2/lambda
-      const float t = fmaf(e, scale(k), parents_max<real>(pg, multi_mask, k, tcol_s));  // T_k - T_s
+      const float t = fmaf(e, scale(k), parents_max<real, Prog, LEAN>(pg, multi_mask, k, tcol_s));  // T_k - T_s
       sts_at_f(tcol_s + k * kRow, t);
       zq[k & 3] = e;
       if ((k & 3) == 3) sts128_f(zrow_s + (uint32_t)(k - 3) * 4u, zq[0], zq[1], zq[2], zq[3]);
@@ -326,7 +332,7 @@ __host__ __device__ constexpr size_t fwd_smem_bytes(bool stages_t = true) {
 // The generic sampler interprets the poset program at run time (event times staged in shared memory).  A
 // poset-specialised sampler generated by jit.cuh has the same call signature with the poset unrolled into
 // straight-line code (event times in registers).
-template <typename real, int PMAX, bool TIMES_GIVEN>
+template <typename real, int PMAX, bool TIMES_GIVEN, int LEAN = 0>
 struct GenericSampler {
   static constexpr bool kStagesT = true;
   static constexpr bool kStagesE = true;  // e_k goes through the thread's shared-memory row; E is left untouched
@@ -337,7 +343,7 @@ struct GenericSampler {
                                              const ScaleSrc<real, PMAX> scale, typename Prog::word_t& X,
                                              real& Ts_out, real (&E)[PMAX]) const {
     (void)E;
-    sample_forward<real, PMAX, TIMES_GIVEN>(pg, tcol_s, zrow_s, l, gi, k0, k1, cw, ts_given, scale, X, Ts_out);
+    sample_forward<real, PMAX, TIMES_GIVEN, Prog, LEAN>(pg, tcol_s, zrow_s, l, gi, k0, k1, cw, ts_given, scale, X, Ts_out);
   }
 };
 
@@ -473,10 +479,10 @@ __device__ __forceinline__ void estep_forward_body(const FwdArgs& a, const Prog&
   }
 }
 
-template <typename real, int PMAX, bool TIMES_GIVEN>
+template <typename real, int PMAX, bool TIMES_GIVEN, int LEAN = 0>
 __global__ void __launch_bounds__(kFwdBlock, sizeof(real) == 4 ? (PMAX >= MCCBN_FWD_BIGP ? MCCBN_FWD_MINB_BIG : 6) : 1)
     estep_forward_kernel(const FwdArgs a, const __grid_constant__ PosetProg pg) {
-  estep_forward_body<real, PMAX, TIMES_GIVEN>(a, pg, GenericSampler<real, PMAX, TIMES_GIVEN>{});
+  estep_forward_body<real, PMAX, TIMES_GIVEN>(a, pg, GenericSampler<real, PMAX, TIMES_GIVEN, LEAN>{});
 }
 
 // 32 < p <= 64: the same body on 64-bit genotype words (PosetProgWide); two resident blocks per SM

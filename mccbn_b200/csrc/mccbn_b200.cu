@@ -354,11 +354,21 @@ struct mccbn_problem {
   template <typename real>
   void launch_forward(const FwdArgs& a, const FlatPoset& f, bool times_given, int grid, int c = 0) {
     cudaStream_t s = ctx->stream;
+    int max_indeg = 0;  // <= 3: the lean variant of the generic kernel (kernels_forward.cuh: parents_max)
+    for (int k = 0; k < f.p; ++k) max_indeg = std::max(max_indeg, (int)__builtin_popcountll(f.parent_pos[k]));
+    static const bool lean_ok = [] {  // MCCBN_FWD_LEAN=0: always the general path (A/B runs; same results)
+      const char* e = std::getenv("MCCBN_FWD_LEAN");
+      return !(e && std::strcmp(e, "0") == 0);
+    }();
 #define MCCBN_FWD(PM)                                                                                   \
   do {                                                                                                  \
     const PosetProg pg = build_prog(f, PM, (int)sizeof(real));                                          \
     constexpr size_t sm = fwd_smem_bytes<real, PM>();                                                   \
-    if (times_given) {                                                                                  \
+    constexpr int kLean3 = sizeof(real) == 4 ? 3 : 0;                                                   \
+    if (kLean3 && lean_ok && max_indeg <= 3 && !times_given) {                                          \
+      MCCBN_OPTIN_ONCE(sm, estep_forward_kernel<real, PM, false, kLean3>);                              \
+      estep_forward_kernel<real, PM, false, kLean3><<<grid, kFwdBlock, sm, s>>>(a, pg);                 \
+    } else if (times_given) {                                                                           \
       MCCBN_OPTIN_ONCE(sm, estep_forward_kernel<real, PM, true>);                  \
       estep_forward_kernel<real, PM, true><<<grid, kFwdBlock, sm, s>>>(a, pg);                          \
     } else {                                                                                            \
