@@ -361,6 +361,8 @@ int mccbn_poset_edit(const int* poset, int p, int op, int u, int v, int* poset_o
  *                            code-generation knobs of the specialised kernels (tuning runs)
  *   MCCBN_TRACE_E2E, MCCBN_ASA_TRACE
  *                            print host time per phase of the one-call path / of an annealing run to stderr
+ *   MCCBN_SEGV_TRACE         install a SIGSEGV handler that prints the faulting thread's native backtrace (dev aid)
+ *   MCCBN_FWD_LEAN=0         generic forward kernel: always the general in-degree path (A/B switch)
  */
 
 /* ---- measurement helper ------------------------------------------------------------------------------------ */

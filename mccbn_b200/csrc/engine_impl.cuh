@@ -447,7 +447,26 @@ static void ctx_init(mccbn_ctx* c, int device) {
   c->sm_count = prop.multiProcessorCount;
 }
 
+// dev aid (MCCBN_SEGV_TRACE=1): native backtrace of the faulting thread on SIGSEGV, then exit
+static void segv_trace_handler(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "mccbn: SIGSEGV, native backtrace of the faulting thread:\n";
+  if (write(2, msg, sizeof(msg) - 1) < 0) {}
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(128 + sig);
+}
+static void maybe_install_segv_trace() {
+  static const bool on = [] {
+    if (!std::getenv("MCCBN_SEGV_TRACE")) return false;
+    std::signal(SIGSEGV, segv_trace_handler);
+    return true;
+  }();
+  (void)on;
+}
+
 static mccbn_ctx* get_ctx(mccbn_ctx* c) {
+  maybe_install_segv_trace();
   if (c) {
     MCCBN_CUDA(cudaSetDevice(c->device));
     return c;

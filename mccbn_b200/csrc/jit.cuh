@@ -13,6 +13,8 @@
 // NVRTC (libnvrtc.so.12) and the loaded module are reached through dlopen / the CUDA runtime library-management API;
 // if NVRTC is unavailable or compilation fails the generic kernel is used (still the device path, never the CPU).
 #pragma once
+#include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <thread>
 #include <cuda_runtime.h>
@@ -36,6 +38,25 @@
 #include "kernels_cond.cuh"
 
 namespace mccbn {
+
+// Background compilations in flight, process-wide.  The default context is never destroyed, so its worker threads may
+// still be inside nvrtcCompileProgram when the process exits -- and libnvrtc's own static destructors would then run
+// under them (observed: SIGSEGV inside nvrtcCompileProgram at exit after a short annealing run).  An atexit handler that
+// runs BEFORE their teardown waits for the workers.
+static std::atomic<int> g_jit_bg_inflight{0};
+static void jit_wait_background_at_exit() {
+  for (int i = 0; i < 3000 && g_jit_bg_inflight.load(std::memory_order_acquire) > 0; ++i)
+    std::this_thread::sleep_for(std::chrono::milliseconds(10));  // a compilation takes ~0.3 s; give up after 30 s
+}
+// atexit handlers and static destructors run in reverse order of registration, and libnvrtc (LLVM) keeps creating
+// function-local statics during its first compilations -- each registers its destructor when it is first used.  The
+// wait must run before ALL of them, so it is registered again after libnvrtc is loaded and after each of the first 64
+// completed compilations (by then every lazily created object exists; the handler returns at once when nothing is in
+// flight).
+static void jit_register_exit_wait() {
+  static std::atomic<int> n{0};
+  if (n.fetch_add(1) < 65) std::atexit(jit_wait_background_at_exit);
+}
 
 struct NvrtcApi {
   typedef struct _nvrtcProgram* program_t;
@@ -75,6 +96,7 @@ struct NvrtcApi {
     GetErrorString = (decltype(GetErrorString))sym("nvrtcGetErrorString");
     if (!ok) lib = nullptr;
     else Version = (decltype(Version))dlsym(lib, "nvrtcVersion");
+    if (ok) jit_register_exit_wait();
     return ok;
   }
 };
@@ -305,6 +327,7 @@ static bool jit_compile(NvrtcApi& rtc, const std::string& src, JitCompiled& out)
     rtc.GetProgramLog(prog, &out.log[0]);
   }
   bool ok = rc == 0;
+  jit_register_exit_wait();  // after a compilation (successful or not): in front of whatever it created lazily
   if (ok) {
     size_t n = 0;
     ok = rtc.GetCUBINSize(prog, &n) == 0 && n > 0;
@@ -524,7 +547,11 @@ struct JitCache {
         pd.kname = kname;
         pd.forward = forward;
         pd.p = p;
+        g_jit_bg_inflight.fetch_add(1, std::memory_order_acq_rel);
         pd.fut = std::async(std::launch::async, [api, src, path] {
+          struct InFlight {
+            ~InFlight() { g_jit_bg_inflight.fetch_sub(1, std::memory_order_acq_rel); }
+          } in_flight;
           setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 10);  // this thread only (Linux: per-thread nice value)
           JitCompiled out;
           if (jit_compile(*api, src, out)) jit_disk_write(path, out.cubin);

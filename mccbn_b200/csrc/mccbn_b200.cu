@@ -11,6 +11,9 @@
 //   the host synchronises once per `update_step_size` iterations to apply the reference's batch-average /
 //   convergence rule on the trace rows.
 #include <algorithm>
+#include <csignal>
+#include <execinfo.h>
+#include <unistd.h>
 #include <array>
 #include <atomic>
 #include <condition_variable>

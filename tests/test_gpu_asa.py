@@ -117,3 +117,23 @@ def test_asa_matches_oracle_in_distribution(oracle, tmp_path, mode, n_seeds, kw)
         joint_check(z, 2 * n_seeds - 2, f"ASA {mode}")
     finally:
         os.environ.pop("MCCBN_ASA_BATCH", None)
+
+
+def test_short_annealing_run_exits_cleanly():
+    """A short run leaves background compilations of look-ahead kernels in flight when the process ends (the default
+    context is never destroyed): the library waits for them at exit, in front of libnvrtc's own teardown -- the process must
+    end with status 0, not with a SIGSEGV after it has printed its result."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, tempfile; sys.path.insert(0, %r)\n"
+        "import numpy as np, mccbn_b200 as mc\n"
+        "from mccbn_b200 import synth\n"
+        "c = synth.make_config(20, 10000, eps=0.05, seed=10)\n"
+        "r = mc.adaptive_simulated_annealing(c['poset'], c['obs'], L=1000, max_iter=100, update_step_size=20, max_iter_asa=8,\n"
+        "                                    outdir=tempfile.mkdtemp() + '/', seed=10)\n"
+        "print('llhood', r['llhood'])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, MCCBN_ASA_PREFETCH_GATE="0", MCCBN_CACHE_DIR=str(__import__("tempfile").mkdtemp()))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert "llhood" in r.stdout, r.stderr[-2000:]
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
